@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the PPO hot path (BASELINE.json metric: PPO env-steps/s and update samples/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c4]
+
+A "step" is one PPO update: rollout of n_steps x n_envs transitions on the GPU-resident synthetic 18-dim env
+(policy step + env + VecNormalize per env step, then GAE) followed by noptepochs x nminibatches train steps.
+`value` = env-steps/s = n_batch / time(update), the reference's own fps formula (ppo2/ppo2.hpp:337-341).
+Default workload = BASELINE.json configs[2] (C3): 4096 envs/GPU, MLP [64,64], n_steps 64 (262 144
+transitions per update per GPU), 32 minibatches, 10 epochs.  Multi-GPU is weak scaling: every rank owns 4096
+envs; per-minibatch gradients are allreduced with NCCL.
+
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on the same
+config — TensorFlow 1.14/Eigen are not installable, see DESIGN.md.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (n_envs per GPU, n_steps, h1, h2, nminibatches, noptepochs, description)
+    "c3": (4096, 64, 64, 64, 32, 10, "C3: synthetic 18-dim env, 4096 envs/GPU, MLP [64,64], 262144 transitions/update/GPU"),
+    "c1": (1, 2048, 4, 5, 32, 10, "C1 shape: 1 env, MLP [4,5], n_steps 2048 (reference CLI defaults)"),
+    "c4": (8192, 64, 256, 256, 32, 10, "C4 shard: 8192 envs/GPU, MLP [256,256], 524288 transitions/update/GPU"),
+    "c1x4096": (4096, 64, 4, 5, 32, 10, "reference net [4,5] on 4096 synthetic envs"),
+}
+LR, CLIPRANGE = 3.9e-4, 0.161
+METRIC, UNIT = "ppo_env_steps_per_sec", "env-steps/s"
+
+
+def train_flops_per_sample(O, A, h1, h2):
+    fwd = 2 * (O * h1 + h1 * h2) + h2 * A + h2
+    dx = 2 * (h1 * h2) + h2 * A + h2
+    return 2 * (2 * fwd + dx)
+
+
+def cpu_learner(workload, threads=0):
+    """The CPU restatement, structured like the reference (oracle/ppo_oracle.c oracle_learner_*)."""
+    import ctypes as C
+
+    import numpy as np
+
+    import oracle_lib as ol
+    n_envs, n_steps, h1, h2, nmb, epochs, _ = WORKLOADS[workload]
+    lib = ol.load(fast=True)
+    o = ol.Oracle(h1=h1, h2=h2, fast=True)
+    rng = np.random.default_rng(0)
+    params = (rng.standard_normal(o.Pq) * 0.1).astype(np.float32)
+    params[o.offset(12):o.offset(13)] = 0.0
+    return lib, o, params, (n_envs, n_steps, h1, h2, nmb, epochs)
+
+
+def time_cpu_update(workload, epochs_run, reps=1, threads=0):
+    """(seconds per full update extrapolated to all epochs, threads used, rollout s, per-epoch s)"""
+    import ctypes as C
+
+    import numpy as np
+
+    import oracle_lib as ol
+    lib, o, params, (n_envs, n_steps, h1, h2, nmb, epochs) = cpu_learner(workload, threads)
+    d = ol.LearnerDesc(ol.Dims(18, 18, h1, h2), ol.HParams(0.0007160293171182275, 0.5, 0.5, 0.9, 0.999, 1e-5), n_envs, n_steps, nmb,
+                       epochs_run, 0.99, 0.95, LR, CLIPRANGE, 1, 42, 0, threads)
+    L = lib.oracle_learner_create(C.byref(d), params)
+    used = lib.oracle_learner_threads(L)
+    losses = np.zeros(5, np.float32)
+    t_roll, t_train = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lib.oracle_learner_rollout(L)
+        t1 = time.perf_counter()
+        lib.oracle_learner_train(L, losses)
+        t2 = time.perf_counter()
+        t_roll.append(t1 - t0)
+        t_train.append((t2 - t1) / max(epochs_run, 1))
+    lib.oracle_learner_destroy(L)
+    r, e = min(t_roll), min(t_train)
+    return r + epochs * e, used, r, e
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    n_envs, n_steps, h1, h2, nmb, epochs, desc = WORKLOADS[args.workload]
+    n_batch = n_envs * n_steps
+    # size the per-step sample so that (steps + warmup) steps end within a few minutes
+    probe_total, threads, r, e = time_cpu_update(args.workload, 1)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    epochs_run = max(1, min(epochs, int((budget - r) / max(e, 1e-9))))
+    times = []
+    for i in range(args.steps + args.warmup):
+        total, threads, r, e = time_cpu_update(args.workload, epochs_run)
+        if i >= args.warmup:
+            times.append(total)
+    sec = statistics.mean(times) if times else probe_total
+    value = n_batch / sec
+    sample = (f"per step: full rollout ({n_steps} steps x {n_envs} envs) + {epochs_run} of {epochs} epochs of {nmb} minibatches, "
+              f"train time scaled to {epochs} epochs")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "n_envs": n_envs, "n_steps": n_steps, "hidden": [h1, h2], "nminibatches": nmb, "noptepochs": epochs,
+                   "note": "CPU restatement of ppo_cpp (TensorFlow 1.14 / Eigen not installable); runs on rank 0 only, n_envs of ONE GPU's shard"},
+        "update_samples_per_sec": n_batch * epochs / (epochs * e),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ppo_cpp_b200 import core
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_envs, n_steps, h1, h2, nmb, epochs, desc = WORKLOADS[args.workload]
+    n_batch_local = n_envs * n_steps
+    n_batch_global = n_batch_local * world
+
+    c = core.PPOCore(device=local, hidden1=h1, hidden2=h2, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=epochs,
+                     seed=1234, rank=rank, world_size=world, env_offset=rank * n_envs, n_envs_global=n_envs * world)
+    c.init_orthogonal(7)  # random-init weights of the named architecture, identical on every rank
+    if world > 1:
+        uid = [core.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        c.comm_init(uid[0], rank, world)
+    c.shuffle_seed(42)
+    c.synth_env_reset()
+    stream = torch.cuda.ExternalStream(c.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        c.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def one_update(ev0=None, ev1=None, evm=None):
+        if ev0 is not None:
+            ev0.record(stream)
+        c.rollout_synthetic()
+        if evm is not None:
+            evm.record(stream)
+        c.train_update(LR, CLIPRANGE, want_losses=False)
+        if ev1 is not None:
+            ev1.record(stream)
+
+    for _ in range(max(args.warmup, 3)):
+        one_update()
+    barrier()
+    c.counters(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for e0, e1, em in evs:
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between timed steps, outside the timed interval
+        one_update(e0, e1, em)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    ctr = c.counters()
+    ms_total = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
+    ms_train = sum(em.elapsed_time(e1) for _, e1, em in evs)
+    t = torch.tensor([ms_total, ms_train], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_train = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = n_batch_global / (ms_per_step * 1e-3)
+    upd_sps = n_batch_global * epochs / (ms_train / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel (loss fwd + bwd), timed alone with CUDA events on the core's stream
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    k_ms = c.profile_kernel("train_fwdbwd", 64)
+    per_rank_B = n_batch_global // nmb // world
+    flops = per_rank_B * train_flops_per_sample(18, 18, h1, h2)
+    bytes_alg = per_rank_B * 160
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ach_tf = flops / (k_ms * 1e-3) / 1e12
+    roofline = {"kernel": "train_tile_kernel (PPO loss fwd + hand-derived bwd, one minibatch)", "bound": "tensor", "achieved": ach_tf,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "pipe": "fp32 FFMA on CUDA cores (no tensor-core path yet)", "fp32_ffma_peak_tflops_nominal": 74.4,
+                "frac_of_fp32_ffma": ach_tf / 74.4, "kernel_ms": k_ms, "flops_per_launch": flops,
+                "hbm_achieved_gbs": bytes_alg / (k_ms * 1e-3) / 1e9, "hbm_frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak}
+    kernels = {}
+    for name in ("policy_step", "norm_moments", "norm_apply", "gae", "grad_reduce", "adam"):
+        try:
+            kernels[name + "_ms"] = c.profile_kernel(name, 32)
+        except Exception as ex:  # noqa: BLE001
+            kernels[name + "_ms"] = str(ex)
+
+    # ---- end to end through the C ABI with HOST buffers (Runner::run protocol against a host env)
+    e2e = None
+    if args.e2e:
+        rng = np.random.default_rng(rank)
+        pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
+        raw_obs, raw_rew, raw_done, act = pin((n_steps, n_envs, 18)), pin((n_steps, n_envs)), pin((n_steps, n_envs)), pin((n_envs, 18))
+        raw_obs[:] = rng.standard_normal(raw_obs.shape)
+        raw_rew[:] = rng.standard_normal(raw_rew.shape)
+        raw_done[:] = rng.random(raw_done.shape) < 1 / 334
+        losses = np.zeros(5, np.float32)
+
+        def host_update():
+            for t_ in range(n_steps):
+                c.runner_act(t_, act)                                    # D2H: actions for the host env
+                c.runner_observe(t_, raw_obs[t_], raw_rew[t_], raw_done[t_])  # H2D: what the host env returned
+            c.runner_finish()
+            return c.train_update(LR, CLIPRANGE, want_losses=True)      # D2H: the update's mean losses
+
+        c.runner_reset(raw_obs[0])
+        host_update()
+        barrier()
+        c.counters(reset=True)
+        k_e2e = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            losses = host_update()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ce = c.counters()
+        e2e = {"value": n_batch_global * k_e2e / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": ce["h2d_bytes"] // k_e2e,
+               "d2h_bytes_per_step": ce["d2h_bytes"] // k_e2e, "steps": k_e2e, "ms_per_step": float(tt[0]) / k_e2e * 1e3,
+               "path": "ppo_runner_act/observe/finish + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
+               "final_losses": [float(x) for x in losses]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        total, threads, r, e = time_cpu_update(args.workload, 2)
+        cpu_baseline = {"value": n_batch_local / total, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"full rollout ({n_steps} steps x {n_envs} envs, {r:.2f} s) + 2 of {epochs} epochs ({e:.2f} s/epoch), "
+                                  f"train time scaled to {epochs} epochs", "update_samples_per_sec": n_batch_local / e}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_envs_per_gpu": n_envs, "n_steps": n_steps, "hidden": [h1, h2], "nminibatches": nmb,
+                       "noptepochs": epochs, "global_batch": n_batch_global, "minibatch": n_batch_global // nmb, "parallelism": f"dp{world}",
+                       "l2": "256 MiB memset between timed steps (L2 flush), outside the per-step event pairs",
+                       "weights": "orthogonal random init (no graph file exists for this size)"},
+            "update_samples_per_sec": upd_sps, "train_ms_per_step": ms_train / args.steps, "wall_ms_per_step": t_wall / args.steps * 1e3,
+            "gpu_launches": int(ctr["kernel_launches"]), "clocks": clocks, "roofline": roofline, "kernel_ms": kernels,
+            "cpu_baseline": cpu_baseline, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

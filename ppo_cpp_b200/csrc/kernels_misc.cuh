@@ -1,0 +1,511 @@
+// HBM-bound kernels of the path: synthetic env, VecNormalize, GAE, advantage statistics,
+// gradient reduction, global-norm clip + Adam, layout conversion.
+#pragma once
+#include "device_common.cuh"
+
+namespace ppo {
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic GPU-resident env: s' = 0.9 s + 0.1 clamp(a,-1,1) + 0.01 xi, reward = s'[0]-s[0],
+// 334-step episodes with per-env phase offset, reset to 0.1*U(-1,1).  One thread per env.
+struct SynthEnv {
+    float* state;      // [n][D]
+    uint32_t* t_env;   // [n]
+    uint32_t* resets;  // [n]
+    uint64_t seed;
+    uint32_t env_id0;
+    int n, D;
+};
+
+__device__ __forceinline__ void synth_reset_state(const SynthEnv& e, int i, float* s /*[D] out*/) {
+    const uint2 key = make_uint2((uint32_t)e.seed, (uint32_t)(e.seed >> 32));
+    const uint32_t gid = e.env_id0 + (uint32_t)i, rc = e.resets[i];
+    for (int blk = 0; blk * 4 < e.D; ++blk) {
+        const uint4 w = philox4x32_10(make_uint4(gid, rc, (uint32_t)blk, PPO_TAG_ENVRESET), key);
+        const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (blk * 4 + k < e.D) s[blk * 4 + k] = __fmul_rn(0.1f, __fsub_rn(__fmul_rn(2.0f, u32_to_unit(wv[k])), 1.0f));
+    }
+    e.resets[i] = rc + 1;
+}
+
+__global__ void synth_env_reset_kernel(SynthEnv e, float* __restrict__ obs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    e.resets[i] = 0;
+    e.t_env[i] = (e.env_id0 + (uint32_t)i) % 334u;
+    float s[32];
+    synth_reset_state(e, i, s);
+    for (int k = 0; k < e.D; ++k) {
+        e.state[(size_t)i * e.D + k] = s[k];
+        obs[(size_t)i * e.D + k] = s[k];
+    }
+}
+
+__global__ void synth_env_step_kernel(SynthEnv e, const float* __restrict__ actions, float* __restrict__ obs,
+                                      float* __restrict__ rew, float* __restrict__ done) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    float s[32];
+    const uint32_t t = e.t_env[i];
+    float s0 = 0.f;
+    for (int blk = 0; blk * 4 < e.D; ++blk) {
+        float xi[4];
+        normal4(e.seed, e.env_id0 + (uint32_t)i, t, (uint32_t)blk, PPO_TAG_ENVNOISE, xi);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = blk * 4 + q;
+            if (k < e.D) {
+                const float sk = e.state[(size_t)i * e.D + k];
+                if (k == 0) s0 = sk;
+                float a = actions[(size_t)i * e.D + k];
+                a = a < -1.f ? -1.f : (a > 1.f ? 1.f : a);
+                s[k] = __fadd_rn(__fadd_rn(__fmul_rn(0.9f, sk), __fmul_rn(0.1f, a)), __fmul_rn(0.01f, xi[q]));
+            }
+        }
+    }
+    rew[i] = __fsub_rn(s[0], s0);
+    e.t_env[i] = t + 1;
+    if ((t + 1) % 334u == 0u) {
+        done[i] = 1.f;
+        synth_reset_state(e, i, s);
+    } else {
+        done[i] = 0.f;
+    }
+    for (int k = 0; k < e.D; ++k) {
+        e.state[(size_t)i * e.D + k] = s[k];
+        obs[(size_t)i * e.D + k] = s[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// VecNormalize (env/env_normalize.hpp:64-116, common/running_statistics.hpp:26-104).
+// Running statistics live on the device: mean/var fp32 [D], count double — as in the reference.
+struct NormStats {
+    float* obs_mean;   // [D]
+    float* obs_var;    // [D]
+    double* obs_count; // [1]
+    float* ret_mean;   // [1]
+    float* ret_var;    // [1]
+    double* ret_count; // [1]
+};
+
+// Chan merge exactly as RunningStatistics::update_from_moments (running_statistics.hpp:88-104): doubles are
+// converted to the fp32 matrix scalar one at a time, left to right.
+__device__ __forceinline__ void chan_merge(float& mean, float& var, double count, float bmean, float bvar, double bcount) {
+    const double total = count + bcount;
+    const float delta = __fsub_rn(bmean, mean);
+    const float new_mean = __fadd_rn(mean, __fdiv_rn(__fmul_rn(delta, (float)bcount), (float)total));
+    const float m_a = __fmul_rn(var, (float)count);
+    const float m_b = __fmul_rn(bvar, (float)bcount);
+    const float cross = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(delta, delta), (float)count), (float)bcount), (float)total);
+    const float m_2 = __fadd_rn(__fadd_rn(m_a, m_b), cross);
+    mean = new_mean;
+    var = __fdiv_rn(m_2, (float)total);
+}
+
+// Pass A: ret = ret*gamma + rew; per-column (sum, sum of squares) in double for the D obs columns and the
+// return column.  Thread i walks elements i, i+S, ... with S a multiple of D so its column never changes
+// (coalesced, all lanes busy).  Per-CTA partials -> moments_partial[cta][2*(D+1)]; the last CTA to finish sums
+// them in fixed order into moments[2*(D+1)+1] (last entry = row count) and, when fuse_merge, performs the
+// Chan merge into the running statistics (single GPU).  Multi-GPU: allreduce `moments`, then norm_merge_kernel.
+struct MomentsArgs {
+    const float* raw_obs;  // [n][D]
+    const float* raw_rew;  // [n] or NULL (reset: observations only)
+    float* ret;            // [n] in/out
+    int n, D;
+    float gamma;
+    double* partial;       // [grid][2*(D+1)]
+    double* moments;       // [2*(D+1)+1]
+    unsigned int* ticket;
+    NormStats st;
+    int fuse_merge, update_obs, update_ret;
+};
+
+__device__ __forceinline__ void norm_merge(const MomentsArgs& a, const double* mom, int tid, int nthreads) {
+    const int D = a.D;
+    const double rows = mom[2 * (D + 1)];
+    for (int c = tid; c <= D; c += nthreads) {
+        const bool is_ret = (c == D);
+        if (is_ret ? !a.update_ret : !a.update_obs) continue;
+        // colwise().mean() and sum((x-mean)^2)/rows of the reference, evaluated in double from sums taken
+        // around a pivot (the running mean before this update; identical on every rank) and rounded once
+        const double pivot = is_ret ? 0.0 : (double)a.st.obs_mean[c];
+        const double m1 = mom[c] / rows;
+        const double mean_d = pivot + m1;
+        double var_d = mom[D + 1 + c] / rows - m1 * m1;
+        if (var_d < 0.0) var_d = 0.0;
+        const float bmean = (float)mean_d, bvar = (float)var_d;
+        if (is_ret) {
+            float m = *a.st.ret_mean, v = *a.st.ret_var;
+            chan_merge(m, v, *a.st.ret_count, bmean, bvar, rows);
+            *a.st.ret_mean = m; *a.st.ret_var = v;
+        } else {
+            float m = a.st.obs_mean[c], v = a.st.obs_var[c];
+            chan_merge(m, v, *a.st.obs_count, bmean, bvar, rows);
+            a.st.obs_mean[c] = m; a.st.obs_var[c] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (a.update_obs) *a.st.obs_count = rows + *a.st.obs_count;
+        if (a.update_ret) *a.st.ret_count = rows + *a.st.ret_count;
+    }
+}
+
+__global__ void norm_moments_kernel(const MomentsArgs a) {
+    extern __shared__ double sm[];  // [blockDim][2] then [2*(D+1)]
+    const int D = a.D, tid = threadIdx.x, nth = blockDim.x;
+    const size_t S = (size_t)gridDim.x * nth;  // multiple of D by construction
+    const size_t total = (size_t)a.n * D;
+    double s = 0.0, q = 0.0;
+    // sums are taken around a per-column pivot (the current running mean) to keep the sum of squares well
+    // conditioned; norm_merge adds the pivot back
+    const int col = (int)(((size_t)blockIdx.x * nth + tid) % D);
+    const float pivot = a.st.obs_mean[col];
+    for (size_t e = (size_t)blockIdx.x * nth + tid; e < total; e += S) {
+        const double x = (double)a.raw_obs[e] - (double)pivot;
+        s += x;
+        q += x * x;
+    }
+    sm[tid * 2] = s;
+    sm[tid * 2 + 1] = q;
+    // return column
+    double rs = 0.0, rq = 0.0;
+    if (a.raw_rew) {
+        for (size_t i = (size_t)blockIdx.x * nth + tid; i < (size_t)a.n; i += S) {
+            const float r = __fadd_rn(__fmul_rn(a.ret[i], a.gamma), a.raw_rew[i]);  // env_normalize.hpp:71
+            a.ret[i] = r;
+            rs += (double)r;
+            rq += (double)r * (double)r;
+        }
+    }
+    rs = warp_sum(rs);
+    rq = warp_sum(rq);
+    double* colsum = sm + 2 * nth;            // [2*(D+1)]
+    double* wred = colsum + 2 * (D + 1);      // [2*32]
+    if ((tid & 31) == 0) { wred[(tid >> 5) * 2] = rs; wred[(tid >> 5) * 2 + 1] = rq; }
+    __syncthreads();
+    if (tid < D) {  // threads with the same (tid % D) hold the same column
+        double cs = 0.0, cq = 0.0;
+        for (int j = tid; j < nth; j += D) { cs += sm[j * 2]; cq += sm[j * 2 + 1]; }
+        colsum[tid] = cs;
+        colsum[D + 1 + tid] = cq;
+    } else if (tid == D) {
+        double cs = 0.0, cq = 0.0;
+        for (int w = 0; w < (nth + 31) / 32; ++w) { cs += wred[w * 2]; cq += wred[w * 2 + 1]; }
+        colsum[D] = cs;
+        colsum[2 * D + 1] = cq;
+    }
+    __syncthreads();
+    double* mine = a.partial + (size_t)blockIdx.x * 2 * (D + 1);
+    for (int c = tid; c < 2 * (D + 1); c += nth) mine[c] = colsum[c];
+    __threadfence();
+    __shared__ bool last;
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int c = tid; c < 2 * (D + 1); c += nth) {
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += a.partial[(size_t)b * 2 * (D + 1) + c];
+        colsum[c] = t;
+    }
+    __syncthreads();
+    for (int c = tid; c < D; c += nth) {
+        a.moments[c] = colsum[c];
+        a.moments[D + 1 + c] = colsum[D + 1 + c];
+    }
+    if (tid == 0) {
+        a.moments[D] = colsum[D];
+        a.moments[2 * D + 1] = colsum[2 * D + 1];
+        a.moments[2 * (D + 1)] = (double)a.n;
+        *a.ticket = 0u;
+    }
+    __syncthreads();
+    __threadfence();
+    if (a.fuse_merge) norm_merge(a, a.moments, tid, nth);
+}
+
+__global__ void norm_merge_kernel(const MomentsArgs a) { norm_merge(a, a.moments, threadIdx.x, blockDim.x); }
+
+// Pass B: normalise + clip observations and rewards, reset ret on done, publish current obs/dones and store
+// this step's rewards (env_normalize.hpp:74-91, matrix_clamp.hpp:32-35, runner.hpp:116-129).
+struct ApplyArgs {
+    const float* raw_obs;  // [n][D]
+    const float* raw_rew;  // [n] or NULL (reset)
+    const float* done;     // [n] or NULL
+    float* ret;            // [n]
+    int n, D;
+    NormStats st;
+    int norm_obs, norm_reward;
+    float clip_obs, clip_rew, eps;
+    float* obs_out;      // [n][D] normalised observation (Runner::obs)
+    float* rew_out;      // [n] normalised reward or NULL
+    float* dones_out;    // [n] or NULL (Runner::dones)
+    float* rew_store;    // rollout true_rewards[t] or NULL
+    float* urew_store;   // rollout unnormalized_rewards[t] or NULL
+    uint32_t* step_ctr;  // incremented once per env step (Philox step counter) or NULL
+};
+
+__global__ void norm_apply_kernel(const ApplyArgs a) {
+    const size_t total = (size_t)a.n * a.D;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int c = (int)(e % a.D);
+        float x = a.raw_obs[e];
+        if (a.norm_obs) {
+            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.st.obs_var[c], a.eps)));
+            x = __fmul_rn(__fsub_rn(x, a.st.obs_mean[c]), inv);
+            x = fminf(fmaxf(x, -a.clip_obs), a.clip_obs);  // cwiseMax(lo).cwiseMin(hi)
+        }
+        a.obs_out[e] = x;
+    }
+    if (a.raw_rew) {
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(*a.st.ret_var, a.eps)));
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.n; i += stride) {
+            const float raw = a.raw_rew[i];
+            float r = raw;
+            if (a.norm_reward) {
+                r = __fmul_rn(raw, inv);  // no mean subtraction (env_normalize.hpp:80)
+                r = fminf(fmaxf(r, -a.clip_rew), a.clip_rew);
+            }
+            const float dn = a.done[i];
+            a.ret[i] = __fmul_rn(a.ret[i], __fsub_rn(1.0f, dn));  // env_normalize.hpp:88
+            if (a.rew_out) a.rew_out[i] = r;
+            if (a.dones_out) a.dones_out[i] = dn;
+            if (a.rew_store) a.rew_store[i] = r;
+            if (a.urew_store) a.urew_store[i] = raw;
+        }
+    }
+    if (a.step_ctr && blockIdx.x == 0 && threadIdx.x == 0) *a.step_ctr += 1u;
+}
+
+__global__ void clamp_kernel(const float* __restrict__ x, size_t n, float lo, float hi, float* __restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = fminf(fmaxf(x[i], lo), hi);
+}
+
+__global__ void bump_counter_kernel(uint32_t* c) { *c += 1u; }
+
+// ------------------------------------------------------------------------------------------------
+// GAE(lambda) reverse scan (Runner::set_returns, runner.hpp:159-191) over time-major [T][N] buffers.
+// One thread per (env, chunk of `chunk` steps).  A chunk that does not end at T-1 first runs `warm` extra
+// steps ahead of it starting from lastgaelam = 0: the recurrence contracts by gamma*lam per step, so after
+// `warm` steps the carried value equals the sequential one to below fp32 resolution (0.9405^512 ~ 2e-14)
+// while every arithmetic operation stays the reference's (bit-identical results in practice).
+__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ dones,
+                           const float* __restrict__ last_val, const float* __restrict__ last_done, int T, int N,
+                           float gamma, float lam, int chunk, int warm, float* __restrict__ adv_out,
+                           float* __restrict__ ret_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (e >= N) return;
+    const int t_lo = c * chunk;
+    const int t_hi = min(T, t_lo + chunk) - 1;  // inclusive
+    const int t_start = min(T - 1, t_hi + warm);
+    const float gl = __fmul_rn(gamma, lam);
+    float last = 0.f;
+    float nextv = (t_start == T - 1) ? last_val[e] : val[(size_t)(t_start + 1) * N + e];
+    float nextnt = 1.0f - ((t_start == T - 1) ? last_done[e] : dones[(size_t)(t_start + 1) * N + e]);
+#pragma unroll 4
+    for (int t = t_start; t >= t_lo; --t) {
+        const size_t idx = (size_t)t * N + e;
+        const float v = val[idx];
+        const float delta = __fsub_rn(__fadd_rn(rew[idx], __fmul_rn(gamma, __fmul_rn(nextv, nextnt))), v);
+        last = __fadd_rn(delta, __fmul_rn(gl, __fmul_rn(nextnt, last)));
+        if (t <= t_hi) {
+            if (adv_out) adv_out[idx] = last;
+            ret_out[idx] = __fadd_rn(last, v);
+        }
+        nextv = v;
+        nextnt = 1.0f - dones[idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Update-phase helpers.
+// perm (semantic flat rows, row = env*T + t of the GLOBAL batch) -> gather list of physical rows:
+// Eigen `perm * buf` writes out[perm[i]] = in[i] (ppo2.hpp:291-296), so minibatch slot s reads row i with perm[i]==s.
+// physical row of semantic row i: env_g = i / T, t = i % T, rank r = env_g / Nl, el = env_g % Nl -> r*T*Nl + t*Nl + el
+__global__ void build_gather_kernel(const int* __restrict__ perm, int n_batch, int T, int Nl, int* __restrict__ gather) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_batch) return;
+    const int env_g = i / T, t = i - env_g * T;
+    const int r = env_g / Nl, el = env_g - r * Nl;
+    gather[perm[i]] = r * T * Nl + t * Nl + el;
+}
+
+// per-minibatch advantage statistics (ppo2.hpp:401-405): one CTA per minibatch.
+// mean = sum(ret-val)/B ; var = sum((adv-mean)^2)/B ; denom = float(sqrt(var) + 1e-8)
+__global__ void advnorm_stats_kernel(const float* __restrict__ ret, const float* __restrict__ val,
+                                     const int* __restrict__ gather, int B, float2* __restrict__ stats) {
+    __shared__ double red[32];
+    __shared__ float s_mean;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    const int* g = gather ? gather + (size_t)k * B : nullptr;
+    double s = 0.0;
+    for (int i = tid; i < B; i += blockDim.x) {
+        const int row = g ? g[i] : (k * B + i);
+        s += (double)__fsub_rn(ret[row], val[row]);
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += red[w];
+        s_mean = (float)(t / (double)B);
+    }
+    __syncthreads();
+    const float mean = s_mean;
+    double q = 0.0;
+    for (int i = tid; i < B; i += blockDim.x) {
+        const int row = g ? g[i] : (k * B + i);
+        const float d = __fsub_rn(__fsub_rn(ret[row], val[row]), mean);
+        q += (double)__fmul_rn(d, d);
+    }
+    q = warp_sum(q);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += red[w];
+        const float var = (float)(t / (double)B);
+        const float denom = (float)((double)__fsqrt_rn(var) + 1e-8);
+        stats[k] = make_float2(mean, denom);
+    }
+}
+
+__global__ void advnorm_apply_kernel(const float* __restrict__ ret, const float* __restrict__ val, int n,
+                                     const float2* __restrict__ stats, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 st = *stats;
+    out[i] = __fdiv_rn(__fsub_rn(__fsub_rn(ret[i], val[i]), st.x), st.y);
+}
+
+// sum the per-CTA partial slabs column-wise (fixed order, double accumulation) -> grad[PS];
+// also per-block sum of squares of the first P columns (for the global norm when no allreduce follows).
+__global__ void grad_reduce_kernel(const float* __restrict__ partial, int G, int PS, int P, float* __restrict__ grad,
+                                   double* __restrict__ sq_partial) {
+    __shared__ double red[32];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double t = 0.0;
+    if (c < PS) {
+        for (int g = 0; g < G; ++g) t += (double)partial[(size_t)g * PS + c];
+        grad[c] = (float)t;
+    }
+    const float gf = (c < P) ? (float)t : 0.f;
+    double q = warp_sum((double)gf * (double)gf);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) s += red[w];
+        sq_partial[blockIdx.x] = s;
+    }
+}
+
+__global__ void sqnorm_kernel(const float* __restrict__ grad, int P, double* __restrict__ sq_partial) {
+    __shared__ double red[32];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const float gf = (c < P) ? grad[c] : 0.f;
+    double q = warp_sum((double)gf * (double)gf);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) s += red[w];
+        sq_partial[blockIdx.x] = s;
+    }
+}
+
+// clip_by_global_norm (GRAPH:24102-25392) + ApplyAdam for all 13 tensors flat + beta-power update
+// (GRAPH:25426-31383; TF 1.14 ApplyAdam: epsilon outside the sqrt, not bias-corrected).
+struct AdamArgs {
+    float* params;
+    float* m;
+    float* v;
+    const float* grad;         // [PS] summed over CTAs (and ranks); columns P.. hold the loss sums
+    const double* sq_partial;  // [nblk]
+    int nblk, P;
+    float lr, beta1, beta2, eps, clip_norm;
+    const float* bpow_in;  // [2] beta1_power, beta2_power
+    float* bpow_out;       // [2]
+    float invB, inv_world;
+    float* loss_row;       // [5] this step's pg, vf, entropy, approxkl, clipfrac
+    float* gnorm_out;      // [1]
+};
+
+__global__ void adam_kernel(const AdamArgs a) {
+    __shared__ float s_scale;
+    if (threadIdx.x == 0) {
+        double ss = 0.0;
+        for (int b = 0; b < a.nblk; ++b) ss += a.sq_partial[b];
+        const float gnorm = (float)sqrt(ss);  // sqrt(2 * sum L2Loss(g_i))
+        const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
+        float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
+        if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);  // GRAPH:24493-24543
+        s_scale = scale;
+        if (blockIdx.x == 0) {
+            *a.gnorm_out = gnorm;
+            const float* L = a.grad + a.P;
+            a.loss_row[0] = L[L_PG] * a.invB;
+            a.loss_row[1] = 0.5f * (L[L_VF] * a.invB);
+            a.loss_row[2] = L[L_ENT] * a.inv_world;
+            a.loss_row[3] = 0.5f * (L[L_KL] * a.invB);
+            a.loss_row[4] = L[L_CLIP] * a.invB;
+            a.bpow_out[0] = __fmul_rn(a.bpow_in[0], a.beta1);
+            a.bpow_out[1] = __fmul_rn(a.bpow_in[1], a.beta2);
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const float b1p = a.bpow_in[0], b2p = a.bpow_in[1];
+    const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+    const float g = __fmul_rn(a.grad[i], s_scale);
+    float m = a.m[i], v = a.v[i];
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+    a.m[i] = m;
+    a.v[i] = v;
+    a.params[i] = __fsub_rn(a.params[i], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+}
+
+// mean over the rows of the per-step loss table (colwise().mean(), ppo2.hpp:335)
+__global__ void loss_mean_kernel(const float* __restrict__ rows, int nrows, float* __restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= 5) return;
+    float s = 0.f;
+    for (int r = 0; r < nrows; ++r) s += rows[r * 5 + c];
+    out[c] = s / (float)nrows;
+}
+
+// physical (slab, time-major) <-> reference flat layout (row = env*T + t) conversion for export/import
+__global__ void export_flat_kernel(const float* __restrict__ phys, int T, int N, int W, float* __restrict__ flat) {
+    const size_t total = (size_t)T * N * W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int w = (int)(e % W);
+        const size_t row = e / W;  // flat row = env*T + t
+        const int env = (int)(row / T), t = (int)(row % T);
+        flat[e] = phys[((size_t)t * N + env) * W + w];
+    }
+}
+__global__ void import_flat_kernel(const float* __restrict__ flat, int T, int N, int W, float* __restrict__ phys) {
+    const size_t total = (size_t)T * N * W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int w = (int)(e % W);
+        const size_t row = e / W;
+        const int env = (int)(row / T), t = (int)(row % T);
+        phys[((size_t)t * N + env) * W + w] = flat[e];
+    }
+}
+
+}  // namespace ppo

@@ -1,0 +1,1231 @@
+// libppo_core.so — C ABI implementation (see include/ppo_core.h).  sm_100a only; no CPU fallback.
+#include "../../include/ppo_core.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_common.cuh"
+#include "host_rand.h"
+#include "kernels_misc.cuh"
+#include "kernels_mlp.cuh"
+#include "meta_parser.h"
+
+using namespace ppo;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(expr)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return fail(PPO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int _s = (expr);          \
+        if (_s != PPO_OK) return _s; \
+    } while (0)
+
+extern "C" const char* ppo_last_error(void) { return g_err; }
+extern "C" int ppo_abi_version(void) { return PPO_CORE_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueIdC { char internal[128]; };
+enum { ncclSuccessC = 0 };
+enum { ncclFloat32C = 7, ncclFloat64C = 8, ncclInt32C = 2 };
+enum { ncclSumC = 0 };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueIdC*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueIdC, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+#define LD(sym, field) field = reinterpret_cast<decltype(field)>(dlsym(lib, sym))
+        LD("ncclGetUniqueId", GetUniqueId);
+        LD("ncclCommInitRank", CommInitRank);
+        LD("ncclCommDestroy", CommDestroy);
+        LD("ncclAllReduce", AllReduce);
+        LD("ncclAllGather", AllGather);
+        LD("ncclGetErrorString", GetErrorString);
+#undef LD
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ the core
+enum { B_OBS, B_RETURNS, B_DONES, B_ACTIONS, B_VALUES, B_NEGLOGP, B_TRUE_REW, B_UNNORM_REW, B_COUNT };
+static const char* const kBufNames[B_COUNT] = {"obs", "returns", "dones", "actions", "values", "neglogpacs",
+                                               "true_rewards", "unnormalized_rewards"};
+
+struct ppo_core {
+    ppo_core_desc desc{};
+    NetDims d{};
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int tm = 64;          // tile size of the MLP kernels
+    int max_train_grid = 0;
+    int PS = 0;           // partial slab width = P + L_PAD
+
+    float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *bpow = nullptr;  // bpow: 2 slots x 2
+    int bpow_slot = 0;
+
+    NormStats st{};
+    float* ret = nullptr;
+    double *mom_partial = nullptr, *moments = nullptr;
+    unsigned int* ticket = nullptr;
+    int mom_grid = 0, mom_threads = 0;
+
+    float *cur_obs = nullptr, *cur_dones = nullptr, *cur_actions = nullptr, *last_values = nullptr;
+    float *raw_obs = nullptr, *raw_rew = nullptr, *raw_done = nullptr, *nrew = nullptr;
+    uint32_t* step_ctr = nullptr;
+    SynthEnv env{};
+
+    int n_batch_local = 0, n_batch_global = 0, B_global = 0;
+    float* buf[B_COUNT] = {};  // [world][T][Nl][w] slabs
+    int buf_w[B_COUNT] = {};
+
+    int *perm_dev = nullptr, *gather = nullptr;
+    float2* mbstats = nullptr;
+    float *partial = nullptr, *grad = nullptr, *loss_rows = nullptr, *loss_mean = nullptr, *gnorm = nullptr;
+    double* sq_partial = nullptr;
+    int n_sq_blocks = 0;
+    bool perm_set = false;
+
+    GlibcRand rng{1};
+    std::vector<int> perm_host;
+    int* perm_pinned = nullptr;  // [noptepochs][n_batch_global]
+    float* stage = nullptr;      // pinned staging
+    size_t stage_floats = 0;
+    float* scratch = nullptr;    // device scratch for host-pointer calls
+    size_t scratch_floats = 0;
+
+    ncclComm_t comm = nullptr;
+    ppo_counters ctr{};
+};
+
+#define LAUNCH(core, kernel, grid, block, smem, ...)                               \
+    do {                                                                           \
+        kernel<<<(grid), (block), (smem), (core)->stream>>>(__VA_ARGS__);          \
+        (core)->ctr.kernel_launches++;                                             \
+    } while (0)
+
+static int ensure_scratch(ppo_core* c, size_t floats) {
+    if (floats <= c->scratch_floats) return PPO_OK;
+    if (c->scratch) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(c->scratch));
+        c->scratch = nullptr;
+    }
+    CU(cudaMalloc(&c->scratch, floats * sizeof(float)));
+    c->scratch_floats = floats;
+    return PPO_OK;
+}
+static int ensure_stage(ppo_core* c, size_t floats) {
+    if (floats <= c->stage_floats) return PPO_OK;
+    if (c->stage) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFreeHost(c->stage));
+        c->stage = nullptr;
+    }
+    CU(cudaMallocHost(&c->stage, floats * sizeof(float)));
+    c->stage_floats = floats;
+    return PPO_OK;
+}
+
+// copy helpers honouring ppo_mem: returns a device pointer for an input / stages an output
+static int h2d(ppo_core* c, float* dst, const float* src, size_t n) {
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->ctr.h2d_bytes += n * sizeof(float);
+    return PPO_OK;
+}
+static int d2h(ppo_core* c, float* dst, const float* src, size_t n) {
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    c->ctr.d2h_bytes += n * sizeof(float);
+    return PPO_OK;
+}
+
+extern "C" int ppo_core_desc_default(ppo_core_desc* d) {
+    if (!d) return fail(PPO_ERR_INVALID, "desc is NULL");
+    memset(d, 0, sizeof(*d));
+    d->abi_version = PPO_CORE_ABI_VERSION;
+    d->obs_dim = 18; d->act_dim = 18; d->hidden1 = 4; d->hidden2 = 5;
+    d->n_envs = 1; d->n_steps = 2048; d->nminibatches = 32; d->noptepochs = 10;
+    d->gamma = 0.99f; d->lam = 0.95f;
+    d->ent_coef = 0.0007160293171182275f; d->vf_coef = 0.5f; d->max_grad_norm = 0.5f;
+    d->adam_beta1 = 0.9f; d->adam_beta2 = 0.999f; d->adam_epsilon = 1e-5f;
+    d->norm_obs = 1; d->norm_reward = 1; d->training = 1;
+    d->clip_obs = 10.f; d->clip_reward = 10.f; d->norm_gamma = 0.99f; d->norm_epsilon = 1e-8f;
+    d->seed = 0; d->rank = 0; d->world_size = 1; d->env_offset = 0; d->n_envs_global = 0;
+    return PPO_OK;
+}
+
+extern "C" int ppo_meta_parse(const char* path, ppo_meta_info* info, float* params_out, size_t cap) {
+    if (!path || !info) return fail(PPO_ERR_INVALID, "ppo_meta_parse: NULL argument");
+    MetaGraph g;
+    const std::string err = parse_meta_txt(path, g);
+    if (!err.empty()) return fail(PPO_ERR_IO, "%s", err.c_str());
+    NetDims d;
+    d.init(g.obs_dim, g.act_dim, g.hidden1, g.hidden2);
+    info->obs_dim = g.obs_dim; info->act_dim = g.act_dim; info->hidden1 = g.hidden1; info->hidden2 = g.hidden2;
+    info->ent_coef = g.ent_coef; info->vf_coef = g.vf_coef; info->max_grad_norm = g.clip_norm;
+    info->adam_beta1 = g.beta1; info->adam_beta2 = g.beta2; info->adam_epsilon = g.adam_eps;
+    info->n_params_trainable = d.P; info->n_params_total = d.Pq;
+    if (params_out) {
+        if (cap < (size_t)d.Pq) return fail(PPO_ERR_INVALID, "params_out holds %zu floats, graph has %d", cap, d.Pq);
+        for (int t = 0; t < kNumTensors; ++t) {
+            const MetaTensor& mt = g.tensors[kTensorNames[t]];
+            if ((int)mt.data.size() != d.off[t + 1] - d.off[t]) return fail(PPO_ERR_IO, "tensor %s has unexpected size", kTensorNames[t]);
+            memcpy(params_out + d.off[t], mt.data.data(), mt.data.size() * sizeof(float));
+        }
+    }
+    return PPO_OK;
+}
+
+template <int TM>
+static int set_smem_attrs(const NetDims& d) {
+    CU(cudaFuncSetAttribute(train_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(train_smem_floats<TM>(d) * sizeof(float))));
+    CU(cudaFuncSetAttribute(policy_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(policy_smem_floats<TM>(d) * sizeof(float))));
+    return PPO_OK;
+}
+
+extern "C" void ppo_core_destroy(ppo_core* c) {
+    if (!c) return;
+    cudaSetDevice(c->desc.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    void* dev_ptrs[] = {c->params, c->adam_m, c->adam_v, c->bpow, c->st.obs_mean, c->st.obs_var, c->st.obs_count,
+                        c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
+                        c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
+                        c->nrew, c->step_ctr, c->env.state, c->env.t_env, c->env.resets, c->perm_dev, c->gather,
+                        c->mbstats, c->partial, c->grad, c->loss_rows, c->loss_mean, c->gnorm, c->sq_partial, c->scratch};
+    for (void* p : dev_ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < B_COUNT; ++i)
+        if (c->buf[i]) cudaFree(c->buf[i]);
+    if (c->perm_pinned) cudaFreeHost(c->perm_pinned);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int core_alloc(ppo_core* c) {
+    const ppo_core_desc& D = c->desc;
+    const NetDims& d = c->d;
+    const int N = D.n_envs, O = d.O, A = d.A, T = D.n_steps, W = D.world_size;
+    auto zalloc = [&](void** p, size_t bytes) -> int {
+        CU(cudaMalloc(p, bytes));
+        CU(cudaMemsetAsync(*p, 0, bytes, c->stream));
+        return PPO_OK;
+    };
+#define ZA(ptr, count) TRY(zalloc(reinterpret_cast<void**>(&(ptr)), sizeof(*(ptr)) * (size_t)(count)))
+    ZA(c->params, d.Pq); ZA(c->adam_m, d.P); ZA(c->adam_v, d.P); ZA(c->bpow, 4);
+    ZA(c->st.obs_mean, O); ZA(c->st.obs_var, O); ZA(c->st.obs_count, 1);
+    ZA(c->st.ret_mean, 1); ZA(c->st.ret_var, 1); ZA(c->st.ret_count, 1);
+    ZA(c->ret, N);
+    c->mom_threads = O * std::max(1, 256 / O);
+    c->mom_grid = std::max(1, std::min(c->sm_count * 2, (int)(((size_t)N * O + c->mom_threads * 8 - 1) / (c->mom_threads * 8))));
+    ZA(c->mom_partial, (size_t)c->mom_grid * 2 * (O + 1)); ZA(c->moments, 2 * (O + 1) + 1); ZA(c->ticket, 1);
+    ZA(c->cur_obs, (size_t)N * O); ZA(c->cur_dones, N); ZA(c->cur_actions, (size_t)N * A); ZA(c->last_values, N);
+    ZA(c->raw_obs, (size_t)N * O); ZA(c->raw_rew, N); ZA(c->raw_done, N); ZA(c->nrew, N);
+    ZA(c->step_ctr, 1);
+    ZA(c->env.state, (size_t)N * O); ZA(c->env.t_env, N); ZA(c->env.resets, N);
+    c->env.seed = D.seed ^ 0x1234ull; c->env.env_id0 = (uint32_t)D.env_offset; c->env.n = N; c->env.D = O;
+    c->n_batch_local = N * T;
+    c->n_batch_global = c->n_batch_local * W;
+    c->B_global = c->n_batch_global / D.nminibatches;
+    const int widths[B_COUNT] = {O, 1, 1, A, 1, 1, 1, 1};
+    for (int i = 0; i < B_COUNT; ++i) {
+        c->buf_w[i] = widths[i];
+        // only the five train inputs are allgathered; the others stay local-sized
+        const bool global = (i == B_OBS || i == B_RETURNS || i == B_ACTIONS || i == B_VALUES || i == B_NEGLOGP);
+        ZA(c->buf[i], (size_t)(global ? c->n_batch_global : c->n_batch_local) * widths[i]);
+    }
+    ZA(c->perm_dev, c->n_batch_global); ZA(c->gather, c->n_batch_global);
+    ZA(c->mbstats, D.nminibatches);
+    c->PS = d.P + L_PAD;
+    c->max_train_grid = c->sm_count * 2;
+    ZA(c->partial, (size_t)c->max_train_grid * c->PS); ZA(c->grad, c->PS);
+    c->n_sq_blocks = (c->PS + 255) / 256;
+    ZA(c->sq_partial, c->n_sq_blocks);
+    ZA(c->loss_rows, (size_t)D.noptepochs * D.nminibatches * 5 + 5); ZA(c->loss_mean, 5); ZA(c->gnorm, 1);
+#undef ZA
+    CU(cudaMallocHost(&c->perm_pinned, sizeof(int) * (size_t)c->n_batch_global * std::max(1, D.noptepochs)));
+    c->perm_host.resize(c->n_batch_global);
+    // RunningStatistics(): mean 0, var 1, count = (double)1e-6f  (running_statistics.hpp:17-20)
+    std::vector<float> ones(O, 1.f);
+    const double cnt = (double)1e-6f;
+    const float one = 1.f;
+    CU(cudaMemcpyAsync(c->st.obs_var, ones.data(), O * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.ret_var, &one, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.obs_count, &cnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.ret_count, &cnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // beta powers start at beta (GRAPH:25426,25579)
+    const float bp[4] = {D.adam_beta1, D.adam_beta2, D.adam_beta1, D.adam_beta2};
+    CU(cudaMemcpyAsync(c->bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
+    if (!desc || !out) return fail(PPO_ERR_INVALID, "ppo_core_create: NULL argument");
+    if (desc->abi_version != PPO_CORE_ABI_VERSION) return fail(PPO_ERR_INVALID, "ABI version mismatch: header %d, library %d", desc->abi_version, PPO_CORE_ABI_VERSION);
+    if (desc->obs_dim < 1 || desc->obs_dim > 32 || desc->act_dim < 1 || desc->act_dim > 64 || desc->obs_dim != desc->act_dim)
+        return fail(PPO_ERR_UNSUPPORTED, "obs_dim/act_dim %d/%d unsupported (need 1..32 and equal, the reference uses 18/18)", desc->obs_dim, desc->act_dim);
+    if (desc->hidden1 < 1 || desc->hidden2 < 1 || desc->hidden1 > 1024 || desc->hidden2 > 1024)
+        return fail(PPO_ERR_UNSUPPORTED, "hidden sizes [%d,%d] out of range 1..1024", desc->hidden1, desc->hidden2);
+    if (desc->n_envs < 1 || desc->n_steps < 1 || desc->nminibatches < 1 || desc->noptepochs < 0)
+        return fail(PPO_ERR_INVALID, "n_envs, n_steps, nminibatches must be >= 1");
+    if (desc->world_size < 1 || desc->rank < 0 || desc->rank >= desc->world_size)
+        return fail(PPO_ERR_INVALID, "bad rank/world_size %d/%d", desc->rank, desc->world_size);
+    const long nbg = (long)desc->n_envs * desc->n_steps * desc->world_size;
+    if (nbg % desc->nminibatches != 0)  // assert((n_batch % nminibatches) == 0), ppo2.hpp:265
+        return fail(PPO_ERR_INVALID, "n_batch %ld not divisible by nminibatches %d", nbg, desc->nminibatches);
+    if ((nbg / desc->nminibatches) % desc->world_size != 0)
+        return fail(PPO_ERR_INVALID, "minibatch size %ld not divisible by world_size %d", nbg / desc->nminibatches, desc->world_size);
+    if (nbg > 0x7fffffffL) return fail(PPO_ERR_UNSUPPORTED, "n_batch %ld exceeds int32 (the reference uses int indices)", nbg);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PPO_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    if (desc->device < 0 || desc->device >= ndev) return fail(PPO_ERR_INVALID, "device %d out of range (have %d)", desc->device, ndev);
+    CU(cudaSetDevice(desc->device));
+    ppo_core* c = new ppo_core();
+    c->desc = *desc;
+    if (c->desc.n_envs_global <= 0) c->desc.n_envs_global = desc->n_envs * desc->world_size;
+    if (c->desc.world_size > 1 && c->desc.env_offset == 0) c->desc.env_offset = desc->rank * desc->n_envs;
+    c->d.init(desc->obs_dim, desc->act_dim, desc->hidden1, desc->hidden2);
+    int st = PPO_OK;
+    do {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, desc->device) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
+        c->sm_count = prop.multiProcessorCount;
+        const size_t max_smem = prop.sharedMemPerBlockOptin;
+        if (train_smem_floats<64>(c->d) * sizeof(float) <= max_smem) c->tm = 64;
+        else if (train_smem_floats<32>(c->d) * sizeof(float) <= max_smem) c->tm = 32;
+        else { st = fail(PPO_ERR_UNSUPPORTED, "hidden sizes [%d,%d] need more shared memory than the device has", desc->hidden1, desc->hidden2); break; }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        st = (c->tm == 64) ? set_smem_attrs<64>(c->d) : set_smem_attrs<32>(c->d);
+        if (st != PPO_OK) break;
+        st = core_alloc(c);
+    } while (0);
+    if (st != PPO_OK) {
+        char keep[1024];
+        strncpy(keep, g_err, sizeof(keep));
+        ppo_core_destroy(c);
+        strncpy(g_err, keep, sizeof(g_err));
+        return st;
+    }
+    *out = c;
+    return PPO_OK;
+}
+
+extern "C" int ppo_core_sync(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+extern "C" void* ppo_core_stream(ppo_core* c) { return c ? (void*)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ tensors
+extern "C" int ppo_core_num_tensors(void) { return kNumTensors; }
+extern "C" const char* ppo_core_tensor_name(int i) { return (i >= 0 && i < kNumTensors) ? kTensorNames[i] : nullptr; }
+
+static int resolve_tensor(ppo_core* c, const char* name, float** ptr, int* count) {
+    const NetDims& d = c->d;
+    const std::string s(name ? name : "");
+    if (s == "params") { *ptr = c->params; *count = d.Pq; return PPO_OK; }
+    if (s == "params_trainable") { *ptr = c->params; *count = d.P; return PPO_OK; }
+    if (s == "adam_m") { *ptr = c->adam_m; *count = d.P; return PPO_OK; }
+    if (s == "adam_v") { *ptr = c->adam_v; *count = d.P; return PPO_OK; }
+    if (s == "grad") { *ptr = c->grad; *count = d.P; return PPO_OK; }
+    if (s == "beta1_power") { *ptr = c->bpow + c->bpow_slot * 2; *count = 1; return PPO_OK; }
+    if (s == "beta2_power") { *ptr = c->bpow + c->bpow_slot * 2 + 1; *count = 1; return PPO_OK; }
+    for (int t = 0; t < kNumTensors; ++t) {
+        const std::string base(kTensorNames[t]);
+        const int n = d.off[t + 1] - d.off[t];
+        if (s == base) { *ptr = c->params + d.off[t]; *count = n; return PPO_OK; }
+        if (t < kNumTrainableTensors) {
+            if (s == base + "/Adam") { *ptr = c->adam_m + d.off[t]; *count = n; return PPO_OK; }
+            if (s == base + "/Adam_1") { *ptr = c->adam_v + d.off[t]; *count = n; return PPO_OK; }
+        }
+    }
+    return fail(PPO_ERR_INVALID, "unknown tensor name '%s'", s.c_str());
+}
+
+extern "C" int ppo_core_tensor_size(ppo_core* c, const char* name) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    float* p; int n;
+    const int st = resolve_tensor(c, name, &p, &n);
+    return st == PPO_OK ? n : st;
+}
+extern "C" int ppo_core_get_tensor(ppo_core* c, const char* name, float* out, size_t cap) {
+    if (!c || !out) return fail(PPO_ERR_INVALID, "NULL argument");
+    float* p; int n;
+    TRY(resolve_tensor(c, name, &p, &n));
+    if (cap < (size_t)n) return fail(PPO_ERR_INVALID, "buffer for '%s' holds %zu floats, need %d", name, cap, n);
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaMemcpyAsync(out, p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+extern "C" int ppo_core_set_tensor(ppo_core* c, const char* name, const float* in, size_t count) {
+    if (!c || !in) return fail(PPO_ERR_INVALID, "NULL argument");
+    float* p; int n;
+    TRY(resolve_tensor(c, name, &p, &n));
+    if (count != (size_t)n) return fail(PPO_ERR_INVALID, "tensor '%s' has %d floats, got %zu", name, n, count);
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaMemcpyAsync(p, in, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_core_load_meta_txt(ppo_core* c, const char* path) {
+    if (!c || !path) return fail(PPO_ERR_INVALID, "NULL argument");
+    ppo_meta_info info;
+    std::vector<float> p(c->d.Pq);
+    ppo_meta_info probe;
+    TRY(ppo_meta_parse(path, &probe, nullptr, 0));
+    if (probe.obs_dim != c->d.O || probe.act_dim != c->d.A || probe.hidden1 != c->d.H1 || probe.hidden2 != c->d.H2)
+        return fail(PPO_ERR_INVALID, "graph %s is obs %d act %d MLP [%d,%d]; core was created for obs %d act %d MLP [%d,%d]", path,
+                    probe.obs_dim, probe.act_dim, probe.hidden1, probe.hidden2, c->d.O, c->d.A, c->d.H1, c->d.H2);
+    TRY(ppo_meta_parse(path, &info, p.data(), p.size()));
+    // the graph's baked constants win over constructor arguments, as in the reference (SURVEY §3.5 "Consequence")
+    c->desc.ent_coef = info.ent_coef; c->desc.vf_coef = info.vf_coef; c->desc.max_grad_norm = info.max_grad_norm;
+    c->desc.adam_beta1 = info.adam_beta1; c->desc.adam_beta2 = info.adam_beta2; c->desc.adam_epsilon = info.adam_epsilon;
+    TRY(ppo_core_set_tensor(c, "params", p.data(), p.size()));
+    // reset() re-creates the session: Adam state starts from zero, beta powers at beta (ppo2.hpp:90-105)
+    CU(cudaMemsetAsync(c->adam_m, 0, c->d.P * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(c->adam_v, 0, c->d.P * sizeof(float), c->stream));
+    const float bp[4] = {info.adam_beta1, info.adam_beta2, info.adam_beta1, info.adam_beta2};
+    CU(cudaMemcpyAsync(c->bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bpow_slot = 0;
+    return PPO_OK;
+}
+
+// Stable-Baselines ortho_init(scale): QR-free variant via modified Gram-Schmidt on a Gaussian matrix
+// (scale sqrt(2) hidden, 1.0 value head, 0.01 policy/q heads; biases and logstd zero) — SURVEY §3.4.
+extern "C" int ppo_core_init_orthogonal(ppo_core* c, uint64_t seed) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    const NetDims& d = c->d;
+    std::vector<float> p(d.Pq, 0.f);
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next_u = [&]() -> double {  // splitmix64 -> (0,1)
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return ((double)(z >> 11) + 0.5) / 9007199254740992.0;
+    };
+    auto gauss = [&]() -> double { return std::sqrt(-2.0 * std::log(next_u())) * std::cos(6.283185307179586 * next_u()); };
+    auto ortho = [&](int t, int rows, int cols, double scale) {
+        // orthonormalise the shorter dimension's vectors
+        const bool tall = rows >= cols;
+        const int nv = tall ? cols : rows, len = tall ? rows : cols;
+        std::vector<std::vector<double>> v(nv, std::vector<double>(len));
+        for (auto& vec : v) for (auto& x : vec) x = gauss();
+        for (int i = 0; i < nv; ++i) {
+            for (int j = 0; j < i; ++j) {
+                double dot = 0;
+                for (int k = 0; k < len; ++k) dot += v[i][k] * v[j][k];
+                for (int k = 0; k < len; ++k) v[i][k] -= dot * v[j][k];
+            }
+            double nrm = 0;
+            for (int k = 0; k < len; ++k) nrm += v[i][k] * v[i][k];
+            nrm = std::sqrt(nrm);
+            for (int k = 0; k < len; ++k) v[i][k] /= nrm;
+        }
+        float* w = p.data() + d.off[t];
+        for (int r = 0; r < rows; ++r)
+            for (int cc = 0; cc < cols; ++cc) w[(size_t)r * cols + cc] = (float)(scale * (tall ? v[cc][r] : v[r][cc]));
+    };
+    const double s2 = std::sqrt(2.0);
+    ortho(T_PI_FC0_W, d.O, d.H1, s2); ortho(T_VF_FC0_W, d.O, d.H1, s2);
+    ortho(T_PI_FC1_W, d.H1, d.H2, s2); ortho(T_VF_FC1_W, d.H1, d.H2, s2);
+    ortho(T_VF_W, d.H2, 1, 1.0); ortho(T_PI_W, d.H2, d.A, 0.01); ortho(T_Q_W, d.H2, d.A, 0.01);
+    TRY(ppo_core_set_tensor(c, "params", p.data(), p.size()));
+    CU(cudaMemsetAsync(c->adam_m, 0, d.P * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(c->adam_v, 0, d.P * sizeof(float), c->stream));
+    const float bp[4] = {c->desc.adam_beta1, c->desc.adam_beta2, c->desc.adam_beta1, c->desc.adam_beta2};
+    CU(cudaMemcpyAsync(c->bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bpow_slot = 0;
+    return PPO_OK;
+}
+
+// TF Saver V2 data file: tensors in sorted-name order, raw little-endian fp32
+static const int kCkptOrder[15] = {T_PI_B, T_LOGSTD, T_PI_W, T_PI_FC0_B, T_PI_FC0_W, T_PI_FC1_B, T_PI_FC1_W, T_Q_B,
+                                   T_Q_W, T_VF_B, T_VF_W, T_VF_FC0_B, T_VF_FC0_W, T_VF_FC1_B, T_VF_FC1_W};
+
+extern "C" int ppo_core_load_checkpoint_data(ppo_core* c, const char* prefix) {
+    if (!c || !prefix) return fail(PPO_ERR_INVALID, "NULL argument");
+    const std::string path = std::string(prefix) + ".data-00000-of-00001";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return fail(PPO_ERR_IO, "cannot open %s", path.c_str());
+    std::vector<float> raw(c->d.Pq), p(c->d.Pq);
+    const size_t got = fread(raw.data(), sizeof(float), raw.size(), f);
+    const bool extra = fgetc(f) != EOF;
+    fclose(f);
+    if (got != raw.size() || extra) return fail(PPO_ERR_IO, "%s does not hold exactly %d floats (MLP [%d,%d])", path.c_str(), c->d.Pq, c->d.H1, c->d.H2);
+    size_t off = 0;
+    for (int i = 0; i < 15; ++i) {
+        const int t = kCkptOrder[i], n = c->d.off[t + 1] - c->d.off[t];
+        memcpy(p.data() + c->d.off[t], raw.data() + off, n * sizeof(float));
+        off += n;
+    }
+    return ppo_core_set_tensor(c, "params", p.data(), p.size());
+}
+
+extern "C" int ppo_core_save_checkpoint_data(ppo_core* c, const char* prefix) {
+    if (!c || !prefix) return fail(PPO_ERR_INVALID, "NULL argument");
+    std::vector<float> p(c->d.Pq), raw(c->d.Pq);
+    TRY(ppo_core_get_tensor(c, "params", p.data(), p.size()));
+    size_t off = 0;
+    for (int i = 0; i < 15; ++i) {
+        const int t = kCkptOrder[i], n = c->d.off[t + 1] - c->d.off[t];
+        memcpy(raw.data() + off, p.data() + c->d.off[t], n * sizeof(float));
+        off += n;
+    }
+    const std::string path = std::string(prefix) + ".data-00000-of-00001";
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return fail(PPO_ERR_IO, "cannot open %s for writing", path.c_str());
+    const size_t put = fwrite(raw.data(), sizeof(float), raw.size(), f);
+    fclose(f);
+    return put == raw.size() ? PPO_OK : fail(PPO_ERR_IO, "short write to %s", path.c_str());
+}
+
+// ------------------------------------------------------------------------------------------------ policy
+static int launch_policy(ppo_core* c, PolicyArgs& a) {
+    a.d = c->d;
+    a.params = c->params;
+    a.seed = c->desc.seed;
+    a.env_id0 = (uint32_t)c->desc.env_offset;
+    a.step_ctr = c->step_ctr;
+    const int tm = c->tm;
+    const int ntiles = (a.n + tm - 1) / tm;
+    const int grid = std::max(1, std::min(ntiles, c->sm_count * 4));
+    if (tm == 64) LAUNCH(c, policy_tile_kernel<64>, grid, NT, policy_smem_floats<64>(c->d) * sizeof(float), a);
+    else LAUNCH(c, policy_tile_kernel<32>, grid, NT, policy_smem_floats<32>(c->d) * sizeof(float), a);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
+static int policy_call(ppo_core* c, int mode, const float* obs, int n, const float* eps, float* action, float* value,
+                       float* neglogp, ppo_mem mem) {
+    if (!c || !obs || n < 1) return fail(PPO_ERR_INVALID, "policy call: bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    const int O = c->d.O, A = c->d.A;
+    PolicyArgs a{};
+    a.n = n;
+    a.mode = mode;
+    if (mem == PPO_DEVICE) {
+        a.obs = obs; a.eps = eps; a.action = action; a.value = value; a.neglogp = neglogp;
+        TRY(launch_policy(c, a));
+        if (mode == 0 && !eps) LAUNCH(c, bump_counter_kernel, 1, 1, 0, c->step_ctr);
+        return PPO_OK;
+    }
+    const size_t need = (size_t)n * (O + 2 * A + 2);
+    TRY(ensure_scratch(c, need));
+    float* d_obs = c->scratch;
+    float* d_eps = d_obs + (size_t)n * O;
+    float* d_act = d_eps + (size_t)n * A;
+    float* d_val = d_act + (size_t)n * A;
+    float* d_nlp = d_val + n;
+    TRY(h2d(c, d_obs, obs, (size_t)n * O));
+    if (eps) TRY(h2d(c, d_eps, eps, (size_t)n * A));
+    a.obs = d_obs; a.eps = eps ? d_eps : nullptr;
+    a.action = action ? d_act : nullptr; a.value = value ? d_val : nullptr; a.neglogp = neglogp ? d_nlp : nullptr;
+    TRY(launch_policy(c, a));
+    if (mode == 0 && !eps) LAUNCH(c, bump_counter_kernel, 1, 1, 0, c->step_ctr);
+    if (action) TRY(d2h(c, action, d_act, (size_t)n * A));
+    if (value) TRY(d2h(c, value, d_val, n));
+    if (neglogp) TRY(d2h(c, neglogp, d_nlp, n));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_policy_step(ppo_core* c, const float* obs, int n, const float* eps, float* action, float* value,
+                               float* neglogp, ppo_mem mem) {
+    return policy_call(c, 0, obs, n, eps, action, value, neglogp, mem);
+}
+extern "C" int ppo_policy_value(ppo_core* c, const float* obs, int n, float* value, ppo_mem mem) {
+    return policy_call(c, 1, obs, n, nullptr, nullptr, value, nullptr, mem);
+}
+extern "C" int ppo_policy_mean(ppo_core* c, const float* obs, int n, float* action, ppo_mem mem) {
+    return policy_call(c, 2, obs, n, nullptr, action, nullptr, nullptr, mem);
+}
+
+// ------------------------------------------------------------------------------------------------ comm
+static int nccl_check(int r, const char* what) {
+    if (r == ncclSuccessC) return PPO_OK;
+    return fail(PPO_ERR_COMM, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+extern "C" int ppo_comm_get_unique_id(char id[PPO_COMM_ID_BYTES]) {
+    if (!g_nccl.load()) return fail(PPO_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    ncclUniqueIdC u;
+    TRY(nccl_check(g_nccl.GetUniqueId(&u), "ncclGetUniqueId"));
+    memcpy(id, u.internal, PPO_COMM_ID_BYTES);
+    return PPO_OK;
+}
+extern "C" int ppo_comm_init(ppo_core* c, const char id[PPO_COMM_ID_BYTES], int rank, int world_size) {
+    if (!c || !id) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (rank != c->desc.rank || world_size != c->desc.world_size) return fail(PPO_ERR_INVALID, "rank/world_size differ from the core's desc");
+    if (!g_nccl.load()) return fail(PPO_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    CU(cudaSetDevice(c->desc.device));
+    ncclUniqueIdC u;
+    memcpy(u.internal, id, PPO_COMM_ID_BYTES);
+    TRY(nccl_check(g_nccl.CommInitRank(&c->comm, world_size, u, rank), "ncclCommInitRank"));
+    return PPO_OK;
+}
+static int need_comm(ppo_core* c) {
+    if (c->desc.world_size > 1 && !c->comm) return fail(PPO_ERR_COMM, "world_size %d but ppo_comm_init was not called", c->desc.world_size);
+    return PPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ VecNormalize
+// d_raw_obs/d_raw_rew/d_done are device pointers; outputs device pointers (may alias core state).
+static int vecnorm_device(ppo_core* c, const float* d_raw_obs, const float* d_raw_rew, const float* d_done, float* d_obs_out,
+                          float* d_rew_out, float* d_dones_out, float* rew_store, float* urew_store, bool bump) {
+    const ppo_core_desc& D = c->desc;
+    const int N = D.n_envs, O = c->d.O;
+    const bool upd_obs = D.training && D.norm_obs;
+    const bool upd_ret = D.training && D.norm_reward && d_raw_rew;
+    if (upd_obs || d_raw_rew) {
+        MomentsArgs m{};
+        m.raw_obs = d_raw_obs; m.raw_rew = d_raw_rew; m.ret = c->ret; m.n = N; m.D = O; m.gamma = D.norm_gamma;
+        m.partial = c->mom_partial; m.moments = c->moments; m.ticket = c->ticket; m.st = c->st;
+        m.update_obs = upd_obs; m.update_ret = upd_ret;
+        m.fuse_merge = (D.world_size == 1) && (upd_obs || upd_ret);
+        const size_t smem = sizeof(double) * (2 * (size_t)c->mom_threads + 2 * (O + 1) + 64);
+        LAUNCH(c, norm_moments_kernel, c->mom_grid, c->mom_threads, smem, m);
+        if (D.world_size > 1 && (upd_obs || upd_ret)) {
+            TRY(need_comm(c));
+            TRY(nccl_check(g_nccl.AllReduce(c->moments, c->moments, 2 * (O + 1) + 1, ncclFloat64C, ncclSumC, c->comm, c->stream), "ncclAllReduce(moments)"));
+            LAUNCH(c, norm_merge_kernel, 1, 64, 0, m);
+        }
+    }
+    ApplyArgs a{};
+    a.raw_obs = d_raw_obs; a.raw_rew = d_raw_rew; a.done = d_done; a.ret = c->ret; a.n = N; a.D = O; a.st = c->st;
+    a.norm_obs = D.norm_obs; a.norm_reward = D.norm_reward; a.clip_obs = D.clip_obs; a.clip_rew = D.clip_reward; a.eps = D.norm_epsilon;
+    a.obs_out = d_obs_out; a.rew_out = d_rew_out; a.dones_out = d_dones_out; a.rew_store = rew_store; a.urew_store = urew_store;
+    a.step_ctr = bump ? c->step_ctr : nullptr;
+    const int grid = std::max(1, std::min(c->sm_count * 8, (int)(((size_t)N * O + 255) / 256)));
+    LAUNCH(c, norm_apply_kernel, grid, 256, 0, a);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_vecnorm_reset(ppo_core* c, const float* raw_obs, float* obs_out, ppo_mem mem) {
+    if (!c || !raw_obs) return fail(PPO_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->desc.device));
+    const size_t no = (size_t)c->desc.n_envs * c->d.O;
+    CU(cudaMemsetAsync(c->ret, 0, c->desc.n_envs * sizeof(float), c->stream));  // ret = Zero (env_normalize.hpp:114)
+    if (mem == PPO_DEVICE) return vecnorm_device(c, raw_obs, nullptr, nullptr, obs_out ? obs_out : c->cur_obs, nullptr, nullptr, nullptr, nullptr, false);
+    TRY(h2d(c, c->raw_obs, raw_obs, no));
+    TRY(vecnorm_device(c, c->raw_obs, nullptr, nullptr, c->cur_obs, nullptr, nullptr, nullptr, nullptr, false));
+    if (obs_out) TRY(d2h(c, obs_out, c->cur_obs, no));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_vecnorm_step(ppo_core* c, const float* raw_obs, const float* raw_rew, const float* done, float* obs_out,
+                                float* rew_out, ppo_mem mem) {
+    if (!c || !raw_obs || !raw_rew || !done) return fail(PPO_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->desc.device));
+    const int N = c->desc.n_envs;
+    const size_t no = (size_t)N * c->d.O;
+    if (mem == PPO_DEVICE)
+        return vecnorm_device(c, raw_obs, raw_rew, done, obs_out ? obs_out : c->cur_obs, rew_out ? rew_out : c->nrew, c->cur_dones, nullptr, nullptr, false);
+    TRY(h2d(c, c->raw_obs, raw_obs, no));
+    TRY(h2d(c, c->raw_rew, raw_rew, N));
+    TRY(h2d(c, c->raw_done, done, N));
+    TRY(vecnorm_device(c, c->raw_obs, c->raw_rew, c->raw_done, c->cur_obs, c->nrew, c->cur_dones, nullptr, nullptr, false));
+    if (obs_out) TRY(d2h(c, obs_out, c->cur_obs, no));
+    if (rew_out) TRY(d2h(c, rew_out, c->nrew, N));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_vecnorm_get_stats(ppo_core* c, float* obs_mean, float* obs_var, double* obs_count, float* ret_mean,
+                                     float* ret_var, double* ret_count) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    const int O = c->d.O;
+    if (obs_mean) CU(cudaMemcpyAsync(obs_mean, c->st.obs_mean, O * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (obs_var) CU(cudaMemcpyAsync(obs_var, c->st.obs_var, O * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (obs_count) CU(cudaMemcpyAsync(obs_count, c->st.obs_count, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (ret_mean) CU(cudaMemcpyAsync(ret_mean, c->st.ret_mean, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (ret_var) CU(cudaMemcpyAsync(ret_var, c->st.ret_var, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (ret_count) CU(cudaMemcpyAsync(ret_count, c->st.ret_count, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_vecnorm_set_stats(ppo_core* c, const float* obs_mean, const float* obs_var, double obs_count,
+                                     const float* ret_mean, const float* ret_var, double ret_count) {
+    if (!c || !obs_mean || !obs_var || !ret_mean || !ret_var) return fail(PPO_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->desc.device));
+    const int O = c->d.O;
+    CU(cudaMemcpyAsync(c->st.obs_mean, obs_mean, O * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.obs_var, obs_var, O * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.obs_count, &obs_count, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.ret_mean, ret_mean, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.ret_var, ret_var, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->st.ret_count, &ret_count, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_vecnorm_set_training(ppo_core* c, int training) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    c->desc.training = training ? 1 : 0;
+    return PPO_OK;
+}
+
+extern "C" int ppo_running_stats_update(ppo_core* c, float* mean, float* var, double* count, int dim, const float* batch,
+                                        int rows, ppo_mem batch_mem) {
+    if (!c || !mean || !var || !count || !batch || dim < 1 || dim > 256 || rows < 1) return fail(PPO_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    const int threads = dim * std::max(1, 256 / dim);
+    const int grid = std::max(1, std::min(c->sm_count * 2, (int)(((size_t)rows * dim + threads * 8 - 1) / (threads * 8))));
+    // scratch: [batch rows*dim] [mean dim] [var dim] then doubles
+    const size_t nd = (size_t)grid * 2 * (dim + 1) + 2 * (dim + 1) + 1 + 2 + 2;  // partial, moments, counts(2), pad
+    const size_t floats = (batch_mem == PPO_HOST ? (size_t)rows * dim : 0) + 2 * (size_t)dim + 4 + 2 * nd + 8;
+    TRY(ensure_scratch(c, floats));
+    float* p = c->scratch;
+    const float* d_batch = batch;
+    if (batch_mem == PPO_HOST) {
+        TRY(h2d(c, p, batch, (size_t)rows * dim));
+        d_batch = p;
+        p += (size_t)rows * dim;
+    }
+    float* d_mean = p; p += dim;
+    float* d_var = p; p += dim;
+    float* d_dummy = p; p += 2;
+    double* dd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
+    double* d_partial = dd; dd += (size_t)grid * 2 * (dim + 1);
+    double* d_moments = dd; dd += 2 * (dim + 1) + 1;
+    double* d_count = dd; dd += 1;
+    double* d_count2 = dd; dd += 1;
+    unsigned int* d_ticket = reinterpret_cast<unsigned int*>(dd);
+    CU(cudaMemcpyAsync(d_mean, mean, dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_var, var, dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_count, count, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), c->stream));
+    MomentsArgs m{};
+    m.raw_obs = d_batch; m.raw_rew = nullptr; m.ret = nullptr; m.n = rows; m.D = dim; m.gamma = 0.f;
+    m.partial = d_partial; m.moments = d_moments; m.ticket = d_ticket;
+    m.st.obs_mean = d_mean; m.st.obs_var = d_var; m.st.obs_count = d_count;
+    m.st.ret_mean = d_dummy; m.st.ret_var = d_dummy + 1; m.st.ret_count = d_count2;
+    m.fuse_merge = 1; m.update_obs = 1; m.update_ret = 0;
+    const size_t smem = sizeof(double) * (2 * (size_t)threads + 2 * (dim + 1) + 64);
+    LAUNCH(c, norm_moments_kernel, grid, threads, smem, m);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(mean, d_mean, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(var, d_var, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(count, d_count, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_matrix_clamp(ppo_core* c, const float* x, size_t n, float lo, float hi, float* out, ppo_mem mem) {
+    if (!c || !x || !out) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (n == 0) return PPO_OK;
+    CU(cudaSetDevice(c->desc.device));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8, (n + 255) / 256));
+    if (mem == PPO_DEVICE) {
+        LAUNCH(c, clamp_kernel, grid, 256, 0, x, n, lo, hi, out);
+        CU(cudaGetLastError());
+        return PPO_OK;
+    }
+    TRY(ensure_scratch(c, n));
+    TRY(h2d(c, c->scratch, x, n));
+    LAUNCH(c, clamp_kernel, grid, 256, 0, c->scratch, n, lo, hi, c->scratch);
+    CU(cudaGetLastError());
+    TRY(d2h(c, out, c->scratch, n));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GAE
+static int launch_gae(ppo_core* c, const float* rew, const float* val, const float* dones, const float* last_val,
+                      const float* last_done, int T, int N, float gamma, float lam, float* adv, float* ret) {
+    // enough (env, chunk) threads to fill the machine; chunks only when there are few envs
+    int chunk = T;
+    const int want_threads = c->sm_count * 512;
+    if (N < want_threads && T > 1024) {
+        const int nchunks = std::min((T + 511) / 512, std::max(1, want_threads / std::max(N, 1)));
+        chunk = (T + nchunks - 1) / nchunks;
+        chunk = std::max(chunk, 256);
+    }
+    const int nchunks = (T + chunk - 1) / chunk;
+    const dim3 grid((N + 127) / 128, nchunks);
+    LAUNCH(c, gae_kernel, grid, 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, chunk, 512, adv, ret);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_gae(ppo_core* c, const float* rewards, const float* values, const float* dones, const float* last_values,
+                       const float* last_dones, int n_steps, int n_envs, float gamma, float lam, float* advs, float* returns,
+                       ppo_mem mem) {
+    if (!c || !rewards || !values || !dones || !last_values || !last_dones || !returns || n_steps < 1 || n_envs < 1)
+        return fail(PPO_ERR_INVALID, "ppo_gae: bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    if (mem == PPO_DEVICE) return launch_gae(c, rewards, values, dones, last_values, last_dones, n_steps, n_envs, gamma, lam, advs, returns);
+    const size_t tn = (size_t)n_steps * n_envs;
+    TRY(ensure_scratch(c, 5 * tn + 2 * (size_t)n_envs));
+    float* d_rew = c->scratch; float* d_val = d_rew + tn; float* d_done = d_val + tn; float* d_adv = d_done + tn; float* d_ret = d_adv + tn;
+    float* d_lv = d_ret + tn; float* d_ld = d_lv + n_envs;
+    TRY(h2d(c, d_rew, rewards, tn)); TRY(h2d(c, d_val, values, tn)); TRY(h2d(c, d_done, dones, tn));
+    TRY(h2d(c, d_lv, last_values, n_envs)); TRY(h2d(c, d_ld, last_dones, n_envs));
+    TRY(launch_gae(c, d_rew, d_val, d_done, d_lv, d_ld, n_steps, n_envs, gamma, lam, d_adv, d_ret));
+    if (advs) TRY(d2h(c, advs, d_adv, tn));
+    TRY(d2h(c, returns, d_ret, tn));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rollout
+static inline float* slab(ppo_core* c, int b, int t) {  // this rank's time-major slab, row t
+    const bool global = (b == B_OBS || b == B_RETURNS || b == B_ACTIONS || b == B_VALUES || b == B_NEGLOGP);
+    const size_t base = global ? (size_t)c->desc.rank * c->n_batch_local : 0;
+    return c->buf[b] + (base + (size_t)t * c->desc.n_envs) * c->buf_w[b];
+}
+
+extern "C" int ppo_runner_reset(ppo_core* c, const float* raw_obs, ppo_mem mem) {
+    if (!c || !raw_obs) return fail(PPO_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaMemsetAsync(c->cur_dones, 0, c->desc.n_envs * sizeof(float), c->stream));  // dones{Zero} (runner.hpp:50)
+    CU(cudaMemsetAsync(c->ret, 0, c->desc.n_envs * sizeof(float), c->stream));
+    const float* d_raw = raw_obs;
+    if (mem == PPO_HOST) {
+        TRY(h2d(c, c->raw_obs, raw_obs, (size_t)c->desc.n_envs * c->d.O));
+        d_raw = c->raw_obs;
+    }
+    TRY(vecnorm_device(c, d_raw, nullptr, nullptr, c->cur_obs, nullptr, nullptr, nullptr, nullptr, false));
+    if (mem == PPO_HOST) CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+static int runner_act_device(ppo_core* c, int t) {
+    PolicyArgs a{};
+    a.obs = c->cur_obs; a.n = c->desc.n_envs; a.eps = nullptr; a.mode = 0;
+    a.action = c->cur_actions;
+    a.obs_store = slab(c, B_OBS, t); a.act_store = slab(c, B_ACTIONS, t); a.val_store = slab(c, B_VALUES, t);
+    a.nlp_store = slab(c, B_NEGLOGP, t); a.dones_in = c->cur_dones; a.dones_store = slab(c, B_DONES, t);
+    return launch_policy(c, a);
+}
+
+extern "C" int ppo_runner_act(ppo_core* c, int t, float* actions_out, ppo_mem mem) {
+    if (!c || t < 0 || t >= c->desc.n_steps) return fail(PPO_ERR_INVALID, "ppo_runner_act: step %d out of range", t);
+    CU(cudaSetDevice(c->desc.device));
+    TRY(runner_act_device(c, t));
+    if (actions_out) {
+        const size_t na = (size_t)c->desc.n_envs * c->d.A;
+        if (mem == PPO_HOST) {
+            TRY(d2h(c, actions_out, c->cur_actions, na));
+            CU(cudaStreamSynchronize(c->stream));
+        } else {
+            CU(cudaMemcpyAsync(actions_out, c->cur_actions, na * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    return PPO_OK;
+}
+
+extern "C" int ppo_runner_observe(ppo_core* c, int t, const float* raw_obs, const float* raw_rew, const float* done, ppo_mem mem) {
+    if (!c || !raw_obs || !raw_rew || !done || t < 0 || t >= c->desc.n_steps) return fail(PPO_ERR_INVALID, "ppo_runner_observe: bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    const int N = c->desc.n_envs;
+    const float *d_o = raw_obs, *d_r = raw_rew, *d_d = done;
+    if (mem == PPO_HOST) {
+        TRY(h2d(c, c->raw_obs, raw_obs, (size_t)N * c->d.O));
+        TRY(h2d(c, c->raw_rew, raw_rew, N));
+        TRY(h2d(c, c->raw_done, done, N));
+        d_o = c->raw_obs; d_r = c->raw_rew; d_d = c->raw_done;
+    }
+    return vecnorm_device(c, d_o, d_r, d_d, c->cur_obs, c->nrew, c->cur_dones, slab(c, B_TRUE_REW, t), slab(c, B_UNNORM_REW, t), true);
+}
+
+extern "C" int ppo_runner_finish(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    PolicyArgs a{};
+    a.obs = c->cur_obs; a.n = c->desc.n_envs; a.mode = 1; a.value = c->last_values;  // model.value(obs) (runner.hpp:161-166)
+    TRY(launch_policy(c, a));
+    return launch_gae(c, slab(c, B_TRUE_REW, 0), slab(c, B_VALUES, 0), slab(c, B_DONES, 0), c->last_values, c->cur_dones,
+                      c->desc.n_steps, c->desc.n_envs, c->desc.gamma, c->desc.lam, nullptr, slab(c, B_RETURNS, 0));
+}
+
+extern "C" int ppo_synth_env_reset(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    LAUNCH(c, synth_env_reset_kernel, (c->desc.n_envs + 127) / 128, 128, 0, c->env, c->raw_obs);
+    CU(cudaGetLastError());
+    return ppo_runner_reset(c, c->raw_obs, PPO_DEVICE);
+}
+
+extern "C" int ppo_rollout_synthetic(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    const int N = c->desc.n_envs;
+    for (int t = 0; t < c->desc.n_steps; ++t) {
+        TRY(runner_act_device(c, t));
+        LAUNCH(c, synth_env_step_kernel, (N + 127) / 128, 128, 0, c->env, c->cur_actions, c->raw_obs, c->raw_rew, c->raw_done);
+        TRY(vecnorm_device(c, c->raw_obs, c->raw_rew, c->raw_done, c->cur_obs, c->nrew, c->cur_dones, slab(c, B_TRUE_REW, t),
+                           slab(c, B_UNNORM_REW, t), true));
+    }
+    return ppo_runner_finish(c);
+}
+
+static int buf_index(const char* name) {
+    for (int i = 0; i < B_COUNT; ++i)
+        if (name && strcmp(name, kBufNames[i]) == 0) return i;
+    return -1;
+}
+
+extern "C" int ppo_rollout_get(ppo_core* c, const char* name, float* out, size_t cap) {
+    const int b = buf_index(name);
+    if (!c || !out || b < 0) return fail(PPO_ERR_INVALID, "ppo_rollout_get: unknown buffer '%s'", name ? name : "(null)");
+    CU(cudaSetDevice(c->desc.device));
+    const size_t n = (size_t)c->n_batch_local * c->buf_w[b];
+    if (cap < n) return fail(PPO_ERR_INVALID, "buffer '%s' needs %zu floats, got %zu", name, n, cap);
+    TRY(ensure_scratch(c, n));
+    LAUNCH(c, export_flat_kernel, std::max(1, std::min(c->sm_count * 8, (int)((n + 255) / 256))), 256, 0, slab(c, b, 0),
+           c->desc.n_steps, c->desc.n_envs, c->buf_w[b], c->scratch);
+    CU(cudaGetLastError());
+    TRY(d2h(c, out, c->scratch, n));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_rollout_set(ppo_core* c, const char* name, const float* in, size_t count) {
+    const int b = buf_index(name);
+    if (!c || !in || b < 0) return fail(PPO_ERR_INVALID, "ppo_rollout_set: unknown buffer '%s'", name ? name : "(null)");
+    CU(cudaSetDevice(c->desc.device));
+    const size_t n = (size_t)c->n_batch_local * c->buf_w[b];
+    if (count != n) return fail(PPO_ERR_INVALID, "buffer '%s' has %zu floats, got %zu", name, n, count);
+    TRY(ensure_scratch(c, n));
+    TRY(h2d(c, c->scratch, in, n));
+    LAUNCH(c, import_flat_kernel, std::max(1, std::min(c->sm_count * 8, (int)((n + 255) / 256))), 256, 0, c->scratch,
+           c->desc.n_steps, c->desc.n_envs, c->buf_w[b], slab(c, b, 0));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ update
+extern "C" int ppo_shuffle_seed(ppo_core* c, unsigned seed) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    c->rng.srand(seed);
+    return PPO_OK;
+}
+extern "C" int ppo_host_srand_rand(unsigned seed, int count, int* out) {
+    if (!out || count < 0) return fail(PPO_ERR_INVALID, "bad arguments");
+    GlibcRand r(seed);
+    for (int i = 0; i < count; ++i) out[i] = r.rand();
+    return PPO_OK;
+}
+extern "C" int ppo_host_random_shuffle(unsigned seed, int n, int epochs, int* perms_out) {
+    if (!perms_out || n < 0 || epochs < 0) return fail(PPO_ERR_INVALID, "bad arguments");
+    GlibcRand r(seed);
+    std::vector<int> p(n);
+    for (int i = 0; i < n; ++i) p[i] = i;
+    for (int e = 0; e < epochs; ++e) {
+        r.random_shuffle(p.data(), n);
+        memcpy(perms_out + (size_t)e * n, p.data(), sizeof(int) * n);
+    }
+    return PPO_OK;
+}
+
+static int allgather_train_inputs(ppo_core* c) {
+    if (c->desc.world_size == 1) return PPO_OK;
+    TRY(need_comm(c));
+    const int ids[5] = {B_OBS, B_RETURNS, B_ACTIONS, B_VALUES, B_NEGLOGP};
+    for (int b : ids) {
+        const size_t n = (size_t)c->n_batch_local * c->buf_w[b];
+        TRY(nccl_check(g_nccl.AllGather(slab(c, b, 0), c->buf[b], n, ncclFloat32C, c->comm, c->stream), "ncclAllGather(rollout)"));
+    }
+    return PPO_OK;
+}
+
+// upload one epoch's permutation and derive the gather list + per-minibatch advantage statistics
+static int prepare_epoch(ppo_core* c, const int* perm_pinned_or_host) {
+    const int nb = c->n_batch_global;
+    CU(cudaMemcpyAsync(c->perm_dev, perm_pinned_or_host, sizeof(int) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+    c->ctr.h2d_bytes += sizeof(int) * (size_t)nb;
+    LAUNCH(c, build_gather_kernel, (nb + 255) / 256, 256, 0, c->perm_dev, nb, c->desc.n_steps, c->desc.n_envs, c->gather);
+    LAUNCH(c, advnorm_stats_kernel, c->desc.nminibatches, 512, 0, c->buf[B_RETURNS], c->buf[B_VALUES], c->gather, c->B_global, c->mbstats);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
+static int launch_train_kernel(ppo_core* c, TrainArgs& a) {
+    a.d = c->d;
+    a.params = c->params;
+    a.ent_coef = c->desc.ent_coef;
+    a.vf_coef = c->desc.vf_coef;
+    a.partial = c->partial;
+    a.PS = c->PS;
+    const int tm = c->tm;
+    const int ntiles = (a.count + tm - 1) / tm;
+    const int grid = std::max(1, std::min(ntiles, c->max_train_grid));
+    if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
+    else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
+    LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
+// one minibatch train step on the device: loss fwd/bwd -> reduce -> (allreduce) -> clip + Adam
+static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int loss_row) {
+    const int W = c->desc.world_size;
+    const int per_rank = c->B_global / W;
+    TrainArgs a{};
+    a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
+    a.gather = c->gather;
+    a.mbstats = c->mbstats + k;
+    a.adv_direct = nullptr;
+    a.slot0 = k * c->B_global + c->desc.rank * per_rank;
+    a.count = per_rank;
+    a.invB = 1.0f / (float)c->B_global;
+    a.cliprange = cliprange;
+    TRY(launch_train_kernel(c, a));
+    if (W > 1) {
+        TRY(need_comm(c));
+        TRY(nccl_check(g_nccl.AllReduce(c->grad, c->grad, c->PS, ncclFloat32C, ncclSumC, c->comm, c->stream), "ncclAllReduce(grad)"));
+        LAUNCH(c, sqnorm_kernel, c->n_sq_blocks, 256, 0, c->grad, c->d.P, c->sq_partial);
+    }
+    AdamArgs ad{};
+    ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
+    ad.nblk = c->n_sq_blocks; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
+    ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
+    ad.bpow_in = c->bpow + c->bpow_slot * 2; ad.bpow_out = c->bpow + (c->bpow_slot ^ 1) * 2;
+    ad.invB = a.invB; ad.inv_world = 1.0f / (float)W;
+    ad.loss_row = c->loss_rows + (size_t)loss_row * 5; ad.gnorm_out = c->gnorm;
+    LAUNCH(c, adam_kernel, (c->d.P + 255) / 256, 256, 0, ad);
+    CU(cudaGetLastError());
+    c->bpow_slot ^= 1;
+    return PPO_OK;
+}
+
+extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* mean_losses) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    const int nb = c->n_batch_global, E = c->desc.noptepochs, M = c->desc.nminibatches;
+    TRY(allgather_train_inputs(c));
+    // previous update's H2D copies out of the pinned permutation buffers must have finished
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nb; ++i) c->perm_host[i] = i;  // perm.setIdentity() once per update (ppo2.hpp:274-275)
+    for (int e = 0; e < E; ++e) {
+        c->rng.random_shuffle(c->perm_host.data(), nb);  // compounded across epochs (ppo2.hpp:288)
+        int* pinned = c->perm_pinned + (size_t)e * nb;
+        memcpy(pinned, c->perm_host.data(), sizeof(int) * (size_t)nb);
+        TRY(prepare_epoch(c, pinned));
+        for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
+    }
+    if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
+    CU(cudaGetLastError());
+    if (mean_losses) {
+        TRY(d2h(c, mean_losses, c->loss_mean, 5));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return PPO_OK;
+}
+
+extern "C" int ppo_train_set_permutation(ppo_core* c, const int* perm, int n) {
+    if (!c || !perm) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (n != c->n_batch_global) return fail(PPO_ERR_INVALID, "permutation has %d entries, n_batch is %d", n, c->n_batch_global);
+    CU(cudaSetDevice(c->desc.device));
+    std::vector<char> seen(n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (perm[i] < 0 || perm[i] >= n || seen[perm[i]]) return fail(PPO_ERR_INVALID, "not a permutation (entry %d = %d)", i, perm[i]);
+        seen[perm[i]] = 1;
+    }
+    TRY(allgather_train_inputs(c));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(c->perm_pinned, perm, sizeof(int) * (size_t)n);
+    TRY(prepare_epoch(c, c->perm_pinned));
+    CU(cudaStreamSynchronize(c->stream));
+    c->perm_set = true;
+    return PPO_OK;
+}
+
+extern "C" int ppo_train_minibatch(ppo_core* c, int k, float lr, float cliprange, float* losses, float* grads) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    if (!c->perm_set) return fail(PPO_ERR_INVALID, "call ppo_train_set_permutation first");
+    if (k < 0 || k >= c->desc.nminibatches) return fail(PPO_ERR_INVALID, "minibatch %d out of range", k);
+    CU(cudaSetDevice(c->desc.device));
+    const int row = c->desc.noptepochs * c->desc.nminibatches;  // spare row
+    TRY(train_step_device(c, k, lr, cliprange, row));
+    if (losses) TRY(d2h(c, losses, c->loss_rows + (size_t)row * 5, 5));
+    if (grads) TRY(d2h(c, grads, c->grad, c->d.P));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_advnorm(ppo_core* c, const float* returns, const float* values, int n, float* advs) {
+    if (!c || !returns || !values || !advs || n < 2) return fail(PPO_ERR_INVALID, "ppo_advnorm: bad arguments (the reference asserts rows > 1)");
+    CU(cudaSetDevice(c->desc.device));
+    TRY(ensure_scratch(c, 3 * (size_t)n + 4));
+    float* d_ret = c->scratch; float* d_val = d_ret + n; float* d_out = d_val + n;
+    float2* d_st = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(d_out + n) + 7) & ~(uintptr_t)7);
+    TRY(h2d(c, d_ret, returns, n)); TRY(h2d(c, d_val, values, n));
+    LAUNCH(c, advnorm_stats_kernel, 1, 512, 0, d_ret, d_val, (const int*)nullptr, n, d_st);
+    LAUNCH(c, advnorm_apply_kernel, (n + 255) / 256, 256, 0, d_ret, d_val, n, d_st, d_out);
+    CU(cudaGetLastError());
+    TRY(d2h(c, advs, d_out, n));
+    CU(cudaStreamSynchronize(c->stream));
+    return PPO_OK;
+}
+
+extern "C" int ppo_loss_grad(ppo_core* c, const float* obs, const float* actions, const float* advs, const float* returns,
+                             const float* old_neglogp, const float* old_values, int B, float cliprange, float* grads, float* losses) {
+    if (!c || !obs || !actions || !advs || !returns || !old_neglogp || !old_values || B < 1) return fail(PPO_ERR_INVALID, "ppo_loss_grad: bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    const int O = c->d.O, A = c->d.A;
+    TRY(ensure_scratch(c, (size_t)B * (O + A + 4)));
+    float* d_obs = c->scratch; float* d_act = d_obs + (size_t)B * O; float* d_adv = d_act + (size_t)B * A;
+    float* d_ret = d_adv + B; float* d_nlp = d_ret + B; float* d_val = d_nlp + B;
+    TRY(h2d(c, d_obs, obs, (size_t)B * O)); TRY(h2d(c, d_act, actions, (size_t)B * A)); TRY(h2d(c, d_adv, advs, B));
+    TRY(h2d(c, d_ret, returns, B)); TRY(h2d(c, d_nlp, old_neglogp, B)); TRY(h2d(c, d_val, old_values, B));
+    TrainArgs a{};
+    a.obs = d_obs; a.act = d_act; a.ret = d_ret; a.val = d_val; a.nlp = d_nlp; a.gather = nullptr; a.mbstats = nullptr;
+    a.adv_direct = d_adv; a.slot0 = 0; a.count = B; a.invB = 1.0f / (float)B; a.cliprange = cliprange;
+    TRY(launch_train_kernel(c, a));
+    std::vector<float> g(c->PS);
+    TRY(d2h(c, g.data(), c->grad, c->PS));
+    CU(cudaStreamSynchronize(c->stream));
+    if (grads) memcpy(grads, g.data(), sizeof(float) * c->d.P);
+    if (losses) {
+        const float* L = g.data() + c->d.P;
+        losses[0] = L[L_PG] * a.invB; losses[1] = 0.5f * (L[L_VF] * a.invB); losses[2] = L[L_ENT];
+        losses[3] = 0.5f * (L[L_KL] * a.invB); losses[4] = L[L_CLIP] * a.invB;
+    }
+    return PPO_OK;
+}
+
+extern "C" int ppo_learn_update_synthetic(ppo_core* c, float lr, float cliprange, float* mean_losses) {
+    TRY(ppo_rollout_synthetic(c));
+    return ppo_train_update(c, lr, cliprange, mean_losses);
+}
+
+extern "C" int ppo_core_counters(ppo_core* c, ppo_counters* out, int reset) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    if (out) *out = c->ctr;
+    if (reset) c->ctr = ppo_counters{};
+    return PPO_OK;
+}
+
+extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, float* avg_ms, int* launches) {
+    if (!c || !which || iters < 1 || !avg_ms) return fail(PPO_ERR_INVALID, "ppo_profile_kernel: bad arguments");
+    CU(cudaSetDevice(c->desc.device));
+    const std::string w(which);
+    const int N = c->desc.n_envs, T = c->desc.n_steps, W = c->desc.world_size;
+    if ((w == "train_fwdbwd" || w == "grad_reduce" || w == "adam") && !c->perm_set) {
+        // identity permutation is as good as any for timing
+        for (int i = 0; i < c->n_batch_global; ++i) c->perm_pinned[i] = i;
+        TRY(prepare_epoch(c, c->perm_pinned));
+        c->perm_set = true;
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const uint64_t before = c->ctr.kernel_launches;
+    int st = PPO_OK;
+    const int bpow_slot = c->bpow_slot;
+    for (int pass = 0; pass < 2 && st == PPO_OK; ++pass) {  // pass 0 = warm-up
+        const int n = pass == 0 ? std::min(iters, 3) : iters;
+        if (pass == 1) cudaEventRecord(e0, c->stream);
+        for (int i = 0; i < n && st == PPO_OK; ++i) {
+            if (w == "train_fwdbwd" || w == "grad_reduce") {
+                const int k = i % c->desc.nminibatches, per_rank = c->B_global / W;
+                TrainArgs a{};
+                a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
+                a.gather = c->gather; a.mbstats = c->mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
+                a.invB = 1.0f / (float)c->B_global; a.cliprange = 0.2f;
+                a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
+                const int tm = c->tm, ntiles = (a.count + tm - 1) / tm, grid = std::max(1, std::min(ntiles, c->max_train_grid));
+                if (w == "train_fwdbwd") {
+                    if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
+                    else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
+                } else {
+                    LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
+                }
+            } else if (w == "adam") {
+                AdamArgs ad{};
+                ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
+                ad.nblk = c->n_sq_blocks; ad.P = c->d.P; ad.lr = 0.f; ad.beta1 = 1.f; ad.beta2 = 1.f;  // state unchanged
+                ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
+                ad.bpow_in = c->bpow + bpow_slot * 2; ad.bpow_out = c->bpow + 4 - 4 + (bpow_slot ^ 1) * 2;
+                ad.invB = 1.f; ad.inv_world = 1.f; ad.loss_row = c->loss_rows + (size_t)c->desc.noptepochs * c->desc.nminibatches * 5;
+                ad.gnorm_out = c->gnorm;
+                // keep the beta powers: write the same values to the other slot
+                ad.beta1 = 1.f; ad.beta2 = 1.f;
+                LAUNCH(c, adam_kernel, (c->d.P + 255) / 256, 256, 0, ad);
+            } else if (w == "policy_step") {
+                PolicyArgs a{};
+                a.obs = c->cur_obs; a.n = N; a.mode = 0; a.action = c->cur_actions; a.value = c->last_values; a.neglogp = c->nrew;
+                st = launch_policy(c, a);
+            } else if (w == "norm_moments") {
+                MomentsArgs m{};
+                m.raw_obs = c->raw_obs; m.raw_rew = nullptr; m.ret = c->ret; m.n = N; m.D = c->d.O; m.gamma = c->desc.norm_gamma;
+                m.partial = c->mom_partial; m.moments = c->moments; m.ticket = c->ticket; m.st = c->st;
+                m.update_obs = 0; m.update_ret = 0; m.fuse_merge = 0;
+                LAUNCH(c, norm_moments_kernel, c->mom_grid, c->mom_threads, sizeof(double) * (2 * (size_t)c->mom_threads + 2 * (c->d.O + 1) + 64), m);
+            } else if (w == "norm_apply") {
+                ApplyArgs a{};
+                a.raw_obs = c->raw_obs; a.raw_rew = nullptr; a.done = nullptr; a.ret = c->ret; a.n = N; a.D = c->d.O; a.st = c->st;
+                a.norm_obs = 1; a.norm_reward = 1; a.clip_obs = c->desc.clip_obs; a.clip_rew = c->desc.clip_reward; a.eps = c->desc.norm_epsilon;
+                a.obs_out = c->cur_obs;
+                LAUNCH(c, norm_apply_kernel, std::max(1, std::min(c->sm_count * 8, (int)(((size_t)N * c->d.O + 255) / 256))), 256, 0, a);
+            } else if (w == "gae") {
+                st = launch_gae(c, slab(c, B_TRUE_REW, 0), slab(c, B_VALUES, 0), slab(c, B_DONES, 0), c->last_values, c->cur_dones, T, N,
+                                c->desc.gamma, c->desc.lam, nullptr, slab(c, B_RETURNS, 0));
+            } else {
+                st = fail(PPO_ERR_INVALID, "unknown kernel '%s'", which);
+            }
+        }
+        if (pass == 1) cudaEventRecord(e1, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(PPO_ERR_CUDA, "profile: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    float ms = 0.f;
+    if (st == PPO_OK && cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) st = fail(PPO_ERR_CUDA, "cudaEventElapsedTime failed");
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (st != PPO_OK) return st;
+    *avg_ms = ms / (float)iters;
+    if (launches) *launches = (int)(c->ctr.kernel_launches - before);
+    return PPO_OK;
+}

@@ -217,3 +217,57 @@ def param_layout(obs_dim: int, act_dim: int, h1: int, h2: int) -> Dict[str, Tupl
         off += int(np.prod(shp[name]))
     out["__total__"] = (off, ())
     return out
+
+
+def _escape(b: bytes) -> str:
+    out = []
+    for c in b:
+        if c == 0x5C:
+            out.append("\\\\")
+        elif c == 0x22:
+            out.append('\\"')
+        elif c == 0x27:
+            out.append("\\'")
+        elif 32 <= c < 127:
+            out.append(chr(c))
+        else:
+            out.append("\\%03o" % c)
+    return "".join(out)
+
+
+def write_meta_txt(path: str, tensors: Dict[str, np.ndarray], ent_coef: float = 0.0, vf_coef: float = 0.5,
+                   clip_norm: float = 0.5, beta1: float = 0.9, beta2: float = 0.999, adam_eps: float = 1e-5) -> None:
+    """Write a minimal .meta.txt (variables + initialisers + baked constants) that both readers accept.
+
+    The reference's graphs come from a Stable-Baselines/TensorFlow export script that is not part of the
+    repo; this writer lets a user produce a graph file for other hidden sizes without TensorFlow."""
+    def dims(shape, ind):
+        return "".join(f"{ind}dim {{\n{ind}  size: {d}\n{ind}}}\n" for d in shape)
+
+    def const_node(name, arr):
+        arr = np.asarray(arr, np.float32)
+        if arr.ndim == 0:
+            val = f"          float_val: {float(arr)!r}\n"
+        elif not arr.any():
+            val = ""
+        else:
+            val = f'          tensor_content: "{_escape(arr.astype("<f4").tobytes())}"\n'
+        return (f'  node {{\n    name: "{name}"\n    op: "Const"\n    attr {{\n      key: "dtype"\n      value {{\n        type: DT_FLOAT\n      }}\n    }}\n'
+                f'    attr {{\n      key: "value"\n      value {{\n        tensor {{\n          dtype: DT_FLOAT\n          tensor_shape {{\n'
+                f'{dims(arr.shape, "            ")}          }}\n{val}        }}\n      }}\n    }}\n  }}\n')
+
+    def var_node(name, shape):
+        return (f'  node {{\n    name: "{name}"\n    op: "VariableV2"\n    attr {{\n      key: "dtype"\n      value {{\n        type: DT_FLOAT\n      }}\n    }}\n'
+                f'    attr {{\n      key: "shape"\n      value {{\n        shape {{\n{dims(shape, "          ")}        }}\n      }}\n    }}\n  }}\n')
+
+    parts = ['meta_info_def {\n  tensorflow_version: "1.14.0"\n}\ngraph_def {\n']
+    for name in TENSOR_ORDER:
+        arr = np.asarray(tensors[name], np.float32)
+        parts.append(const_node(f"{name}/Initializer/initial_value", arr))
+        parts.append(var_node(name, arr.shape))
+    for name, val in (("loss/mul_4/y", ent_coef), ("loss/mul_5/y", vf_coef), ("loss/clip_by_global_norm/mul/x", clip_norm),
+                      ("ppo2/_train/beta1", beta1), ("ppo2/_train/beta2", beta2), ("ppo2/_train/epsilon", adam_eps)):
+        parts.append(const_node(name, np.float32(val)))
+    parts.append("}\n")
+    with open(path, "w", encoding="latin-1") as f:
+        f.write("".join(parts))

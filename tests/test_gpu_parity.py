@@ -1,0 +1,444 @@
+"""GPU parity tests: every entry point of the C ABI against the CPU oracle / the golden fixtures.
+
+Bar (BASELINE.json north_star): bit-exact for permutation indices and done masks; <= 1e-5 relative
+(tensor-wise: max|a-b| / max|b|) for log-probs, GAE, losses, gradients and one Adam step.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def core_mod():
+    from ppo_cpp_b200 import core
+    return core
+
+
+def make_core(core_mod, flat=None, **kw):
+    c = core_mod.PPOCore(**kw)
+    if flat is not None:
+        c.set_tensor("params", flat)
+    return c
+
+
+def rand_params(rng, h1, h2, O=18, A=18):
+    o = ol.Oracle(h1=h1, h2=h2)
+    p = (rng.standard_normal(o.Pq) * 0.3).astype(np.float32)
+    p[o.offset(12):o.offset(13)] = (-0.5 + 0.2 * rng.standard_normal(A)).astype(np.float32)  # logstd
+    return p
+
+
+# ------------------------------------------------------------------ policy step (a1-a3)
+@pytest.mark.parametrize("wname", ["init", "ckpt"])
+def test_policy_step_golden(core_mod, wname, forward_kat, init_weights, ckpt_weights):
+    _, flat = init_weights if wname == "init" else ckpt_weights
+    k = forward_kat[wname]
+    c = make_core(core_mod, flat, n_envs=8, n_steps=4, nminibatches=4)
+    act, val, nlp = c.policy_step(k["obs"], k["eps"])
+    assert rel_err(act, k["action"]) < TOL and rel_err(val, k["value"]) < TOL and rel_err(nlp, k["neglogp"]) < TOL
+    assert rel_err(c.policy_mean(k["obs"]), k["mean"]) < TOL
+    assert rel_err(c.policy_value(k["obs"]), k["value"]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("h1,h2,n", [(4, 5, 1), (4, 5, 1000), (8, 8, 129), (64, 64, 4096), (64, 32, 77), (256, 256, 300), (5, 3, 65)])
+def test_policy_step_vs_oracle(core_mod, h1, h2, n):
+    rng = np.random.default_rng(h1 * 1000 + h2 + n)
+    p = rand_params(rng, h1, h2)
+    obs = rng.standard_normal((n, 18)).astype(np.float32)
+    eps = rng.standard_normal((n, 18)).astype(np.float32)
+    c = make_core(core_mod, p, hidden1=h1, hidden2=h2, n_envs=4, n_steps=8, nminibatches=4)
+    act, val, nlp = c.policy_step(obs, eps)
+    o = ol.Oracle(h1=h1, h2=h2)
+    a64, v64, n64, m64 = o.policy_step(p, obs, eps, "f64")
+    assert rel_err(act, a64) < TOL and rel_err(val, v64) < TOL and rel_err(nlp, n64) < TOL
+    assert rel_err(c.policy_mean(obs), m64) < TOL
+    c.close()
+
+
+def test_policy_step_philox_noise(core_mod, ckpt_weights):
+    """eps == NULL: noise is Philox4x32-10 on (seed, env id, step counter); same stream as the oracle's."""
+    _, flat = ckpt_weights
+    n, seed = 500, 0xABCDEF0123
+    rng = np.random.default_rng(5)
+    obs = rng.standard_normal((n, 18)).astype(np.float32)
+    c = make_core(core_mod, flat, n_envs=4, n_steps=8, nminibatches=4, seed=seed)
+    lib = ol.load()
+    o = ol.Oracle()
+    std = np.exp(flat[o.offset(12):o.offset(13)].astype(np.float64))
+    mean = o.policy_step(flat, obs, None, "f64")[3]
+    for step in range(3):  # the step counter advances by one per call
+        act, _, nlp = c.policy_step(obs, None)
+        eps = np.zeros((n, 18), np.float32)
+        for e in range(n):
+            lib.oracle_normal_eps(seed, e, step, 18, eps[e])
+        assert np.max(np.abs((act - mean) / std - eps)) < 2e-5
+        a64, _, n64, _ = o.policy_step(flat, obs, eps, "f64")
+        assert rel_err(nlp, n64) < 5e-5  # eps itself carries ~1e-7 logf/sinf differences, amplified by 1/std^2
+    c.close()
+
+
+# ------------------------------------------------------------------ VecNormalize (a6-a8)
+def test_vecnorm_sequence_vs_oracle(core_mod):
+    rng = np.random.default_rng(11)
+    N, D, K = 96, 18, 12
+    c = make_core(core_mod, None, n_envs=N, n_steps=4, nminibatches=4)
+    lib = ol.load()
+    vn = lib.oracle_vecnorm_create(N, D, 1)
+    want_obs, want_rew = np.zeros((N, D), np.float32), np.zeros(N, np.float32)
+    raw0 = (rng.standard_normal((N, D)) * 3 + 1).astype(np.float32)
+    lib.oracle_vecnorm_reset_f32(vn, raw0, want_obs)
+    got = c.vecnorm_reset(raw0)
+    assert rel_err(got, want_obs) < TOL
+    for k in range(K):
+        raw = (rng.standard_normal((N, D)) * (1 + k) + 0.5 * k).astype(np.float32)
+        rew = (rng.standard_normal(N) * 5).astype(np.float32)
+        done = (rng.random(N) < 0.2).astype(np.float32)
+        lib.oracle_vecnorm_step_f32(vn, raw, rew, done, want_obs, want_rew)
+        obs, r = c.vecnorm_step(raw, rew, done)
+        assert rel_err(obs, want_obs) < TOL and rel_err(r, want_rew) < TOL
+    st = c.vecnorm_stats()
+    v = vn.contents
+    assert st["obs_count"] == v.obs_rms.count and st["ret_count"] == v.ret_rms.count  # exact doubles
+    assert st["obs_count"] == pytest.approx(1e-6 + N * (K + 1))
+    assert rel_err(st["obs_mean"], np.ctypeslib.as_array(v.obs_rms.mean, (D,))) < TOL
+    assert rel_err(st["obs_var"], np.ctypeslib.as_array(v.obs_rms.var, (D,))) < TOL
+    assert rel_err(st["ret_var"], np.ctypeslib.as_array(v.ret_rms.var, (1,))) < TOL
+    lib.oracle_vecnorm_destroy(vn)
+    # frozen statistics (training = false, playback): outputs keep following the oracle, counts stay
+    c.vecnorm_set_training(0)
+    c.vecnorm_step(raw, rew, done)
+    assert c.vecnorm_stats()["obs_count"] == st["obs_count"]
+    c.close()
+
+
+def test_vecnorm_clip_and_constant_input(core_mod):
+    """EnvMock-style constant observation (C1): mean -> obs, var -> ~0, output stays finite and inside the clip."""
+    N, D = 4, 18
+    c = make_core(core_mod, None, n_envs=N, n_steps=4, nminibatches=4)
+    out = c.vecnorm_reset(np.ones((N, D), np.float32))
+    for _ in range(5):
+        out, r = c.vecnorm_step(np.ones((N, D), np.float32), np.ones(N, np.float32), np.zeros(N, np.float32))
+        assert np.all(np.isfinite(out)) and np.abs(out).max() <= 10 and np.abs(r).max() <= 10
+    st = c.vecnorm_stats()
+    assert np.allclose(st["obs_mean"], 1.0, atol=1e-5)
+    big = c.vecnorm_step(np.full((N, D), 1e6, np.float32), np.full(N, 1e9, np.float32), np.zeros(N, np.float32))
+    assert big[0].max() == 10.0 and big[1].max() == 10.0
+    c.close()
+
+
+def test_running_stats_and_clamp_standalone(core_mod):
+    rng = np.random.default_rng(12)
+    c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)
+    lib = ol.load()
+    for D, rows in ((18, 1), (18, 5000), (1, 333), (7, 64)):
+        batch = (rng.standard_normal((rows, D)) * 2 + 3).astype(np.float32)
+        mean, var = rng.standard_normal(D).astype(np.float32), (rng.random(D) + 0.5).astype(np.float32)
+        m, v, cnt = c.running_stats_update(mean, var, 123.5, batch)
+        wm, wv, wc = mean.astype(np.float64), var.astype(np.float64), C.c_double(123.5)
+        lib.oracle_rstats_update_f64(wm, wv, C.byref(wc), D, batch.astype(np.float64), rows)
+        assert cnt == wc.value and rel_err(m, wm) < TOL and rel_err(v, wv) < TOL
+    x = (rng.standard_normal(10001) * 20).astype(np.float32)
+    want = np.zeros_like(x)
+    lib.oracle_matrix_clamp_f32(x, x.size, -10.0, 10.0, want)
+    assert np.array_equal(c.matrix_clamp(x, -10.0, 10.0), want)  # bit-exact
+    c.close()
+
+
+# ------------------------------------------------------------------ GAE (a5)
+@pytest.mark.parametrize("T,N", [(1, 1), (64, 4096), (2048, 1), (5000, 3), (333, 257)])
+def test_gae_vs_oracle(core_mod, T, N):
+    rng = np.random.default_rng(T * 7 + N)
+    rew, val = rng.standard_normal((T, N)).astype(np.float32), rng.standard_normal((T, N)).astype(np.float32)
+    done = (rng.random((T, N)) < 1 / 50).astype(np.float32)
+    lv, ld = rng.standard_normal(N).astype(np.float32), (rng.random(N) < 0.3).astype(np.float32)
+    c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)
+    g, lam = np.float32(0.99), np.float32(0.95)
+    adv, ret = c.gae(rew, val, done, lv, ld, g, lam)
+    o = ol.Oracle()
+    a64, r64 = o.gae(rew, val, done, lv, ld, float(g), float(lam), "f64")
+    assert rel_err(adv, a64) < TOL and rel_err(ret, r64) < TOL
+    a32, r32 = o.gae(rew, val, done, lv, ld, g, lam, "f32")
+    assert np.array_equal(adv, a32) and np.array_equal(ret, r32)  # same fp32 operation order: bit-exact
+    c.close()
+
+
+def test_gae_full_size_properties(core_mod):
+    """C5 size (16 M transitions): size-independent properties instead of an oracle run."""
+    import torch
+    T, N = 256, 65536
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(0)
+    rew = torch.randn(T, N, device=dev, generator=gen)
+    val = torch.randn(T, N, device=dev, generator=gen)
+    lv = torch.randn(N, device=dev, generator=gen)
+    c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    ones, zeros = torch.ones(T, N, device=dev), torch.zeros(N, device=dev)
+    torch.cuda.synchronize()
+    # every step terminal: adv = rew - val exactly (except the last row, which bootstraps with last_dones=0)
+    c.gae_device(rew, val, ones, lv, torch.ones(N, device=dev), 0.99, 0.95, adv, ret)
+    c.sync()
+    assert torch.equal(adv, rew - val) and torch.equal(ret, (rew - val) + val)
+    # gamma = 0: adv = rew - val regardless of dones
+    c.gae_device(rew, val, torch.zeros(T, N, device=dev), lv, zeros, 0.0, 0.95, adv, ret)
+    c.sync()
+    assert torch.equal(adv, rew - val)
+    # lam = 1, no dones, gamma = 1: adv_t = sum_{s>=t} rew_s + last_v - val_t  (telescoping) — checked in fp64
+    c.gae_device(rew, val, torch.zeros(T, N, device=dev), lv, zeros, 1.0, 1.0, adv, ret)
+    c.sync()
+    want = torch.flip(torch.cumsum(torch.flip(rew.double(), [0]), 0), [0]) + lv.double() - val.double()
+    assert float((adv.double() - want).abs().max() / want.abs().max()) < TOL
+    c.close()
+
+
+# ------------------------------------------------------------------ advantage normalisation (a10)
+@pytest.mark.parametrize("n", [2, 64, 2048, 131072])
+def test_advnorm_vs_oracle(core_mod, n):
+    rng = np.random.default_rng(n)
+    r, v = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)
+    assert rel_err(c.advnorm(r, v), ol.Oracle().advnorm(r, v, "f64")) < TOL
+    c.close()
+
+
+# ------------------------------------------------------------------ loss + gradient (a11)
+@pytest.mark.parametrize("case", ["init_4_5", "ckpt_4_5", "rand_64_64", "rand_8_8"])
+def test_loss_grad_golden_autograd(core_mod, case, loss_kat, kat):
+    k = loss_kat[case]
+    h1, h2 = (int(x) for x in k["hidden"])
+    cst = kat["consts"]
+    c = make_core(core_mod, k["params"], hidden1=h1, hidden2=h2, n_envs=4, n_steps=8, nminibatches=4,
+                  ent_coef=cst["ent_coef"], vf_coef=cst["vf_coef"])
+    g, l = c.loss_grad(k["obs"], k["act"], k["adv"], k["ret"], k["old_nlp"], k["old_v"], float(k["cliprange"]))
+    assert rel_err(g, k["grads"]) < TOL
+    assert np.allclose(l, k["losses"], rtol=TOL, atol=1e-7)
+    from ppo_cpp_b200.meta_graph import TENSOR_ORDER, param_layout
+    lay = param_layout(18, 18, h1, h2)
+    for name in TENSOR_ORDER[:13]:  # per tensor, so small tensors cannot hide behind large ones
+        off, shp = lay[name]
+        n = int(np.prod(shp))
+        assert rel_err(g[off:off + n], k["grads"][off:off + n]) < 5 * TOL, name
+    c.close()
+
+
+@pytest.mark.parametrize("h1,h2,B", [(4, 5, 64), (4, 5, 2048), (64, 64, 8192), (256, 256, 512), (12, 20, 100), (5, 3, 37)])
+def test_loss_grad_vs_oracle(core_mod, h1, h2, B):
+    rng = np.random.default_rng(B + h1)
+    p = rand_params(rng, h1, h2)
+    o = ol.Oracle(h1=h1, h2=h2)
+    obs = rng.standard_normal((B, 18)).astype(np.float32)
+    _, v64, _, m64 = o.policy_step(p, obs, None, "f64")
+    std = np.exp(p[o.offset(12):o.offset(13)].astype(np.float64))
+    act = (m64 + std * rng.standard_normal((B, 18))).astype(np.float32)
+    z = (act - m64) / std
+    old_nlp = (0.5 * (z * z).sum(1) + 18 * 0.9189385175704956 + np.log(std).sum() + 0.1 * rng.standard_normal(B)).astype(np.float32)
+    old_v = (v64 + 0.3 * rng.standard_normal(B)).astype(np.float32)
+    ret = (v64 + 0.5 * rng.standard_normal(B)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    c = make_core(core_mod, p, hidden1=h1, hidden2=h2, n_envs=4, n_steps=8, nminibatches=4)
+    g, l = c.loss_grad(obs, act, adv, ret, old_nlp, old_v, 0.2)
+    g64, l64 = o.loss_grad(p, obs, act, adv, ret, old_nlp, old_v, 0.2, "f64")
+    assert rel_err(g, g64) < TOL
+    assert np.allclose(l, l64, rtol=TOL, atol=1e-7)
+    assert l[4] == pytest.approx(l64[4], abs=1.5 / B)  # clipfrac is a count
+    c.close()
+
+
+# ------------------------------------------------------------------ minibatch step / whole update (a9-a11)
+def _oracle_learner(kat, flat, n_envs, n_steps, nmb, epochs, env_kind, seed=77, shuffle_seed=42, h1=4, h2=5, lr=3.9e-4, cr=0.2):
+    c = kat["consts"]
+    lib = ol.load()
+    d = ol.LearnerDesc(ol.Dims(18, 18, h1, h2), ol.HParams(c["ent_coef"], c["vf_coef"], c["clip_norm"], c["beta1"], c["beta2"], c["adam_eps"]),
+                       n_envs, n_steps, nmb, epochs, 0.99, 0.95, lr, cr, seed, shuffle_seed, env_kind, 1)
+    return lib, lib.oracle_learner_create(C.byref(d), np.ascontiguousarray(flat, np.float32))
+
+
+def _buffers(lib, L, nb):
+    names = ["obs", "returns", "dones", "actions", "values", "neglogpacs", "true_rewards", "unnormalized_rewards"]
+    widths = [18, 1, 1, 18, 1, 1, 1, 1]
+    return {n: np.ctypeslib.as_array(lib.oracle_learner_buffer(L, i), (nb, w)).copy() for i, (n, w) in enumerate(zip(names, widths))}
+
+
+def test_train_minibatch_one_adam_step(core_mod, init_weights, kat):
+    """Import the oracle's rollout, set the oracle's permutation, run ONE minibatch: gradient, losses and the
+    Adam-updated parameters must match the fp64 oracle chain advnorm -> loss_grad -> clip_adam."""
+    _, flat = init_weights
+    n_envs, n_steps, nmb = 4, 64, 4
+    nb = n_envs * n_steps
+    lib, L = _oracle_learner(kat, flat, n_envs, n_steps, nmb, 1, 0)
+    lib.oracle_learner_rollout(L)
+    bufs = _buffers(lib, L, nb)
+    cst = kat["consts"]
+    c = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=1, ent_coef=cst["ent_coef"])
+    for name, v in bufs.items():
+        c.rollout_set(name, v)
+        assert np.array_equal(c.rollout_get(name), v)  # layout round trip (flat row = env*n_steps + t)
+    perm = ol.glibc_shuffle(42, nb, 1)[0]
+    c.train_set_permutation(perm)
+    src = np.zeros(nb, np.int32)
+    lib.oracle_perm_to_gather(perm, nb, src)
+    o = ol.Oracle()
+    B = nb // nmb
+    k = 2
+    idx = src[k * B:(k + 1) * B]
+    adv = o.advnorm(bufs["returns"][idx, 0], bufs["values"][idx, 0], "f64")
+    g64, l64 = o.loss_grad(flat, bufs["obs"][idx], bufs["actions"][idx], adv, bufs["returns"][idx, 0], bufs["neglogpacs"][idx, 0],
+                           bufs["values"][idx, 0], 0.2, "f64")
+    losses, grads = c.train_minibatch(k, 3.9e-4, 0.2)
+    assert rel_err(grads, g64) < TOL and np.allclose(losses, l64, rtol=TOL, atol=1e-7)
+    th0 = flat[:o.P].astype(np.float64)
+    th1, m1, v1, _, b1p, b2p, gn = o.clip_adam(3.9e-4, th0, np.zeros(o.P), np.zeros(o.P), g64, float(np.float32(0.9)), float(np.float32(0.999)), "f64")
+    got = c.get_tensor("params")
+    assert rel_err(got[:o.P] - flat[:o.P], th1 - th0) < 1e-4  # the step itself (difference of nearly equal fp32 numbers)
+    assert rel_err(got[:o.P], th1) < 1e-6
+    assert np.array_equal(got[o.P:], flat[o.P:])  # q head untouched
+    assert rel_err(c.get_tensor("adam_m"), m1) < TOL and rel_err(c.get_tensor("adam_v"), v1) < TOL
+    assert c.get_tensor("beta1_power")[0] == pytest.approx(b1p, rel=1e-6) and c.get_tensor("beta2_power")[0] == pytest.approx(b2p, rel=1e-6)
+    lib.oracle_learner_destroy(L)
+    c.close()
+
+
+@pytest.mark.parametrize("h1,h2,n_envs,n_steps,nmb,epochs", [(4, 5, 2, 64, 4, 3), (4, 5, 1, 2048, 32, 2), (64, 64, 16, 32, 8, 2)])
+def test_train_update_vs_oracle_learner(core_mod, kat, init_weights, h1, h2, n_envs, n_steps, nmb, epochs):
+    """Whole update (epochs x minibatches, compounded glibc shuffles, scatter semantics) vs the oracle's
+    reference-structured learner on the SAME rollout."""
+    rng = np.random.default_rng(3)
+    flat = init_weights[1] if (h1, h2) == (4, 5) else rand_params(rng, h1, h2)
+    nb = n_envs * n_steps
+    lib, L = _oracle_learner(kat, flat, n_envs, n_steps, nmb, epochs, 0, h1=h1, h2=h2)
+    lib.oracle_learner_rollout(L)
+    bufs = _buffers(lib, L, nb)
+    cst = kat["consts"]
+    c = make_core(core_mod, flat, hidden1=h1, hidden2=h2, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=epochs,
+                  ent_coef=cst["ent_coef"])
+    for name, v in bufs.items():
+        c.rollout_set(name, v)
+    c.shuffle_seed(42)
+    losses = c.train_update(3.9e-4, 0.2)
+    want = np.zeros(5, np.float32)
+    lib.oracle_learner_train(L, want)
+    o = ol.Oracle(h1=h1, h2=h2)
+    p1 = np.ctypeslib.as_array(lib.oracle_learner_params(L), (o.Pq,)).copy()
+    got = c.get_tensor("params")
+    # after epochs*nmb Adam steps of size ~lr the trajectories must still agree to a small fraction of the total movement
+    moved = np.abs(p1[:o.P] - flat[:o.P]).max()
+    assert np.abs(got[:o.P] - p1[:o.P]).max() < 2e-3 * moved
+    assert np.allclose(losses, want, rtol=1e-4, atol=1e-6)
+    lib.oracle_learner_destroy(L)
+    c.close()
+
+
+# ------------------------------------------------------------------ rollout (a4) — device env and host env
+def test_rollout_synthetic_vs_oracle(core_mod, kat, ckpt_weights):
+    _, flat = ckpt_weights
+    n_envs, n_steps = 32, 400  # crosses the 334-step episode boundary of every env
+    nb = n_envs * n_steps
+    lib, L = _oracle_learner(kat, flat, n_envs, n_steps, 4, 1, 0, seed=2024)
+    lib.oracle_learner_rollout(L)
+    want = _buffers(lib, L, nb)
+    c = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=2024)
+    c.synth_env_reset()
+    c.rollout_synthetic()
+    got = {n: c.rollout_get(n) for n in want}
+    assert np.array_equal(got["dones"], want["dones"])  # done masks: bit-exact
+    assert want["dones"].sum() == n_envs  # every env ended exactly one episode
+    for name in ("obs", "actions", "values", "neglogpacs", "true_rewards", "unnormalized_rewards", "returns"):
+        assert rel_err(got[name], want[name]) < 2e-4, name  # 400 recurrent env+normaliser steps in fp32
+    om, ov = np.zeros(18, np.float32), np.zeros(18, np.float32)
+    oc, rm, rv, rc = C.c_double(), C.c_float(), C.c_float(), C.c_double()
+    lib.oracle_learner_get_norm(L, om, ov, C.byref(oc), C.byref(rm), C.byref(rv), C.byref(rc))
+    st = c.vecnorm_stats()
+    assert st["obs_count"] == oc.value and st["ret_count"] == rc.value
+    assert rel_err(st["obs_mean"], om) < 1e-4 and rel_err(st["obs_var"], ov) < 1e-4 and st["ret_var"][0] == pytest.approx(rv.value, rel=1e-4)
+    lib.oracle_learner_destroy(L)
+    c.close()
+
+
+def test_runner_host_env_protocol_equals_device_env(core_mod, ckpt_weights):
+    """Runner::run through host buffers (act -> env.step on the host -> observe) with the oracle's synthetic env
+    as the host env must reproduce the all-device rollout of the same seed."""
+    _, flat = ckpt_weights
+    n_envs, n_steps, seed = 16, 48, 99
+    lib = ol.load()
+    env = lib.oracle_synth_env_create(n_envs, 18, seed ^ 0x1234, 0)
+    obs, rew, done = np.zeros((n_envs, 18), np.float32), np.zeros(n_envs, np.float32), np.zeros(n_envs, np.float32)
+    c = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=seed)
+    lib.oracle_synth_env_reset(env, obs)
+    c.runner_reset(obs)
+    for t in range(n_steps):
+        act = c.runner_act(t)
+        lib.oracle_synth_env_step(env, act, obs, rew, done)
+        c.runner_observe(t, obs, rew, done)
+    c.runner_finish()
+    host = {n: c.rollout_get(n) for n in ("obs", "actions", "values", "returns", "dones", "true_rewards")}
+    lib.oracle_synth_env_destroy(env)
+    c2 = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=seed)
+    c2.synth_env_reset()
+    c2.rollout_synthetic()
+    for n, v in host.items():
+        assert rel_err(v, c2.rollout_get(n)) < 1e-5, n
+    c.close()
+    c2.close()
+
+
+def test_rollout_mock_env_c1(core_mod, init_weights, kat):
+    """Config C1: EnvMock (constant obs/reward 1, done every 300th step) driven through the host protocol.
+    Rewards, dones and the done-lag of Runner::run are exact; the normalised observation is cancellation noise
+    (SURVEY §7 'C1 is numerically degenerate'), so only its clip bound is checked."""
+    _, flat = init_weights
+    n_steps = 640
+    c = make_core(core_mod, flat, n_envs=1, n_steps=n_steps, nminibatches=32, noptepochs=1)
+    lib, L = _oracle_learner(kat, flat, 1, n_steps, 32, 1, 1)
+    lib.oracle_learner_rollout(L)
+    want = _buffers(lib, L, n_steps)
+    c.runner_reset(np.ones((1, 18), np.float32))
+    for t in range(n_steps):
+        c.runner_act(t)
+        c.runner_observe(t, np.ones((1, 18), np.float32), np.ones(1, np.float32), np.full(1, 1.0 if (t + 1) % 300 == 0 else 0.0, np.float32))
+    c.runner_finish()
+    assert np.array_equal(c.rollout_get("dones"), want["dones"])  # dones[t] = done of step t-1
+    assert np.flatnonzero(want["dones"][:, 0]).tolist() == [300, 600]
+    assert np.array_equal(c.rollout_get("unnormalized_rewards"), want["unnormalized_rewards"])
+    assert rel_err(c.rollout_get("true_rewards"), want["true_rewards"]) < 1e-4
+    assert np.abs(c.rollout_get("obs")).max() <= 10.0
+    lib.oracle_learner_destroy(L)
+    c.close()
+
+
+# ------------------------------------------------------------------ weights I/O (graph file, checkpoint)
+def test_graph_and_checkpoint_io(core_mod, init_weights, ckpt_weights, tmp_path):
+    from ppo_cpp_b200.meta_graph import CKPT_ORDER, write_meta_txt
+    tensors, flat = init_weights
+    path = str(tmp_path / "g.meta.txt")
+    write_meta_txt(path, tensors, ent_coef=0.0007160293171182275)
+    c = make_core(core_mod, None, n_envs=4, n_steps=8, nminibatches=4)
+    c.load_meta_txt(path)
+    assert np.array_equal(c.get_tensor("params"), flat)
+    assert np.array_equal(c.get_tensor("model/pi_fc1/w"), tensors["model/pi_fc1/w"].ravel())
+    ck, ckflat = ckpt_weights
+    prefix = str(tmp_path / "run.pkl.71")
+    np.concatenate([ck[n].ravel() for n in CKPT_ORDER]).astype("<f4").tofile(prefix + ".data-00000-of-00001")
+    c.load_checkpoint_data(prefix)
+    assert np.array_equal(c.get_tensor("params"), ckflat)
+    c.save_checkpoint_data(str(tmp_path / "again"))
+    assert open(prefix + ".data-00000-of-00001", "rb").read() == open(str(tmp_path / "again") + ".data-00000-of-00001", "rb").read()
+    with pytest.raises(core_mod.PPOError):
+        c.load_meta_txt(str(tmp_path / "missing.meta.txt"))
+    c.close()
+    wide = core_mod.PPOCore(hidden1=64, hidden2=64, n_envs=4, n_steps=8, nminibatches=4)
+    with pytest.raises(core_mod.PPOError, match="MLP"):
+        wide.load_meta_txt(path)  # shape mismatch is an error, not a silent reshape
+    wide.init_orthogonal(3)
+    w = wide.get_tensor("model/pi_fc1/w").reshape(64, 64)
+    assert np.allclose(w.T @ w, 2 * np.eye(64), atol=1e-4)  # orthogonal, gain sqrt(2)
+    wide.close()
