@@ -503,6 +503,9 @@ __global__ void __launch_bounds__(NT) train_tile_kernel(const TrainArgs a) {
         L[L_ENT] = ent;
         L[5] = 0.f; L[6] = 0.f; L[7] = 0.f;
     }
+    // loss = pg_loss - entropy*ent_coef + vf_loss*vf_coef: d(-ent_coef*entropy)/dlogstd_j = -ent_coef, added once
+    // (a.ent_coef is already divided by the number of ranks whose slabs get summed)
+    if (blockIdx.x == 0 && tid < d.A) my[d.off[T_LOGSTD] + tid] -= a.ent_coef;  // same thread wrote it in tile_rowsum
 }
 
 }  // namespace ppo

@@ -994,7 +994,7 @@ static int prepare_epoch(ppo_core* c, const int* perm_pinned_or_host) {
 static int launch_train_kernel(ppo_core* c, TrainArgs& a) {
     a.d = c->d;
     a.params = c->params;
-    a.ent_coef = c->desc.ent_coef;
+    a.ent_coef = c->desc.ent_coef / (float)c->desc.world_size;
     a.vf_coef = c->desc.vf_coef;
     a.partial = c->partial;
     a.PS = c->PS;
@@ -1175,7 +1175,7 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
                 a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
                 a.gather = c->gather; a.mbstats = c->mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
                 a.invB = 1.0f / (float)c->B_global; a.cliprange = 0.2f;
-                a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
+                a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
                 const int tm = c->tm, ntiles = (a.count + tm - 1) / tm, grid = std::max(1, std::min(ntiles, c->max_train_grid));
                 if (w == "train_fwdbwd") {
                     if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
