@@ -16,6 +16,7 @@
 #include "host_rand.h"
 #include "kernels_misc.cuh"
 #include "kernels_mlp.cuh"
+#include "kernels_mlp2.cuh"
 #include "meta_parser.h"
 
 using namespace ppo;
@@ -80,6 +81,8 @@ struct NcclApi {
 NcclApi g_nccl;
 }  // namespace
 
+constexpr int F_TM_TRAIN = 64, F_NT_TRAIN = 512, F_TM_POLICY = 32, F_NT_POLICY = 256;
+
 // ------------------------------------------------------------------------------------------------ the core
 enum { B_OBS, B_RETURNS, B_DONES, B_ACTIONS, B_VALUES, B_NEGLOGP, B_TRUE_REW, B_UNNORM_REW, B_COUNT };
 static const char* const kBufNames[B_COUNT] = {"obs", "returns", "dones", "actions", "values", "neglogpacs",
@@ -90,7 +93,9 @@ struct ppo_core {
     NetDims d{};
     cudaStream_t stream = nullptr;
     int sm_count = 0;
-    int tm = 64;          // tile size of the MLP kernels
+    int tm = 64;          // tile size of the generic (T family) MLP kernels
+    bool fused = false;   // F family usable: weights + one tile fit in shared memory, H1 % 4 == H2 % 4 == 0
+    size_t fused_train_smem = 0, fused_policy_smem = 0;
     int max_train_grid = 0;
     int PS = 0;           // partial slab width = P + L_PAD
 
@@ -337,6 +342,22 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaStreamCreate failed"); break; }
         st = (c->tm == 64) ? set_smem_attrs<64>(c->d) : set_smem_attrs<32>(c->d);
         if (st != PPO_OK) break;
+        {
+            FLayout lt, lp;
+            lt.init(c->d, F_TM_TRAIN, true);
+            lp.init(c->d, F_TM_POLICY, false);
+            c->fused_train_smem = (size_t)lt.total * sizeof(float);
+            c->fused_policy_smem = (size_t)lp.total * sizeof(float);
+            c->fused = (c->d.H1 % 4 == 0) && (c->d.H2 % 4 == 0) && c->fused_train_smem <= max_smem && c->fused_policy_smem <= max_smem &&
+                       getenv("PPO_DISABLE_FUSED") == nullptr;
+            if (c->fused) {
+                if (cudaFuncSetAttribute(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fused_train_smem) != cudaSuccess ||
+                    cudaFuncSetAttribute(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fused_policy_smem) != cudaSuccess) {
+                    st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(fused kernels) failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    break;
+                }
+            }
+        }
         st = core_alloc(c);
     } while (0);
     if (st != PPO_OK) {
@@ -533,6 +554,13 @@ static int launch_policy(ppo_core* c, PolicyArgs& a) {
     a.seed = c->desc.seed;
     a.env_id0 = (uint32_t)c->desc.env_offset;
     a.step_ctr = c->step_ctr;
+    if (c->fused) {
+        const int ntiles = (a.n + F_TM_POLICY - 1) / F_TM_POLICY;
+        const int grid = std::max(1, std::min(ntiles, c->sm_count * 2));
+        LAUNCH(c, (policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>), grid, F_NT_POLICY, c->fused_policy_smem, a);
+        CU(cudaGetLastError());
+        return PPO_OK;
+    }
     const int tm = c->tm;
     const int ntiles = (a.n + tm - 1) / tm;
     const int grid = std::max(1, std::min(ntiles, c->sm_count * 4));
@@ -998,10 +1026,11 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a) {
     a.vf_coef = c->desc.vf_coef;
     a.partial = c->partial;
     a.PS = c->PS;
-    const int tm = c->tm;
+    const int tm = c->fused ? F_TM_TRAIN : c->tm;
     const int ntiles = (a.count + tm - 1) / tm;
-    const int grid = std::max(1, std::min(ntiles, c->max_train_grid));
-    if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
+    const int grid = std::max(1, std::min(ntiles, c->fused ? c->sm_count : c->max_train_grid));
+    if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
+    else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
     else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
     LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
     CU(cudaGetLastError());
@@ -1176,9 +1205,11 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
                 a.gather = c->gather; a.mbstats = c->mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
                 a.invB = 1.0f / (float)c->B_global; a.cliprange = 0.2f;
                 a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
-                const int tm = c->tm, ntiles = (a.count + tm - 1) / tm, grid = std::max(1, std::min(ntiles, c->max_train_grid));
+                const int tm = c->fused ? F_TM_TRAIN : c->tm, ntiles = (a.count + tm - 1) / tm;
+                const int grid = std::max(1, std::min(ntiles, c->fused ? c->sm_count : c->max_train_grid));
                 if (w == "train_fwdbwd") {
-                    if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
+                    if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
+                    else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
                     else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
                 } else {
                     LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
