@@ -483,3 +483,19 @@ def test_graph_and_checkpoint_io(core_mod, init_weights, ckpt_weights, tmp_path)
     w = wide.get_tensor("model/pi_fc1/w").reshape(64, 64)
     assert np.allclose(w.T @ w, 2 * np.eye(64), atol=1e-4)  # orthogonal, gain sqrt(2)
     wide.close()
+
+
+# ------------------------------------------------------------------ multi-GPU
+def test_two_gpu_sharded_run_equals_single_gpu():
+    """Runs tests/mgpu_check.py under torchrun when the box has >= 2 GPUs (gpurun --gpus 2)."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
