@@ -1,6 +1,8 @@
 // HBM-bound kernels of the path: synthetic env, VecNormalize, GAE, advantage statistics,
 // gradient reduction, global-norm clip + Adam, layout conversion.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "device_common.cuh"
 
 namespace ppo {
@@ -475,6 +477,94 @@ __global__ void adam_kernel(const AdamArgs a) {
     a.m[i] = m;
     a.v[i] = v;
     a.params[i] = __fsub_rn(a.params[i], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+}
+
+// Fused (single GPU, small P): column-reduce the CTA slabs + global norm + clip + Adam in ONE cooperative launch.
+// Block = 64 columns x 4 row groups; phase 1 sums the G slabs (fixed order: 4 interleaved row groups, combined in
+// double) and publishes per-block sum of squares; grid.sync(); phase 2 computes the norm from the block partials
+// and applies Adam to the block's own columns straight from registers.
+struct ReduceAdamArgs {
+    const float* partial;
+    int G, PS;
+    float* grad;  // [PS] written for inspection / loss sums
+    double* sq_partial;
+    AdamArgs adam;
+};
+
+__global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const ReduceAdamArgs r) {
+    namespace cg = cooperative_groups;
+    __shared__ float part[4][64];
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + lane_c;
+    float acc = 0.f;
+    if (c < r.PS) {
+        const float* p = r.partial + c;
+        int g = rg;
+#pragma unroll 1
+        for (; g + 28 < r.G; g += 32) {  // 8 independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(g + 4 * u) * r.PS];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; g < r.G; g += 4) acc += p[(size_t)g * r.PS];
+    }
+    part[rg][lane_c] = acc;
+    __syncthreads();
+    float gsum = 0.f;
+    double q = 0.0;
+    if (rg == 0) {
+        const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
+        gsum = (float)t;
+        if (c < r.PS) r.grad[c] = gsum;
+        if (c < r.adam.P) q = (double)gsum * (double)gsum;
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) r.sq_partial[blockIdx.x] = red[0] + red[1];  // warps 0,1 hold rg == 0
+    __threadfence();
+    cg::this_grid().sync();
+    const AdamArgs& a = r.adam;
+    if (threadIdx.x < 32) {
+        double ss = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) ss += r.sq_partial[b];
+        // fixed-order combine: lane partials summed by a butterfly (same order in every block)
+        ss = warp_sum(ss);
+        if (threadIdx.x == 0) {
+            const float gnorm = (float)sqrt(ss);
+            const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
+            float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
+            if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
+            s_scale = scale;
+            if (blockIdx.x == 0) *a.gnorm_out = gnorm;
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // the block that owns the loss columns
+        const float* Ls = r.grad + a.P;
+        a.loss_row[0] = Ls[L_PG] * a.invB;
+        a.loss_row[1] = 0.5f * (Ls[L_VF] * a.invB);
+        a.loss_row[2] = Ls[L_ENT] * a.inv_world;
+        a.loss_row[3] = 0.5f * (Ls[L_KL] * a.invB);
+        a.loss_row[4] = Ls[L_CLIP] * a.invB;
+        a.bpow_out[0] = __fmul_rn(a.bpow_in[0], a.beta1);
+        a.bpow_out[1] = __fmul_rn(a.bpow_in[1], a.beta2);
+    }
+    if (rg == 0 && c < a.P) {
+        const float b1p = a.bpow_in[0], b2p = a.bpow_in[1];
+        const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+        const float g = __fmul_rn(gsum, s_scale);
+        float m = a.m[c], v = a.v[c];
+        m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+        v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+        a.m[c] = m;
+        a.v[c] = v;
+        a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+    }
 }
 
 // mean over the rows of the per-step loss table (colwise().mean(), ppo2.hpp:335)

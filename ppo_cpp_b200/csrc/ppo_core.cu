@@ -123,6 +123,16 @@ struct ppo_core {
     double* sq_partial = nullptr;
     int n_sq_blocks = 0;
     bool perm_set = false;
+    bool coop = false;        // fused cooperative reduce+Adam kernel usable (single GPU, grid co-resident)
+    int coop_grid = 0;
+    bool use_graph = false;   // replay each epoch's launches as a CUDA graph
+    struct EpochGraph {
+        cudaGraphExec_t exec = nullptr;
+        float lr = 0.f, cliprange = 0.f;
+        int bpow_slot = -1;
+        uint64_t kernels = 0;
+    };
+    std::vector<EpochGraph> graphs;
 
     GlibcRand rng{1};
     std::vector<int> perm_host;
@@ -228,6 +238,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     void* dev_ptrs[] = {c->params, c->adam_m, c->adam_v, c->bpow, c->st.obs_mean, c->st.obs_var, c->st.obs_count,
                         c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
                         c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
@@ -359,6 +371,21 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             }
         }
         st = core_alloc(c);
+        if (st != PPO_OK) break;
+        {
+            int per_sm = 0, coop_ok = 0;
+            cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, desc->device);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grad_reduce_adam_coop_kernel, 256, 0);
+            c->coop_grid = (c->PS + 63) / 64;
+            c->coop = coop_ok && desc->world_size == 1 && c->coop_grid <= per_sm * c->sm_count && getenv("PPO_DISABLE_COOP") == nullptr;
+            if (c->coop && c->coop_grid > c->n_sq_blocks) {  // sq_partial is sized for 256-column blocks
+                cudaFree(c->sq_partial);
+                c->sq_partial = nullptr;
+                if (cudaMalloc(&c->sq_partial, sizeof(double) * c->coop_grid) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_partial) failed"); break; }
+            }
+            c->use_graph = desc->world_size == 1 && getenv("PPO_DISABLE_GRAPH") == nullptr;
+            c->graphs.resize(std::max(1, desc->noptepochs));
+        }
     } while (0);
     if (st != PPO_OK) {
         char keep[1024];
@@ -1019,7 +1046,7 @@ static int prepare_epoch(ppo_core* c, const int* perm_pinned_or_host) {
     return PPO_OK;
 }
 
-static int launch_train_kernel(ppo_core* c, TrainArgs& a) {
+static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = true, int* grid_out = nullptr) {
     a.d = c->d;
     a.params = c->params;
     a.ent_coef = c->desc.ent_coef / (float)c->desc.world_size;
@@ -1032,7 +1059,8 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a) {
     if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
     else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
     else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
-    LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
+    if (with_reduce) LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
+    if (grid_out) *grid_out = grid;
     CU(cudaGetLastError());
     return PPO_OK;
 }
@@ -1050,7 +1078,24 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
     a.count = per_rank;
     a.invB = 1.0f / (float)c->B_global;
     a.cliprange = cliprange;
-    TRY(launch_train_kernel(c, a));
+    int train_grid = 0;
+    TRY(launch_train_kernel(c, a, !c->coop, &train_grid));
+    if (c->coop) {
+        ReduceAdamArgs r{};
+        r.partial = c->partial; r.G = train_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
+        AdamArgs& ad = r.adam;
+        ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
+        ad.nblk = c->coop_grid; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
+        ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
+        ad.bpow_in = c->bpow + c->bpow_slot * 2; ad.bpow_out = c->bpow + (c->bpow_slot ^ 1) * 2;
+        ad.invB = a.invB; ad.inv_world = 1.0f;
+        ad.loss_row = c->loss_rows + (size_t)loss_row * 5; ad.gnorm_out = c->gnorm;
+        void* kargs[] = {&r};
+        CU(cudaLaunchCooperativeKernel((void*)grad_reduce_adam_coop_kernel, dim3(c->coop_grid), dim3(256), kargs, 0, c->stream));
+        c->ctr.kernel_launches++;
+        c->bpow_slot ^= 1;
+        return PPO_OK;
+    }
     if (W > 1) {
         TRY(need_comm(c));
         TRY(nccl_check(g_nccl.AllReduce(c->grad, c->grad, c->PS, ncclFloat32C, ncclSumC, c->comm, c->stream), "ncclAllReduce(grad)"));
@@ -1081,8 +1126,43 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         c->rng.random_shuffle(c->perm_host.data(), nb);  // compounded across epochs (ppo2.hpp:288)
         int* pinned = c->perm_pinned + (size_t)e * nb;
         memcpy(pinned, c->perm_host.data(), sizeof(int) * (size_t)nb);
-        TRY(prepare_epoch(c, pinned));
-        for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
+        if (!c->use_graph) {
+            TRY(prepare_epoch(c, pinned));
+            for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
+            continue;
+        }
+        ppo_core::EpochGraph& eg = c->graphs[e];
+        if (!eg.exec || eg.lr != lr || eg.cliprange != cliprange || eg.bpow_slot != c->bpow_slot) {
+            if (eg.exec) {
+                cudaGraphExecDestroy(eg.exec);
+                eg.exec = nullptr;
+            }
+            const int slot0 = c->bpow_slot;
+            const uint64_t k0 = c->ctr.kernel_launches, h0 = c->ctr.h2d_bytes;
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int st = prepare_epoch(c, pinned);
+            for (int k = 0; k < M && st == PPO_OK; ++k) st = train_step_device(c, k, lr, cliprange, e * M + k);
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            eg.kernels = c->ctr.kernel_launches - k0;
+            c->ctr.kernel_launches = k0;  // nothing ran yet; replay accounts for them
+            c->ctr.h2d_bytes = h0;
+            c->bpow_slot = slot0;
+            if (st != PPO_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return st;
+            }
+            if (ce != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&eg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            eg.lr = lr; eg.cliprange = cliprange; eg.bpow_slot = slot0;
+        }
+        CU(cudaGraphLaunch(eg.exec, c->stream));
+        c->ctr.graph_launches++;
+        c->ctr.kernel_launches += eg.kernels;
+        c->ctr.h2d_bytes += sizeof(int) * (size_t)nb;
+        if (M & 1) c->bpow_slot ^= 1;
     }
     if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
     CU(cudaGetLastError());
