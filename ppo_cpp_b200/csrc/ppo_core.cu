@@ -133,6 +133,7 @@ struct ppo_core {
         uint64_t kernels = 0;
     };
     std::vector<EpochGraph> graphs;
+    EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
 
     GlibcRand rng{1};
     std::vector<int> perm_host;
@@ -240,6 +241,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (c->rollout_graph.exec) cudaGraphExecDestroy(c->rollout_graph.exec);
     void* dev_ptrs[] = {c->params, c->adam_m, c->adam_v, c->bpow, c->st.obs_mean, c->st.obs_var, c->st.obs_count,
                         c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
                         c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
@@ -951,9 +953,7 @@ extern "C" int ppo_synth_env_reset(ppo_core* c) {
     return ppo_runner_reset(c, c->raw_obs, PPO_DEVICE);
 }
 
-extern "C" int ppo_rollout_synthetic(ppo_core* c) {
-    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
-    CU(cudaSetDevice(c->desc.device));
+static int rollout_synthetic_enqueue(ppo_core* c) {
     const int N = c->desc.n_envs;
     for (int t = 0; t < c->desc.n_steps; ++t) {
         TRY(runner_act_device(c, t));
@@ -962,6 +962,41 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
                            slab(c, B_UNNORM_REW, t), true));
     }
     return ppo_runner_finish(c);
+}
+
+extern "C" int ppo_rollout_synthetic(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    CU(cudaSetDevice(c->desc.device));
+    if (!c->use_graph) return rollout_synthetic_enqueue(c);
+    // every launch argument of the rollout is a fixed device address (the Philox step counter lives on the device),
+    // so the whole rollout is captured once and replayed; the training flag is baked into the captured launches
+    ppo_core::EpochGraph& g = c->rollout_graph;
+    if (!g.exec || g.bpow_slot != c->desc.training) {
+        if (g.exec) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        const uint64_t k0 = c->ctr.kernel_launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int st = rollout_synthetic_enqueue(c);
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        g.kernels = c->ctr.kernel_launches - k0;
+        c->ctr.kernel_launches = k0;
+        if (st != PPO_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return st;
+        }
+        if (ce != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaStreamEndCapture(rollout) failed: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaGraphInstantiate(rollout) failed: %s", cudaGetErrorString(ie));
+        g.bpow_slot = c->desc.training;
+    }
+    CU(cudaGraphLaunch(g.exec, c->stream));
+    c->ctr.graph_launches++;
+    c->ctr.kernel_launches += g.kernels;
+    return PPO_OK;
 }
 
 static int buf_index(const char* name) {
