@@ -332,6 +332,7 @@ struct TrainArgs {
     float cliprange, ent_coef, vf_coef;
     float* partial;  // [gridDim.x][PS]
     int PS;
+    long long* prof;  // optional [2][32] phase timestamps of CTA 0 of each tower (U family, PPO_UMMA_PROF=1)
 };
 
 template <int TM>

@@ -1,0 +1,779 @@
+// "U family": tcgen05 (5th-gen tensor core) train kernel for the [64,64] MLP (H1 == H2 == 64, obs/act widths as template parameters, 18/18 instantiated).
+//
+// Replaces the loss / autodiff sub-graph of one PPO2::_train_step (ppo2/ppo2.hpp:430-470, GRAPH:6889-23699) for a
+// minibatch; math and TF tie-breaking rules are those of SURVEY §3.5b, identical to train_fused_kernel.
+//
+// Mapping to the hardware
+//   * one CTA = one tower (blockIdx.y: 0 = pi, 1 = V) of one tile of 128 samples (= the 128 TMEM lanes); the towers
+//     share nothing but the advantage / return inputs, so a minibatch of 8192 samples is 64 tiles x 2 towers = 128 CTAs.
+//   * every GEMM of the forward and the hand-derived backward pass runs on tcgen05.mma (kind::f16, bf16 operands,
+//     fp32 accumulators in TMEM).  fp32 parity (1e-5) is kept by splitting every fp32 operand x into three bf16
+//     pieces x = p0 + p1 + p2 (24 mantissa bits) and issuing the six products p0p0, p0p1, p1p0, p1p1, p0p2, p2p0
+//     (dropped terms are < 2^-24 relative).  kind::tf32 was measured first (tools/probe/umma_probe*.cu): it silently
+//     produces zeros for MN-major operands on sm_100a, and the dW GEMMs need MN-major views; bf16 supports both.
+//   * operands live in shared memory as [rows][64 bf16] blocks in the canonical SWIZZLE_128B layout, so the SAME bytes
+//     serve as K-major operand (forward: act x W, backward: dY x W^T) and as MN-major operand (dW = act^T x dY, reduced
+//     over the 128 samples of the tile).  dY overwrites the activation it was derived from in place.
+//   * bias gradients and the logstd gradient are column sums over samples: one extra N=8 MMA against a block whose
+//     first row is ones.  The V head (N = 1) is a dot product in the epilogue; its weight gradient is again an N=8 MMA.
+//   * weight gradients accumulate in TMEM across the tiles a CTA processes and are written once to the CTA's slab.
+//   * the epilogues (tanh, loss, tanh', bf16 splitting) run on 8 warps: warp w owns TMEM lanes 32*(w&3).. and the
+//     32-column half (w>>2) of a 64-wide accumulator; activations stay in registers between forward and backward.
+//   * accuracy: the tensor core truncates (RZ) at every accumulation, a bias that grows with the number of MMAs chained
+//     into one accumulator and that the value loss amplifies (v - R cancels over the batch).  The leading product p0p0
+//     therefore accumulates alone, the five small cross products go to a second TMEM accumulator (2^-8 of the
+//     magnitude, so 2^-8 of the truncation error) and the epilogue adds the two in fp32 (round to nearest).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "kernels_mlp2.cuh"
+
+namespace ppo {
+namespace umma {
+
+constexpr int TM = 128;   // samples per tile
+constexpr int NTH = 256;  // threads per CTA
+constexpr int HID = 64;   // hidden width handled by this family
+
+// ---- shared memory map (bytes from a 1024-aligned base)
+constexpr uint32_t ACT_PIECE = TM * 128;        // [128 x 64] bf16 = 16 KB
+constexpr uint32_t ACT_BLOCK = 3 * ACT_PIECE;   // three pieces
+constexpr uint32_t W0_PIECE = 32 * 128;         // [32 x 64] bf16 (rows: O inputs, bias row, zero padding)
+constexpr uint32_t W1_PIECE = 64 * 128;         // [64 x 64]
+constexpr uint32_t WP_PIECE = 64 * 128;         // [64 x 64], columns >= A are zero
+constexpr uint32_t ROW8_PIECE = 2 * 1024;       // [8 x 128] bf16, K-major operand over the 128 samples
+constexpr uint32_t OFF_H1 = 0;
+constexpr uint32_t OFF_H2 = OFF_H1 + ACT_BLOCK;
+constexpr uint32_t OFF_Y = OFF_H2 + ACT_BLOCK;  // X' (obs + ones column), later [dMU | dLS], later X' again
+constexpr uint32_t OFF_W0 = OFF_Y + ACT_BLOCK;
+constexpr uint32_t OFF_W1 = OFF_W0 + 3 * W0_PIECE;
+constexpr uint32_t OFF_WP = OFF_W1 + 3 * W1_PIECE;   // pi head weights; the V tower keeps its dv rows here
+constexpr uint32_t OFF_ONES = OFF_WP + 3 * WP_PIECE;
+constexpr uint32_t OFF_F32 = OFF_ONES + ROW8_PIECE;  // fp32 vectors
+constexpr uint32_t F32_B1 = 0, F32_BH = 64, F32_WV = 96, F32_SD = 160, F32_LS = 192, F32_MISC = 224, F32_PV = 256,
+                   F32_DV = 512, F32_RED = 640, F32_ISD = 704, F32_COUNT = 736;
+constexpr uint32_t OFF_BAR = OFF_F32 + F32_COUNT * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64 + 1024;  // + alignment slack
+
+// ---- TMEM columns: every accumulator has a twin ("+ XC") for the small cross products
+constexpr uint32_t ACC_WORK = 0, ACC_WORK_C = 64;  // Z1, Z2, MU (first 32 columns), dH2, dH1
+constexpr uint32_t ACC_DWP = 128, ACC_DWP_C = 160, ACC_CS = 192, ACC_CS_C = 200, ACC_DW1 = 208, ACC_DW1_C = 272, ACC_DB1 = 336,
+                   ACC_DB1_C = 344, ACC_DW0 = 352, ACC_DW0_C = 384, TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of the 16-byte chunk j (8 bf16 columns) of row r inside a SWIZZLE_128B [R x 64] bf16 block
+__device__ __forceinline__ uint32_t chunk_off(int r, int j) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = f32, A = B = bf16
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// One operand of a GEMM: descriptor of piece 0 / k-step 0 plus strides (in 16-byte units).
+// k-step ks (16 elements of K) sits at (ks >> 2) * k_hi + (ks & 3) * k_lo.
+struct Operand {
+    uint64_t desc;
+    uint32_t piece, k_lo, k_hi;
+};
+// K-major view (mn = row, k = column) of a [rows x (64 * nblk)] block
+__device__ __forceinline__ Operand op_kmajor(uint32_t base, uint32_t piece_bytes, int rows) {
+    return Operand{make_desc(base, 16, 1024), piece_bytes >> 4, 32 >> 4, (uint32_t)((rows >> 3) * 1024) >> 4};
+}
+// MN-major view (k = row, mn = column) of a [rows x 64] block: one k-step = 16 rows = 2 KB
+__device__ __forceinline__ Operand op_mnmajor(uint32_t base, uint32_t piece_bytes, int rows) {
+    return Operand{make_desc(base, (uint32_t)((rows >> 3) * 1024), 1024), piece_bytes >> 4, 2048 >> 4, 8192 >> 4};
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D (+)= A * B with split operands: the leading product goes to `dm`, the cross products to `dc`.
+// NPB == 3: six products (both operands in three pieces); NPB == 1: B is exact in bf16 (ones), three products.
+template <int NPB, int KSTEPS>
+__device__ __forceinline__ void issue_gemm(uint32_t dm, uint32_t dc, const Operand& A, const Operand& B, uint32_t idesc, bool accumulate) {
+    const uint32_t acc0 = accumulate ? 1u : 0u;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t a = A.desc + (uint64_t)((ks >> 2) * A.k_hi + (ks & 3) * A.k_lo);
+        const uint64_t b = B.desc + (uint64_t)((ks >> 2) * B.k_hi + (ks & 3) * B.k_lo);
+        const uint32_t acc = ks ? 1u : acc0;
+        mma_bf16(dm, a, b, idesc, acc);
+        if (NPB == 3) {
+            mma_bf16(dc, a, b + B.piece, idesc, acc);
+            mma_bf16(dc, a + A.piece, b, idesc, 1u);
+            mma_bf16(dc, a + A.piece, b + B.piece, idesc, 1u);
+            mma_bf16(dc, a, b + 2 * B.piece, idesc, 1u);
+            mma_bf16(dc, a + 2 * A.piece, b, idesc, 1u);
+        } else {
+            mma_bf16(dc, a + A.piece, b, idesc, acc);
+            mma_bf16(dc, a + 2 * A.piece, b, idesc, 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define PPO_TMEM_LD32(taddr, r)                                                                                                        \
+    asm volatile(                                                                                                                      \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                      \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),      \
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),         \
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),         \
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                           \
+        : "r"(taddr))
+#define PPO_TMEM_LD8(taddr, r)                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+                 : "r"(taddr))
+
+// v[0..32) = main + cross accumulator: 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32_sum(uint32_t tmain, uint32_t tcross, float* v) {
+    uint32_t r[32], s[32];
+    PPO_TMEM_LD32(tmain, r);
+    PPO_TMEM_LD32(tcross, s);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
+}
+__device__ __forceinline__ void tmem_ld8_sum(uint32_t tmain, uint32_t tcross, float* v) {
+    uint32_t r[8], s[8];
+    PPO_TMEM_LD8(tmain, r);
+    PPO_TMEM_LD8(tcross, s);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
+}
+
+// x0, x1 -> three packed bf16 pairs (x0 in the low half = lower address)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+    p0 = *reinterpret_cast<uint32_t*>(&b);
+    const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+    b = __floats2bfloat162_rn(r0, r1);
+    p1 = *reinterpret_cast<uint32_t*>(&b);
+    const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
+    b = __floats2bfloat162_rn(s0, s1);
+    p2 = *reinterpret_cast<uint32_t*>(&b);
+}
+// eight consecutive columns (one 16-byte chunk) -> the three pieces of a block
+__device__ __forceinline__ void store_chunk(uint8_t* block, uint32_t piece_bytes, uint32_t off, const float* x) {
+    uint4 q0, q1, q2;
+    split_pair(x[0], x[1], q0.x, q1.x, q2.x);
+    split_pair(x[2], x[3], q0.y, q1.y, q2.y);
+    split_pair(x[4], x[5], q0.z, q1.z, q2.z);
+    split_pair(x[6], x[7], q0.w, q1.w, q2.w);
+    *reinterpret_cast<uint4*>(block + off) = q0;
+    *reinterpret_cast<uint4*>(block + piece_bytes + off) = q1;
+    *reinterpret_cast<uint4*>(block + 2 * piece_bytes + off) = q2;
+}
+__device__ __forceinline__ void zero_chunk(uint8_t* block, uint32_t piece_bytes, uint32_t off) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(block + off) = z;
+    *reinterpret_cast<uint4*>(block + piece_bytes + off) = z;
+    *reinterpret_cast<uint4*>(block + 2 * piece_bytes + off) = z;
+}
+// 32 consecutive columns [32 * half, 32 * half + 32) of row r of an activation block
+__device__ __forceinline__ void store_row32(uint8_t* block, int r, int half, const float* x) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_chunk(block, ACT_PIECE, chunk_off(r, 4 * half + j), x + 8 * j);
+}
+
+// Observation row of a sample, as the registers of the two threads (h = 0, 1) that stage it: columns [16h, 16h+16)
+template <int O>
+struct ObsRegs {
+    float2 x[8];
+    __device__ __forceinline__ void load(const float* __restrict__ obs, long grow, int h, bool valid) {
+        const float2* src = reinterpret_cast<const float2*>(obs + grow * O);  // rows are 8-byte aligned (O even)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = 16 * h + 2 * i;
+            x[i] = (valid && c < O) ? __ldg(src + (c >> 1)) : make_float2(0.f, 0.f);
+        }
+    }
+    // X' = [obs | 1 | 0 ...]: the ones column folds the layer-0 bias into the GEMM and yields its gradient
+    __device__ __forceinline__ void store(uint8_t* Y, int r, int h) const {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[2 * i] = x[i].x;
+            v[2 * i + 1] = x[i].y;
+        }
+        if (O >= 16 * h && O < 16 * h + 16) v[O - 16 * h] = 1.f;
+        store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h), v);
+        store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h + 1), v + 8);
+    }
+};
+
+#define UMMA_PROF()                                                                                              \
+    do {                                                                                                         \
+        if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 32) a.prof[tower * 32 + prof_i++] = clock64();      \
+    } while (0)
+
+template <int O, int A>
+__global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
+    static_assert(O % 2 == 0 && O >= 2 && O <= 30 && A % 2 == 0 && A >= 2 && A <= 32, "unsupported obs/act width");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const NetDims& d = a.d;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+    const int q = warp & 3, half = warp >> 2;                // TMEM lane quarter / column half
+    const int row = q * 32 + lane;                           // sample row of this thread in the epilogues
+    const int tower = blockIdx.y;                            // 0 = pi, 1 = V
+    int prof_i = 0;
+    UMMA_PROF();  // kernel entry
+
+    uint8_t* sH1 = smem + OFF_H1;
+    uint8_t* sH2 = smem + OFF_H2;
+    uint8_t* sY = smem + OFF_Y;
+    float* f32 = reinterpret_cast<float*>(smem + OFF_F32);
+    const uint32_t barA = sbase + OFF_BAR, barB = barA + 8;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+    const int ntiles = (a.count + TM - 1) / TM;
+
+    // ---------------------------------------------------------------- inputs of the first tile (latency overlaps the setup)
+    // Thread (gr = tid & 127, gh = tid >> 7) stages half of observation row gr; for column half 0, gr == row.
+    const int gr = tid & 127, gh = tid >> 7;
+    ObsRegs<O> xin;
+    long grow = 0;
+    bool gvalid = false;
+    float s_adv = 0.f, s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
+    auto load_inputs = [&](int tile) {
+        const int s0 = a.slot0 + tile * TM;
+        const int nv = min(TM, a.slot0 + a.count - s0);
+        gvalid = tile < ntiles && gr < nv;
+        grow = gvalid ? (long)(a.gather ? __ldg(a.gather + s0 + gr) : (s0 + gr)) : 0;
+        xin.load(a.obs, grow, gh, gvalid);
+        s_adv = s_ret = s_oldn = s_oldv = 0.f;
+        if (gh == 0 && gvalid) {
+            s_ret = __ldg(a.ret + grow);
+            s_oldv = __ldg(a.val + grow);
+            s_oldn = __ldg(a.nlp + grow);
+            if (a.adv_direct) {
+                s_adv = __ldg(a.adv_direct + s0 + gr);
+            } else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
+                const float2 st = __ldg(a.mbstats);
+                s_adv = __fdiv_rn(__fsub_rn(__fsub_rn(s_ret, s_oldv), st.x), st.y);
+            }
+        }
+    };
+    load_inputs(blockIdx.x);
+
+    // ---------------------------------------------------------------- one-time setup
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barB));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        // weights -> three bf16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
+        const float* P = a.params;
+        const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
+        const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
+        const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+        float4 w1v[2][2], w0v[2];
+        float wpv[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {  // W1: 64 rows x 8 chunks = 512 tasks
+            const int e = tid + NTH * i, r = e >> 3, j = e & 7;
+            w1v[i][0] = __ldg(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j));
+            w1v[i][1] = __ldg(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j + 4));
+        }
+        {  // W0': rows < O weights, row O bias, rows up to 31 zero: 32 rows x 8 chunks = 256 tasks
+            const int r = tid >> 3, j = tid & 7;
+            const float* src = r < O ? (W0 + r * HID + 8 * j) : (B0 + 8 * j);
+            const bool nz = r <= O;
+            w0v[0] = nz ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w0v[1] = nz ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tower == 0) {  // Wpi [64 x A] -> chunks 0..3 of every row (columns >= A zero): 256 tasks
+            const int r = tid >> 2, j = tid & 3;
+            const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? __ldg(src + k) : 0.f;
+        }
+        float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
+        if (tid < HID) {
+            b1 = __ldg(P + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
+            wv = __ldg(P + d.off[T_VF_W] + tid);
+        }
+        if (tid < 32) {
+            ls = tid < A ? __ldg(P + d.off[T_LOGSTD] + tid) : 0.f;
+            bh = tid < A ? __ldg(P + d.off[T_PI_B] + tid) : 0.f;
+            bv = __ldg(P + d.off[T_VF_B]);
+        }
+        // ---- consume
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + NTH * i, r = e >> 3, j = e & 7;
+            const float x[8] = {w1v[i][0].x, w1v[i][0].y, w1v[i][0].z, w1v[i][0].w, w1v[i][1].x, w1v[i][1].y, w1v[i][1].z, w1v[i][1].w};
+            store_chunk(smem + OFF_W1, W1_PIECE, chunk_off(r, j), x);
+        }
+        {
+            const int r = tid >> 3, j = tid & 7;
+            const float x[8] = {w0v[0].x, w0v[0].y, w0v[0].z, w0v[0].w, w0v[1].x, w0v[1].y, w0v[1].z, w0v[1].w};
+            store_chunk(smem + OFF_W0, W0_PIECE, chunk_off(r, j), x);
+        }
+        if (tower == 0) {
+            const int r = tid >> 2, j = tid & 3;
+            store_chunk(smem + OFF_WP, WP_PIECE, chunk_off(r, j), wpv);
+        } else {
+            for (int i = tid; i < 3 * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
+        }
+        // ones block: row 0 of each 8-row group = 1.0 (bf16 0x3F80), rows 1..7 = 0
+        if (tid < (int)ROW8_PIECE / 16) {
+            const uint32_t v = ((tid & 63) < 8) ? 0x3F803F80u : 0u;
+            reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
+        }
+        if (tid < HID) {
+            f32[F32_B1 + tid] = b1;
+            f32[F32_WV + tid] = wv;
+        }
+        if (tid < 32) {
+            f32[F32_BH + tid] = bh;
+            f32[F32_LS + tid] = ls;
+            f32[F32_SD + tid] = expf(ls);
+            f32[F32_ISD + tid] = 1.f / expf(ls);
+            const float sl = warp_sum(ls);  // lanes >= A contribute 0
+            if (tid == 0) {
+                f32[F32_MISC + 0] = bv;
+                f32[F32_MISC + 1] = sl;
+            }
+        }
+    }
+    xin.store(sY, gr, gh);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    UMMA_PROF();  // setup done, X' of the first tile staged
+
+    // operand views
+    const Operand opY_k = op_kmajor(sbase + OFF_Y, ACT_PIECE, TM);      // X' / dMU as A (m = sample)
+    const Operand opY_mn = op_mnmajor(sbase + OFF_Y, ACT_PIECE, TM);    // X' / [dMU|dLS] reduced over samples
+    const Operand opH1_k = op_kmajor(sbase + OFF_H1, ACT_PIECE, TM);
+    const Operand opH1_mn = op_mnmajor(sbase + OFF_H1, ACT_PIECE, TM);
+    const Operand opH2_k = op_kmajor(sbase + OFF_H2, ACT_PIECE, TM);
+    const Operand opH2_mn = op_mnmajor(sbase + OFF_H2, ACT_PIECE, TM);
+    const Operand opW0_f = op_mnmajor(sbase + OFF_W0, W0_PIECE, 32);    // forward: B(n = out, k = in)
+    const Operand opW1_f = op_mnmajor(sbase + OFF_W1, W1_PIECE, 64);
+    const Operand opW1_b = op_kmajor(sbase + OFF_W1, W1_PIECE, 64);     // backward: B(n = in, k = out)
+    const Operand opWP_f = op_mnmajor(sbase + OFF_WP, WP_PIECE, 64);
+    const Operand opWP_b = op_kmajor(sbase + OFF_WP, WP_PIECE, 64);
+    const Operand opDV = op_kmajor(sbase + OFF_WP, ROW8_PIECE, 8);      // V tower: row 0 = dv over the samples
+    const Operand opONES = op_kmajor(sbase + OFF_ONES, ROW8_PIECE, 8);
+    const uint32_t id_f64 = make_idesc(128, 64, 0, 1);    // act(K-major) x W(MN view), N = 64
+    const uint32_t id_f32 = make_idesc(128, 32, 0, 1);    // head forward, N = 32
+    const uint32_t id_b64 = make_idesc(128, 64, 0, 0);    // dY(K-major) x W(K-major view)
+    const uint32_t id_w64 = make_idesc(64, 64, 1, 1);     // dY^T x act over samples, N = 64
+    const uint32_t id_w32 = make_idesc(64, 32, 1, 1);     // N = 32
+    const uint32_t id_s8 = make_idesc(64, 8, 1, 0);       // column sums / V head: MN-major A x K-major [8 x 128] B
+
+    const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+    uint32_t phA = 0, phB = 0;
+    float l_0 = 0.f, l_1 = 0.f, l_2 = 0.f, l_dbv = 0.f;  // pi: pg, kl, clipfrac sums; V: vf sum, dbv
+    bool accw = false;
+    float h1r[32], h2r[32];
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // inputs of this tile (the registers are refilled with the next tile's before the end of the loop);
+        // gr == row for both column halves, so grow is the rollout row of this thread's sample
+        const float c_adv = s_adv, c_ret = s_ret, c_oldn = s_oldn, c_oldv = s_oldv;
+        const long c_grow = grow;
+        const bool valid = gvalid;
+
+        // ---- layer 0: Z1 = X' * W0'  (bias through the ones column)
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                issue_gemm<3, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opW0_f, id_f64, false);
+                umma_commit(barA);
+            }
+            __syncwarp();
+        }
+        mbar_wait(barA, phA); phA ^= 1;
+        tc_fence_after();
+        UMMA_PROF();
+        {
+            float v[32];
+            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h1r[j] = tanhf(v[j]);
+            store_row32(sH1, row, half, h1r);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        UMMA_PROF();
+
+        // ---- layer 1: Z2 = H1 * W1
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH1_k, opW1_f, id_f64, false);
+                umma_commit(barA);
+            }
+            __syncwarp();
+        }
+        // pi tower: the action row of the sample (both column halves need all of it for the loss stage)
+        float2 act2[A / 2];
+        if (tower == 0) {
+            const float2* src = reinterpret_cast<const float2*>(a.act + c_grow * A);
+#pragma unroll
+            for (int i = 0; i < A / 2; ++i) act2[i] = valid ? __ldg(src + i) : make_float2(0.f, 0.f);
+        }
+        mbar_wait(barA, phA); phA ^= 1;
+        tc_fence_after();
+        UMMA_PROF();
+        {
+            float v[32];
+            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
+            float pv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                h2r[j] = tanhf(v[j] + f32[F32_B1 + 32 * half + j]);
+                pv = fmaf(h2r[j], f32[F32_WV + 32 * half + j], pv);
+            }
+            store_row32(sH2, row, half, h2r);
+            if (tower == 1) f32[F32_PV + half * TM + row] = pv;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        UMMA_PROF();
+
+        if (tower == 0) {
+            // ---- pi head: MU = H2 * Wpi
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opWP_f, id_f32, false);
+                    umma_commit(barA);
+                }
+                __syncwarp();
+            }
+            mbar_wait(barA, phA); phA ^= 1;
+            tc_fence_after();
+            UMMA_PROF();
+            {
+                // loss stage (GRAPH:9428-11446).  Both column halves evaluate the sample's scalars; half 0 then emits
+                // dL/dmu (columns 0..31 of Y), half 1 the logstd contributions (columns 32..63).
+                float z[32];
+                float ss = 0.f;
+                {
+                    float mu[32];
+                    tmem_ld32_sum(tlane + ACC_WORK, tlane + ACC_WORK_C, mu);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        z[j] = 0.f;
+                        if (j < A) {
+                            const float aj = (j & 1) ? act2[j >> 1].y : act2[j >> 1].x;
+                            z[j] = (aj - (mu[j] + f32[F32_BH + j])) * f32[F32_ISD + j];  // (a - mu) / sigma
+                            ss += z[j] * z[j];
+                        }
+                    }
+                }
+                float g_nlp = 0.f;
+                // the scalars live in the threads of column half 0; half 1 gets them through shared memory
+                if (half == 0) {
+                    f32[F32_PV + row] = c_adv;
+                    f32[F32_PV + TM + row] = c_oldn;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float adv = f32[F32_PV + row], oldn = f32[F32_PV + TM + row];
+                if (valid) {
+                    const float nlp = (0.5f * ss + PPO_HALF_LOG_2PI * (float)A) + f32[F32_MISC + 1];
+                    const float ratio = expf(oldn - nlp);                          // GRAPH:10423-10447
+                    const float pg1 = -adv * ratio;
+                    const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);          // clip_by_value = max(min(x,hi),lo)
+                    const bool take1 = pg1 >= pg2;                                 // ties -> unclipped branch
+                    g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
+                    if (half == 0) {
+                        l_0 += take1 ? pg1 : pg2;
+                        const float dn = nlp - oldn;
+                        l_1 += dn * dn;
+                        l_2 += (fabsf(ratio - 1.f) > a.cliprange) ? 1.f : 0.f;
+                    }
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) z[j] = (j < A) ? g_nlp * (-z[j] * f32[F32_ISD + j]) : 0.f;  // dL/dmu
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) z[j] = (j < A) ? g_nlp * (1.f - z[j] * z[j]) : 0.f;  // d nlp / d logstd_j
+                }
+                store_row32(sY, row, half, z);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            UMMA_PROF();
+            // ---- backward through the head: dH2 = dMU * Wpi^T ; dWpi += H2^T * dMU ; column sums of [dMU | dLS]
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_gemm<3, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opWP_b, id_b64, false);
+                    umma_commit(barA);
+                    issue_gemm<3, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opY_mn, id_w32, accw);
+                    issue_gemm<1, 8>(tmem + ACC_CS, tmem + ACC_CS_C, opY_mn, opONES, id_s8, accw);
+                    umma_commit(barB);
+                }
+                __syncwarp();
+            }
+            mbar_wait(barA, phA); phA ^= 1;
+            tc_fence_after();
+            float v[32];
+            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h2r[j] * h2r[j]);
+            mbar_wait(barB, phB); phB ^= 1;  // dWpi has read H2
+            UMMA_PROF();
+            store_row32(sH2, row, half, v);  // dP2 in place of H2
+        } else {
+            // ---- V head (GRAPH:10213-10400): value, clipped value loss and dL/dv on the CUDA cores
+            if (half == 0) {
+                float dv = 0.f;
+                if (valid) {
+                    const float v = (f32[F32_PV + row] + f32[F32_PV + TM + row]) + f32[F32_MISC + 0];
+                    const float dvo = v - c_oldv;
+                    const float vc = c_oldv + fmaxf(fminf(dvo, a.cliprange), -a.cliprange);
+                    const float l1 = (v - c_ret) * (v - c_ret), l2 = (vc - c_ret) * (vc - c_ret);
+                    const bool tk = l1 >= l2;  // ties -> unclipped branch
+                    l_0 += tk ? l1 : l2;
+                    const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
+                    dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (v - c_ret) : (inr ? 2.f * (vc - c_ret) : 0.f));
+                    l_dbv += dv;
+                }
+                f32[F32_DV + row] = dv;
+                uint32_t p0, p1, p2;
+                split_pair(dv, 0.f, p0, p1, p2);
+                const uint32_t o = (uint32_t)((row >> 6) * 1024 + (((row & 63) >> 3) << 4) + (row & 7) * 2);  // row 0 of the [8 x 128] block
+                *reinterpret_cast<uint16_t*>(smem + OFF_WP + o) = (uint16_t)p0;
+                *reinterpret_cast<uint16_t*>(smem + OFF_WP + ROW8_PIECE + o) = (uint16_t)p1;
+                *reinterpret_cast<uint16_t*>(smem + OFF_WP + 2 * ROW8_PIECE + o) = (uint16_t)p2;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            UMMA_PROF();
+            // dWv += H2^T * dv
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_gemm<3, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opDV, id_s8, accw);
+                    umma_commit(barB);
+                }
+                __syncwarp();
+            }
+            const float dvr = f32[F32_DV + row];
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = dvr * f32[F32_WV + 32 * half + j] * (1.f - h2r[j] * h2r[j]);
+            mbar_wait(barB, phB); phB ^= 1;  // dWv has read H2
+            tc_fence_after();
+            UMMA_PROF();
+            store_row32(sH2, row, half, v);  // dP2 in place of H2
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        UMMA_PROF();
+
+        // ---- hidden layer 1 backward: dH1 = dP2 * W1^T ; dW1^T += dP2^T * H1 ; db1 += colsum(dP2)
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opW1_b, id_b64, false);
+                umma_commit(barA);
+                issue_gemm<3, 8>(tmem + ACC_DW1, tmem + ACC_DW1_C, opH2_mn, opH1_mn, id_w64, accw);
+                issue_gemm<1, 8>(tmem + ACC_DB1, tmem + ACC_DB1_C, opH2_mn, opONES, id_s8, accw);
+                umma_commit(barB);
+            }
+            __syncwarp();
+        }
+        // pi tower: X' again for the layer-0 weight gradient (its block held [dMU | dLS] in between; the MMAs that read
+        // those completed before the dP2 epilogue)
+        if (tower == 0) {
+            ObsRegs<O> xr;
+            xr.load(a.obs, c_grow, gh, valid);
+            xr.store(sY, gr, gh);
+        }
+        mbar_wait(barA, phA); phA ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h1r[j] * h1r[j]);
+            mbar_wait(barB, phB); phB ^= 1;  // dW1 has read H1
+            UMMA_PROF();
+            store_row32(sH1, row, half, v);  // dP1 in place of H1
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        UMMA_PROF();
+        // ---- layer 0 backward: dW0'^T += dP1^T * X'   (column O of the result is the bias gradient)
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                issue_gemm<3, 8>(tmem + ACC_DW0, tmem + ACC_DW0_C, opH1_mn, opY_mn, id_w32, accw);
+                umma_commit(barB);
+            }
+            __syncwarp();
+        }
+        accw = true;
+        const bool more = tile + (int)gridDim.x < ntiles;
+        if (more) load_inputs(tile + gridDim.x);
+        mbar_wait(barB, phB); phB ^= 1;
+        tc_fence_after();
+        UMMA_PROF();
+        if (more) {
+            xin.store(sY, gr, gh);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+
+    // ---------------------------------------------------------------- flush the weight gradients of this CTA
+    float* my = a.partial + (size_t)blockIdx.x * a.PS;
+    // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15)
+    const int r64 = q * 16 + lane;
+    const bool has = lane < 16;
+    if (!accw) {  // no tile for this CTA: write zeros
+        if (tower == 0) {
+            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) my[d.off[T_PI_FC0_W] + i] = 0.f;
+            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) my[d.off[T_PI_FC1_W] + i] = 0.f;
+            for (int i = tid; i < d.H2 * A + 2 * A; i += NTH) my[d.off[T_PI_W] + i] = 0.f;
+        } else {
+            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) my[d.off[T_VF_FC0_W] + i] = 0.f;
+            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) my[d.off[T_VF_FC1_W] + i] = 0.f;
+            for (int i = tid; i < d.H2 + 1; i += NTH) my[d.off[T_VF_W] + i] = 0.f;
+        }
+    } else {
+        float v[32];
+        // dW1^T[j][k] -> W1[k][j]
+        tmem_ld32_sum(tlane + ACC_DW1 + 32 * half, tlane + ACC_DW1_C + 32 * half, v);
+        if (has) {
+            float* g = my + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) g[(size_t)(32 * half + k) * HID + r64] = v[k];
+        }
+        if (half == 0) {
+            // dW0'^T[j][k]: k < O -> W0[k][j], k == O -> b0[j]
+            tmem_ld32_sum(tlane + ACC_DW0, tlane + ACC_DW0_C, v);
+            if (has) {
+                float* g = my + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
+                float* gb = my + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    if (k < O) g[(size_t)k * HID + r64] = v[k];
+                    else if (k == O) gb[r64] = v[k];
+                }
+            }
+        } else {
+            float b[8];
+            tmem_ld8_sum(tlane + ACC_DB1, tlane + ACC_DB1_C, b);
+            if (has) my[d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + r64] = b[0];
+            if (tower == 0) {
+                // dWpi[k][j]
+                tmem_ld32_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, v);
+                if (has) {
+                    float* g = my + d.off[T_PI_W] + (size_t)r64 * A;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < A) g[j] = v[j];
+                }
+                // column sums: rows < A -> dbpi, rows 32 .. 32 + A -> dlogstd
+                tmem_ld8_sum(tlane + ACC_CS, tlane + ACC_CS_C, b);
+                if (has) {
+                    if (r64 < A) my[d.off[T_PI_B] + r64] = b[0];
+                    // d(-ent_coef*entropy)/dlogstd_j = -ent_coef, once (a.ent_coef is pre-divided by the number of ranks)
+                    if (r64 >= 32 && r64 < 32 + A) my[d.off[T_LOGSTD] + r64 - 32] = b[0] - (blockIdx.x == 0 ? a.ent_coef : 0.f);
+                }
+            } else {
+                tmem_ld8_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, b);
+                if (has) my[d.off[T_VF_W] + r64] = b[0];
+            }
+        }
+    }
+    // ---- loss sums
+    {
+        float v4[4] = {l_0, l_1, l_2, l_dbv};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v4[k] = warp_sum(v4[k]);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f32[F32_RED + warp * 4 + k] = v4[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int w = 0; w < NTH / 32; ++w)
+                for (int k = 0; k < 4; ++k) t[k] += f32[F32_RED + w * 4 + k];
+            float* Lp = my + d.P;
+            if (tower == 0) {
+                Lp[L_PG] = t[0]; Lp[L_KL] = t[1]; Lp[L_CLIP] = t[2];
+                float ent = 0.f;
+                if (blockIdx.x == 0)
+                    for (int j = 0; j < A; ++j) ent += f32[F32_LS + j] + PPO_HALF_LOG_2PIE;  // GRAPH:10021-10180
+                Lp[L_ENT] = ent;
+                Lp[5] = 0.f; Lp[6] = 0.f; Lp[7] = 0.f;
+            } else {
+                Lp[L_VF] = t[0];
+                my[d.off[T_VF_B]] = t[3];
+            }
+        }
+    }
+    UMMA_PROF();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+#undef UMMA_PROF
+
+}  // namespace umma
+}  // namespace ppo

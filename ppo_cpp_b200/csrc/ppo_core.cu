@@ -17,6 +17,7 @@
 #include "kernels_misc.cuh"
 #include "kernels_mlp.cuh"
 #include "kernels_mlp2.cuh"
+#include "kernels_umma.cuh"
 #include "meta_parser.h"
 
 using namespace ppo;
@@ -96,7 +97,10 @@ struct ppo_core {
     int tm = 64;          // tile size of the generic (T family) MLP kernels
     bool fused = false;   // F family usable: weights + one tile fit in shared memory, H1 % 4 == H2 % 4 == 0
     size_t fused_train_smem = 0, fused_policy_smem = 0;
+    bool umma = false;    // U family (tcgen05) train kernel usable: H1 == H2 == 64, obs/act 18/18
     int max_train_grid = 0;
+    int prof_train_grid = 0;
+    long long* umma_prof = nullptr;  // PPO_UMMA_PROF=1: phase timestamps of the U-family train kernel
     int PS = 0;           // partial slab width = P + L_PAD
 
     float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *bpow = nullptr;  // bpow: 2 slots x 2
@@ -372,8 +376,18 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                 }
             }
         }
+        c->umma = c->d.H1 == umma::HID && c->d.H2 == umma::HID && c->d.O == 18 && c->d.A == 18 && umma::SMEM_BYTES <= max_smem &&
+                  prop.major == 10 && getenv("PPO_DISABLE_UMMA") == nullptr && getenv("PPO_DISABLE_FUSED") == nullptr;
+        if (c->umma && cudaFuncSetAttribute(umma::train_umma_kernel<18, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) != cudaSuccess) {
+            st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(train_umma_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         st = core_alloc(c);
         if (st != PPO_OK) break;
+        if (c->umma && getenv("PPO_UMMA_PROF")) {
+            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 64) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
+            cudaMemset(c->umma_prof, 0, sizeof(long long) * 64);
+        }
         {
             int per_sm = 0, coop_ok = 0;
             cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, desc->device);
@@ -1088,12 +1102,20 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = tru
     a.vf_coef = c->desc.vf_coef;
     a.partial = c->partial;
     a.PS = c->PS;
-    const int tm = c->fused ? F_TM_TRAIN : c->tm;
-    const int ntiles = (a.count + tm - 1) / tm;
-    const int grid = std::max(1, std::min(ntiles, c->fused ? c->sm_count : c->max_train_grid));
-    if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
-    else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
-    else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
+    int grid;
+    a.prof = c->umma_prof;
+    if (c->umma) {  // tcgen05 path: one CTA per (tile of 128 samples, tower)
+        const int ntiles = (a.count + umma::TM - 1) / umma::TM;
+        grid = std::max(1, std::min(ntiles, c->sm_count / 2));
+        LAUNCH(c, (umma::train_umma_kernel<18, 18>), dim3(grid, 2), umma::NTH, umma::SMEM_BYTES, a);
+    } else {
+        const int tm = c->fused ? F_TM_TRAIN : c->tm;
+        const int ntiles = (a.count + tm - 1) / tm;
+        grid = std::max(1, std::min(ntiles, c->fused ? c->sm_count : c->max_train_grid));
+        if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
+        else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
+        else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
+    }
     if (with_reduce) LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
     if (grid_out) *grid_out = grid;
     CU(cudaGetLastError());
@@ -1320,14 +1342,11 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
                 a.gather = c->gather; a.mbstats = c->mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
                 a.invB = 1.0f / (float)c->B_global; a.cliprange = 0.2f;
                 a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
-                const int tm = c->fused ? F_TM_TRAIN : c->tm, ntiles = (a.count + tm - 1) / tm;
-                const int grid = std::max(1, std::min(ntiles, c->fused ? c->sm_count : c->max_train_grid));
                 if (w == "train_fwdbwd") {
-                    if (c->fused) LAUNCH(c, (train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>), grid, F_NT_TRAIN, c->fused_train_smem, a);
-                    else if (tm == 64) LAUNCH(c, train_tile_kernel<64>, grid, NT, train_smem_floats<64>(c->d) * sizeof(float), a);
-                    else LAUNCH(c, train_tile_kernel<32>, grid, NT, train_smem_floats<32>(c->d) * sizeof(float), a);
+                    st = launch_train_kernel(c, a, false, &c->prof_train_grid);
                 } else {
-                    LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, grid, c->PS, c->d.P, c->grad, c->sq_partial);
+                    if (c->prof_train_grid == 0) st = launch_train_kernel(c, a, false, &c->prof_train_grid);
+                    LAUNCH(c, grad_reduce_kernel, c->n_sq_blocks, 256, 0, c->partial, c->prof_train_grid, c->PS, c->d.P, c->grad, c->sq_partial);
                 }
             } else if (w == "adam") {
                 AdamArgs ad{};
@@ -1371,6 +1390,15 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (st != PPO_OK) return st;
+    if (c->umma_prof && w == "train_fwdbwd") {
+        long long h[64];
+        cudaMemcpy(h, c->umma_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int t = 0; t < 2; ++t) {
+            fprintf(stderr, "umma phases tower %d (cycles since setup):", t);
+            for (int i = 1; i < 32 && h[t * 32 + i]; ++i) fprintf(stderr, " %lld", h[t * 32 + i] - h[t * 32 + i - 1]);
+            fprintf(stderr, "\n");
+        }
+    }
     *avg_ms = ms / (float)iters;
     if (launches) *launches = (int)(c->ctr.kernel_launches - before);
     return PPO_OK;

@@ -251,33 +251,45 @@ def test_loss_grad_vs_oracle(core_mod, h1, h2, B):
     g, l = c.loss_grad(obs, act, adv, ret, old_nlp, old_v, 0.2)
     g64, l64 = o.loss_grad(p, obs, act, adv, ret, old_nlp, old_v, 0.2, "f64")
     assert rel_err(g, g64) < TOL
+    for t in range(13):  # every gradient tensor separately
+        sl = slice(o.offset(t), o.offset(t + 1))
+        assert rel_err(g[sl], g64[sl]) < TOL, f"gradient tensor {t}"
     assert np.allclose(l, l64, rtol=TOL, atol=1e-7)
     assert l[4] == pytest.approx(l64[4], abs=1.5 / B)  # clipfrac is a count
     c.close()
 
 
-def test_generic_and_fused_kernel_families_agree(core_mod, monkeypatch):
-    """[64,64] runs on the fused (weights-in-smem) family by default; the generic tile family must give the same
-    answers (both are also checked against the oracle above)."""
+@pytest.mark.parametrize("B", [1000, 128, 77, 20000])
+def test_kernel_families_agree(core_mod, monkeypatch, B):
+    """[64,64] trains on the tcgen05 (U) family by default; the fused FFMA (F) family and the generic tile (T) family
+    must give the same answers (all are also checked against the oracle above).  B = 1000 / 77 leave a ragged last
+    tile, B = 20000 makes every CTA of the U family loop over several tiles (accumulation in TMEM)."""
     rng = np.random.default_rng(99)
     h1 = h2 = 64
-    B = 1000
     p = rand_params(rng, h1, h2)
     obs = rng.standard_normal((B, 18)).astype(np.float32)
     eps = rng.standard_normal((B, 18)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
     res = []
-    for disable in (False, True):
-        if disable:
-            monkeypatch.setenv("PPO_DISABLE_FUSED", "1")
+    for env in (None, "PPO_DISABLE_UMMA", "PPO_DISABLE_FUSED"):
+        if env:
+            monkeypatch.setenv(env, "1")
         c = make_core(core_mod, p, hidden1=h1, hidden2=h2, n_envs=4, n_steps=8, nminibatches=4)
         act, val, nlp = c.policy_step(obs, eps)
-        adv = rng.standard_normal(B).astype(np.float32) if not res else res[0][3]
         g, l = c.loss_grad(obs, act, adv, val + 0.1, nlp + 0.01, val - 0.05, 0.2)
-        res.append((act, val, nlp, adv, g, l))
+        res.append((act, val, nlp, g, l))
         c.close()
-    monkeypatch.delenv("PPO_DISABLE_FUSED")
-    for a, b in zip(res[0], res[1]):
-        assert rel_err(a, b) < 5e-6
+        if env:
+            monkeypatch.delenv(env)
+    names = ["actions", "values", "neglogp", "grads", "losses"]
+    for other in res[1:]:
+        for nm, a, b in zip(names, res[0], other):
+            assert rel_err(a, b) < 5e-6, nm
+    # every gradient tensor separately (a small tensor must not hide behind a big one)
+    o = ol.Oracle(h1=h1, h2=h2)
+    for t in range(13):
+        sl = slice(o.offset(t), o.offset(t + 1))
+        assert rel_err(res[0][3][sl], res[2][3][sl]) < 1e-5, f"gradient tensor {t}"
 
 
 # ------------------------------------------------------------------ minibatch step / whole update (a9-a11)
