@@ -185,6 +185,10 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
 } ppo_counters;
 int ppo_core_counters(ppo_core *core, ppo_counters *out, int reset);
+/* which kernel family the core selected for this MLP shape: "which" = "train" | "policy";
+ * returns e.g. "train_umma_kernel (tcgen05, bf16x3 split)", "train_fused_kernel (fp32 FFMA, weights in smem)",
+ * "train_tile_kernel (fp32 FFMA, generic)"; NULL on bad arguments */
+const char *ppo_core_kernel_family(ppo_core *core, const char *which);
 /* average device time (ms, CUDA events on the core's stream) of `iters` back-to-back launches of one kernel of
  * the path on the core's current rollout buffers: "train_fwdbwd" (rotating over the minibatches of the current
  * permutation), "grad_reduce", "adam" (lr = 0: weights unchanged), "policy_step", "norm_moments", "norm_apply",

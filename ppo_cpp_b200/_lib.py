@@ -117,6 +117,7 @@ def load():
         "ppo_comm_get_unique_id": ([C.c_char_p], C.c_int),
         "ppo_comm_init": ([core, C.c_char_p, C.c_int, C.c_int], C.c_int),
         "ppo_core_counters": ([core, C.POINTER(Counters), C.c_int], C.c_int),
+        "ppo_core_kernel_family": ([core, C.c_char_p], C.c_char_p),
         "ppo_profile_kernel": ([core, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)], C.c_int),
     }
     undeclared = [s for s in declared_symbols() if s not in sig]

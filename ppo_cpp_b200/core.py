@@ -288,6 +288,10 @@ class PPOCore:
         _check(self.lib, self.lib.ppo_learn_update_synthetic(self._h, lr, cliprange, _addr(out)))
         return out
 
+    def kernel_family(self, which="train"):
+        r = self.lib.ppo_core_kernel_family(self._h, which.encode())
+        return r.decode() if r else None
+
     def profile_kernel(self, which, iters=50):
         ms, n = C.c_float(), C.c_int()
         _check(self.lib, self.lib.ppo_profile_kernel(self._h, which.encode(), iters, C.byref(ms), C.byref(n)))

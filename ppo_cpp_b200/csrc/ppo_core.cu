@@ -1314,6 +1314,21 @@ extern "C" int ppo_core_counters(ppo_core* c, ppo_counters* out, int reset) {
     return PPO_OK;
 }
 
+extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
+    if (!c || !which) return nullptr;
+    const std::string w(which);
+    if (w == "train") {
+        if (c->umma) return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators)";
+        if (c->fused) return "train_fused_kernel (fp32 FFMA, weights staged in shared memory)";
+        return "train_tile_kernel (fp32 FFMA, generic hidden sizes)";
+    }
+    if (w == "policy") {
+        if (c->fused) return "policy_fused_kernel (fp32 FFMA, weights staged in shared memory)";
+        return "policy_tile_kernel (fp32 FFMA, generic hidden sizes)";
+    }
+    return nullptr;
+}
+
 extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, float* avg_ms, int* launches) {
     if (!c || !which || iters < 1 || !avg_ms) return fail(PPO_ERR_INVALID, "ppo_profile_kernel: bad arguments");
     CU(cudaSetDevice(c->desc.device));
