@@ -188,9 +188,8 @@ def run_ours(args):
                      seed=1234, rank=rank, world_size=world, env_offset=rank * n_envs, n_envs_global=n_envs * world)
     c.init_orthogonal(7)  # random-init weights of the named architecture, identical on every rank
     if world > 1:
-        uid = [core.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        c.comm_init(uid[0], rank, world)
+        from ppo_cpp_b200.dist import setup_comm
+        setup_comm(core, c, rank, world)  # NCCL communicator + peer mailboxes (NVLink P2P)
     c.shuffle_seed(42)
     c.synth_env_reset()
     stream = torch.cuda.ExternalStream(c.stream, device=dev)

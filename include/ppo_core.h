@@ -177,6 +177,18 @@ int ppo_learn_update_synthetic(ppo_core *core, float lr, float cliprange, float 
 #define PPO_COMM_ID_BYTES 128
 int ppo_comm_get_unique_id(char id[PPO_COMM_ID_BYTES]);
 int ppo_comm_init(ppo_core *core, const char id[PPO_COMM_ID_BYTES], int rank, int world_size);
+/* Peer-memory mailboxes (one process per GPU, one NVLink/NVSwitch node): every rank exports the cudaIpc handle of its
+ * mailbox, the host gathers the world_size handles (rank order) and every rank maps them.  Once mapped, the
+ * per-env-step VecNormalize moment exchange and the per-minibatch gradient allreduce run INSIDE the persistent rollout
+ * kernel / the cooperative reduce+Adam kernel as NVLink P2P stores + flags (no NCCL call on those paths; NCCL remains
+ * for the once-per-update allgather of the rollout buffers).  Without this call the NCCL path is used. */
+#define PPO_IPC_HANDLE_BYTES 64
+int ppo_comm_ipc_handle(ppo_core *core, char out[PPO_IPC_HANDLE_BYTES]);
+int ppo_comm_ipc_open(ppo_core *core, const char *handles /* [world_size][PPO_IPC_HANDLE_BYTES] */, int world_size);
+/* switch the mailbox path off (NCCL for every exchange) or back on; must be the same on every rank */
+int ppo_comm_set_p2p(ppo_core *core, int enable);
+/* 1 if a mailbox wait timed out (a peer never arrived); 0 otherwise */
+int ppo_comm_error(ppo_core *core);
 
 /* ---- introspection for the bench: kernels launched / device time of the dominant kernel ---- */
 typedef struct {

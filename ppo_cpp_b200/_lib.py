@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ppo_core.h")
 
 PPO_HOST, PPO_DEVICE = 0, 1
 PPO_COMM_ID_BYTES = 128
+PPO_IPC_HANDLE_BYTES = 64
 ABI_VERSION = 1
 
 
@@ -116,6 +117,10 @@ def load():
         "ppo_learn_update_synthetic": ([core, C.c_float, C.c_float, fp], C.c_int),
         "ppo_comm_get_unique_id": ([C.c_char_p], C.c_int),
         "ppo_comm_init": ([core, C.c_char_p, C.c_int, C.c_int], C.c_int),
+        "ppo_comm_ipc_handle": ([core, C.c_char_p], C.c_int),
+        "ppo_comm_ipc_open": ([core, C.c_char_p, C.c_int], C.c_int),
+        "ppo_comm_error": ([core], C.c_int),
+        "ppo_comm_set_p2p": ([core, C.c_int], C.c_int),
         "ppo_core_counters": ([core, C.POINTER(Counters), C.c_int], C.c_int),
         "ppo_core_kernel_family": ([core, C.c_char_p], C.c_char_p),
         "ppo_profile_kernel": ([core, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)], C.c_int),

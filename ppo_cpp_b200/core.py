@@ -300,3 +300,19 @@ class PPOCore:
     # ---- multi-GPU
     def comm_init(self, unique_id: bytes, rank: int, world_size: int):
         _check(self.lib, self.lib.ppo_comm_init(self._h, unique_id, rank, world_size))
+
+    def comm_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PPO_IPC_HANDLE_BYTES)
+        _check(self.lib, self.lib.ppo_comm_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def comm_ipc_open(self, handles, world_size: int):
+        blob = b"".join(handles)
+        assert len(blob) == world_size * _lib.PPO_IPC_HANDLE_BYTES
+        _check(self.lib, self.lib.ppo_comm_ipc_open(self._h, blob, world_size))
+
+    def comm_set_p2p(self, enable: bool):
+        _check(self.lib, self.lib.ppo_comm_set_p2p(self._h, int(enable)))
+
+    def comm_error(self) -> bool:
+        return bool(self.lib.ppo_comm_error(self._h))

@@ -4,6 +4,7 @@
 #include <cooperative_groups.h>
 
 #include "device_common.cuh"
+#include "sync_prims.cuh"
 
 namespace ppo {
 
@@ -479,60 +480,112 @@ __global__ void adam_kernel(const AdamArgs a) {
     a.params[i] = __fsub_rn(a.params[i], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
 }
 
-// Fused (single GPU, small P): column-reduce the CTA slabs + global norm + clip + Adam in ONE cooperative launch.
-// Block = 64 columns x 4 row groups; phase 1 sums the G slabs (fixed order: 4 interleaved row groups, combined in
-// double) and publishes per-block sum of squares; grid.sync(); phase 2 computes the norm from the block partials
-// and applies Adam to the block's own columns straight from registers.
+// Fused gradient step: column-reduce the CTA slabs -> (multi-GPU: allreduce through the peer mailboxes) -> global norm
+// -> clip -> Adam, in ONE cooperative launch (replaces grad_reduce_kernel + ncclAllReduce + sqnorm_kernel + adam_kernel).
+// A block owns 64-column chunks (chunk = blockIdx.x + j * gridDim.x, j < RA_MAXJ), 4 row groups of threads per chunk.
+//   phase 1  sum the G slabs per column (fixed order: 4 interleaved row groups in fp32, combined in double)
+//   phase 1b multi-GPU: store the block's columns into slot [seq & 1][rank] of EVERY rank's mailbox (NVLink P2P stores),
+//            signal channel = blockIdx.x, wait for the same block of every peer, add the `world` slots in rank order
+//            (every rank adds the same numbers in the same order -> replicas stay bit-identical)
+//   phase 2  per-block sum of squares -> grid barrier -> global norm, clip scale, TF ApplyAdam on the block's columns
+//            straight from registers, loss row, beta powers.
+constexpr int RA_MAXJ = 4;
 struct ReduceAdamArgs {
     const float* partial;
     int G, PS;
     float* grad;  // [PS] written for inspection / loss sums
     double* sq_partial;
     AdamArgs adam;
+    unsigned* bar_ctr;  // grid barrier counter (monotonic) and generations completed (device-resident so that the
+    unsigned* bar_gen;  // launch can be replayed from a CUDA graph)
+    PeerMailbox mbox;   // world == 1: unused
+    unsigned* mbox_seq; // device-resident sequence number of the gradient exchange
 };
 
 __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const ReduceAdamArgs r) {
-    namespace cg = cooperative_groups;
     __shared__ float part[4][64];
     __shared__ double red[8];
     __shared__ float s_scale;
+    const AdamArgs& a = r.adam;
     const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    const int c = blockIdx.x * 64 + lane_c;
-    float acc = 0.f;
-    if (c < r.PS) {
-        const float* p = r.partial + c;
-        int g = rg;
-#pragma unroll 1
-        for (; g + 28 < r.G; g += 32) {  // 8 independent loads in flight per thread
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(g + 4 * u) * r.PS];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc += v[u];
-        }
-        for (; g < r.G; g += 4) acc += p[(size_t)g * r.PS];
-    }
-    part[rg][lane_c] = acc;
-    __syncthreads();
-    float gsum = 0.f;
+    const int nchunks = (r.PS + 63) >> 6;
+    GridBarrier bar{r.bar_ctr, gridDim.x, *r.bar_gen};
+    const int world = r.mbox.world;
+    const unsigned seq = world > 1 ? (*r.mbox_seq + 1u) : 0u;
+    float gsum[RA_MAXJ];
     double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < RA_MAXJ; ++j) {
+        gsum[j] = 0.f;
+        const int chunk = blockIdx.x + j * gridDim.x;
+        if (chunk >= nchunks) break;  // block-uniform
+        const int c = chunk * 64 + lane_c;
+        float acc = 0.f;
+        if (c < r.PS) {
+            const float* p = r.partial + c;
+            int g = rg;
+#pragma unroll 1
+            for (; g + 28 < r.G; g += 32) {  // 8 independent loads in flight per thread
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(g + 4 * u) * r.PS];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; g < r.G; g += 4) acc += p[(size_t)g * r.PS];
+        }
+        __syncthreads();
+        part[rg][lane_c] = acc;
+        __syncthreads();
+        if (rg == 0) {
+            const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
+            gsum[j] = (float)t;
+            if (world > 1 && c < r.PS) {
+                for (int dst = 0; dst < world; ++dst)
+                    reinterpret_cast<float*>(r.mbox.slot(dst, seq, r.mbox.rank))[c] = gsum[j];
+            }
+        }
+    }
+    if (world > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            r.mbox.signal_all((int)blockIdx.x, seq);
+            r.mbox.wait_all((int)blockIdx.x, seq);
+        }
+        __syncthreads();
+        if (rg == 0) {
+#pragma unroll
+            for (int j = 0; j < RA_MAXJ; ++j) {
+                const int chunk = blockIdx.x + j * gridDim.x;
+                if (chunk >= nchunks) break;
+                const int c = chunk * 64 + lane_c;
+                if (c < r.PS) {
+                    float t = 0.f;
+                    for (int src = 0; src < world; ++src) t += __ldcg(reinterpret_cast<const float*>(r.mbox.slot(r.mbox.rank, seq, src)) + c);
+                    gsum[j] = t;
+                }
+            }
+        }
+    }
     if (rg == 0) {
-        const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
-        gsum = (float)t;
-        if (c < r.PS) r.grad[c] = gsum;
-        if (c < r.adam.P) q = (double)gsum * (double)gsum;
+#pragma unroll
+        for (int j = 0; j < RA_MAXJ; ++j) {
+            const int chunk = blockIdx.x + j * gridDim.x;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < r.PS) r.grad[c] = gsum[j];
+            if (c < a.P) q += (double)gsum[j] * (double)gsum[j];
+        }
     }
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
     __syncthreads();
     if (threadIdx.x == 0) r.sq_partial[blockIdx.x] = red[0] + red[1];  // warps 0,1 hold rg == 0
-    __threadfence();
-    cg::this_grid().sync();
-    const AdamArgs& a = r.adam;
+    bar.sync();
     if (threadIdx.x < 32) {
         double ss = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) ss += r.sq_partial[b];
-        // fixed-order combine: lane partials summed by a butterfly (same order in every block)
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) ss += __ldcg(r.sq_partial + b);
+        // fixed-order combine: lane partials summed by a butterfly (same order in every block and on every rank)
         ss = warp_sum(ss);
         if (threadIdx.x == 0) {
             const float gnorm = (float)sqrt(ss);
@@ -540,30 +593,45 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const Reduce
             float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
             if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
             s_scale = scale;
-            if (blockIdx.x == 0) *a.gnorm_out = gnorm;
+            if (blockIdx.x == 0) {
+                *a.gnorm_out = gnorm;
+                *r.bar_gen = bar.gen;
+                if (world > 1) *r.mbox_seq = seq;
+            }
         }
     }
     __syncthreads();
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // the block that owns the loss columns
-        const float* Ls = r.grad + a.P;
-        a.loss_row[0] = Ls[L_PG] * a.invB;
-        a.loss_row[1] = 0.5f * (Ls[L_VF] * a.invB);
-        a.loss_row[2] = Ls[L_ENT] * a.inv_world;
-        a.loss_row[3] = 0.5f * (Ls[L_KL] * a.invB);
-        a.loss_row[4] = Ls[L_CLIP] * a.invB;
+    const int loss_chunk = (a.P >> 6);  // the chunk that holds column P (the loss sums start there)
+    if ((int)blockIdx.x == loss_chunk % (int)gridDim.x && threadIdx.x == 0) {
+        const float* Ls = r.grad + a.P;   // written above by this block (P + 8 <= PS may straddle into the next chunk:
+        float L[5];                        // read those through L2)
+        for (int k = 0; k < 5; ++k) L[k] = __ldcg(Ls + k);
+        a.loss_row[0] = L[L_PG] * a.invB;
+        a.loss_row[1] = 0.5f * (L[L_VF] * a.invB);
+        a.loss_row[2] = L[L_ENT] * a.inv_world;
+        a.loss_row[3] = 0.5f * (L[L_KL] * a.invB);
+        a.loss_row[4] = L[L_CLIP] * a.invB;
         a.bpow_out[0] = __fmul_rn(a.bpow_in[0], a.beta1);
         a.bpow_out[1] = __fmul_rn(a.bpow_in[1], a.beta2);
     }
-    if (rg == 0 && c < a.P) {
+    if (rg == 0) {
         const float b1p = a.bpow_in[0], b2p = a.bpow_in[1];
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
-        const float g = __fmul_rn(gsum, s_scale);
-        float m = a.m[c], v = a.v[c];
-        m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
-        v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
-        a.m[c] = m;
-        a.v[c] = v;
-        a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+#pragma unroll
+        for (int j = 0; j < RA_MAXJ; ++j) {
+            const int chunk = blockIdx.x + j * gridDim.x;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < a.P) {
+                const float g = __fmul_rn(gsum[j], s_scale);
+                float m = a.m[c], v = a.v[c];
+                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+                a.m[c] = m;
+                a.v[c] = v;
+                a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+            }
+        }
     }
 }
 

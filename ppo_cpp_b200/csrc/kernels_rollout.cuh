@@ -1,0 +1,455 @@
+// "R family": the whole synthetic-env rollout (Runner::run + set_returns, ppo2/runner.hpp:56-191) as ONE persistent
+// cooperative kernel.
+//
+// The per-step chain of the reference — MlpPolicy::step (policies.hpp:33-46), env.step, EnvNormalize::step
+// (env_normalize.hpp:64-92) — is a sequence of tiny dependent operations; launched as separate kernels it is pure
+// launch latency (4 launches x n_steps, profiles/r1_v3_launches_summary.txt: 2.3 ms of an 11.3 ms update at C3).
+// Here a CTA owns TM envs (x tiles-per-CTA) for the whole rollout:
+//   * the parameter vector is staged into shared memory ONCE per rollout (cp.async, 16 B), activations live in shared
+//     memory feature-major, env state / running returns / normalised observations stay in shared memory across steps;
+//   * the only cross-CTA dependency of a step is the VecNormalize batch moment (RunningStatistics::update,
+//     running_statistics.hpp:26-35): per-CTA fp64 partial sums -> one grid barrier -> every CTA sums the partials in
+//     the same fixed order and performs the Chan merge redundantly (bit-identical in every CTA, no second barrier);
+//   * bootstrap value and the GAE reverse scan (runner.hpp:159-191) run in the same kernel: a CTA only needs the
+//     rewards / values / dones of its own envs.
+// Arithmetic is the same as the step-by-step kernels (policy_*_kernel, synth_env_step_kernel, norm_*_kernel,
+// gae_kernel): same Philox counters, same fp32 operation order, fp64 moment sums around the same pivot.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "kernels_misc.cuh"
+#include "kernels_mlp2.cuh"
+
+namespace ppo {
+
+struct RolloutArgs {
+    NetDims d;
+    const float* params;
+    int n, T, tpc;  // envs of this rank, steps, tiles per CTA
+    uint64_t seed;
+    uint32_t env_id0;
+    uint32_t* step_ctr;
+    SynthEnv env;
+    NormStats st;
+    float* ret;  // [n] discounted return accumulator of EnvNormalize
+    float norm_gamma, clip_obs, clip_rew, eps;
+    int norm_obs, norm_reward, upd_obs, upd_ret;
+    double* partial;  // [2][gridDim.x][2*(D+1)]
+    float *cur_obs, *cur_dones, *last_values;
+    // time-major rollout slabs of this rank, row t = 0; one step further = n rows
+    float *obs_store, *act_store, *val_store, *nlp_store, *dones_store, *rew_store, *urew_store, *ret_store;
+    float gamma, lam;
+    unsigned *bar_ctr, *bar_gen;  // grid barrier (sync_prims.cuh), device-resident generation
+    int n_global;                 // envs over all ranks (rows of one VecNormalize batch)
+    PeerMailbox mbox;             // multi-GPU: per-step exchange of the batch moments over NVLink P2P stores
+    unsigned* mbox_seq;
+    long long* prof;  // optional [32] phase timestamps of CTA 0 during env step 1 (PPO_ROLLOUT_PROF=1)
+};
+
+#define R_PROF()                                                                              \
+    do {                                                                                      \
+        if (a.prof && blockIdx.x == 0 && tid == 0 && t == 1 && prof_i < 32) a.prof[prof_i++] = clock64(); \
+    } while (0)
+
+constexpr int R_TM = 32, R_NTH = 256;
+
+struct RLayout {
+    FLayout f;
+    int obs, state, raw, ret, dn, tenv, res, rew, done, lastv, z2, mean, var, inv, misc, csum, total_bytes;
+    __host__ __device__ void init(const NetDims& d, int tpc) {
+        f.init(d, R_TM, false);
+        int o = f.total;
+        auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+        obs = take(tpc * d.O * R_TM);
+        state = take(tpc * d.O * R_TM);
+        raw = take(tpc * d.O * R_TM);
+        ret = take(tpc * R_TM); dn = take(tpc * R_TM); tenv = take(tpc * R_TM); res = take(tpc * R_TM);
+        rew = take(tpc * R_TM); done = take(tpc * R_TM); lastv = take(tpc * R_TM);
+        z2 = take(d.A * R_TM);
+        mean = take(d.O + 1); var = take(d.O + 1); inv = take(d.O + 1); misc = take(8);
+        o = (o + 1) & ~1;  // 8-byte alignment for the doubles
+        csum = o;
+        o += 2 * (2 * (d.O + 1) + 2);  // doubles: column sums, obs_count, ret_count
+        total_bytes = o * 4;
+    }
+};
+
+__global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const RolloutArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const NetDims& d = a.d;
+    constexpr int TM = R_TM, NTH = R_NTH;
+    const int O = d.O, A = d.A, D = d.O;
+    RLayout L;
+    L.init(d, a.tpc);
+    float* sW = smem + L.f.w;
+    float* Ac = smem + L.f.ac;  // [A][TM+1]
+    float* MU = smem + L.f.mu;
+    float* Vs = smem + L.f.vs;
+    float* OBS = smem + L.obs;      // [tpc][O][TM] normalised observation, feature-major (the policy's input)
+    float* S = smem + L.state;      // [tpc][TM][D] env state
+    float* RAW = smem + L.raw;      // [tpc][TM][D] raw observation of this step
+    float* RET = smem + L.ret;
+    float* DN = smem + L.dn;
+    uint32_t* TENV = reinterpret_cast<uint32_t*>(smem + L.tenv);
+    uint32_t* RES = reinterpret_cast<uint32_t*>(smem + L.res);
+    float* REW = smem + L.rew;
+    float* DONE = smem + L.done;
+    float* LASTV = smem + L.lastv;
+    float* Z2 = smem + L.z2;        // [A][TM]
+    float* s_mean = smem + L.mean;  // [D] obs mean, [D] = ret mean
+    float* s_var = smem + L.var;
+    float* s_inv = smem + L.inv;
+    double* csum = reinterpret_cast<double*>(smem + L.csum);  // [2*(D+1)] then obs_count, ret_count
+    double* s_cnt = csum + 2 * (D + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int HALF = NTH / 2;
+    const int tw = tid / HALF;
+    const Sub half{tid % HALF, HALF};
+    float* H1 = smem + L.f.h1[tw];
+    float* H2 = smem + L.f.h2[tw];
+    const int ntiles = (a.n + TM - 1) / TM;
+    const int tile0 = blockIdx.x * a.tpc;
+    const int my_tiles = max(0, min(a.tpc, ntiles - tile0));
+    const int nblk = (D + 3) >> 2;  // Philox blocks of 4 dims
+    const uint32_t step0 = *a.step_ctr;
+    const bool merge = a.upd_obs || a.upd_ret;
+    GridBarrier bar{a.bar_ctr, gridDim.x, *a.bar_gen};
+    const int world = a.mbox.world;
+    const unsigned seq0 = world > 1 ? *a.mbox_seq : 0u;
+
+    // ---- one-time: weights, running statistics, per-env state
+    stage_weights<NTH>(sW, a.params, d.P);
+    if (tid < D) {
+        s_mean[tid] = a.st.obs_mean[tid];
+        s_var[tid] = a.st.obs_var[tid];
+    } else if (tid == D) {
+        s_mean[D] = *a.st.ret_mean;
+        s_var[D] = *a.st.ret_var;
+        s_cnt[0] = *a.st.obs_count;
+        s_cnt[1] = *a.st.ret_count;
+    }
+    for (int tl = 0; tl < my_tiles; ++tl) {
+        const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
+        for (int e = tid; e < TM * D; e += NTH) {
+            const int m = e / D, k = e - m * D;
+            const bool ok = m < nv;
+            OBS[(tl * O + k) * TM + m] = ok ? a.cur_obs[(size_t)(r0 + m) * O + k] : 0.f;
+            S[(tl * TM + m) * D + k] = ok ? a.env.state[(size_t)(r0 + m) * D + k] : 0.f;
+        }
+        if (tid < TM) {
+            const bool ok = tid < nv;
+            RET[tl * TM + tid] = ok ? a.ret[r0 + tid] : 0.f;
+            DN[tl * TM + tid] = ok ? a.cur_dones[r0 + tid] : 0.f;
+            TENV[tl * TM + tid] = ok ? a.env.t_env[r0 + tid] : 0u;
+            RES[tl * TM + tid] = ok ? a.env.resets[r0 + tid] : 0u;
+        }
+    }
+    cp_async_wait_all();
+    bar.sync();  // every CTA has read the launch-time state (step counter, barrier generation, sequence number)
+
+    const float* logstd = sW + d.off[T_LOGSTD];
+    const uint2 ekey = make_uint2((uint32_t)a.env.seed, (uint32_t)(a.env.seed >> 32));
+
+    int prof_i = 0;
+    for (int t = 0; t < a.T; ++t) {
+        const uint32_t step = step0 + (uint32_t)t;
+        R_PROF();  // step start
+        double ps = 0.0, pq = 0.0;  // this thread's column partial over the CTA's envs (threads 0..D)
+        const float pivot = (tid < D) ? s_mean[tid] : 0.f;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
+            float* Xs = OBS + tl * O * TM;
+            // -- store the observation the policy acts on (runner.hpp:75-78)
+            {
+                float* dst = a.obs_store + ((size_t)t * a.n + r0) * O;
+                for (int e = tid; e < nv * O; e += NTH) {
+                    const int m = e / O, k = e - m * O;
+                    dst[e] = Xs[k * TM + m];
+                }
+            }
+            // -- MlpPolicy::step: both towers in the same phase
+            f_fwd<TM, true>(Xs, O, sW + d.off[tw ? T_VF_FC0_W : T_PI_FC0_W], sW + d.off[tw ? T_VF_FC0_B : T_PI_FC0_B], d.H1, H1, half);
+            __syncthreads();
+            f_fwd<TM, true>(H1, d.H1, sW + d.off[tw ? T_VF_FC1_W : T_PI_FC1_W], sW + d.off[tw ? T_VF_FC1_B : T_PI_FC1_B], d.H2, H2, half);
+            __syncthreads();
+            if (tw == 0) f_fwd<TM, false>(H2, d.H2, sW + d.off[T_PI_W], sW + d.off[T_PI_B], A, MU, half);
+            else f_fwd<TM, false>(H2, d.H2, sW + d.off[T_VF_W], sW + d.off[T_VF_B], 1, Vs, half);
+            __syncthreads();
+            R_PROF();  // forward done
+            // -- Gaussian sample (GRAPH:5894-6019): thread (m, blk) draws 4 actions
+            for (int e = tid; e < TM * nblk; e += NTH) {
+                const int m = e % TM, blk = e / TM;
+                if (m < nv) {
+                    float e4[4];
+                    normal4(a.seed, a.env_id0 + (uint32_t)(r0 + m), step, (uint32_t)blk, PPO_TAG_ACTION, e4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = blk * 4 + q;
+                        if (j < A) {
+                            const float sd = expf(logstd[j]);
+                            const float mu = MU[j * TM + m];
+                            const float act = __fadd_rn(mu, __fmul_rn(sd, e4[q]));
+                            const float z = __fdiv_rn(__fsub_rn(act, mu), sd);
+                            Ac[j * (TM + 1) + m] = act;
+                            Z2[j * TM + m] = __fmul_rn(z, z);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nv) {  // neglogp (GRAPH:6103-6672): sequential sums in action order, as the step kernels
+                const int m = tid, row = r0 + m;
+                float ss = 0.f, sl = 0.f;
+                for (int j = 0; j < A; ++j) {
+                    ss = __fadd_rn(ss, Z2[j * TM + m]);
+                    sl = __fadd_rn(sl, logstd[j]);
+                }
+                const float nl = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, ss), __fmul_rn(PPO_HALF_LOG_2PI, (float)A)), sl);
+                const size_t idx = (size_t)t * a.n + row;
+                a.nlp_store[idx] = nl;
+                a.val_store[idx] = Vs[m];
+                a.dones_store[idx] = DN[tl * TM + m];  // done flag of the previous env step (runner.hpp:110)
+            }
+            {
+                float* dst = a.act_store + ((size_t)t * a.n + r0) * A;
+                for (int e = tid; e < nv * A; e += NTH) {
+                    const int m = e / A, j = e - m * A;
+                    dst[e] = Ac[j * (TM + 1) + m];
+                }
+            }
+            R_PROF();  // sample + stores issued
+            // -- synthetic env step: thread (m, blk) advances 4 state dims
+            for (int e = tid; e < TM * nblk; e += NTH) {
+                const int m = e % TM, blk = e / TM;
+                if (m < nv) {
+                    const uint32_t gid = a.env.env_id0 + (uint32_t)(r0 + m);
+                    const uint32_t te = TENV[tl * TM + m];
+                    const bool dn = ((te + 1u) % 334u) == 0u;
+                    float xi[4];
+                    normal4(a.env.seed, gid, te, (uint32_t)blk, PPO_TAG_ENVNOISE, xi);
+                    float* st = S + (tl * TM + m) * D;
+                    float* rw = RAW + (tl * TM + m) * D;
+                    uint4 w = make_uint4(0, 0, 0, 0);
+                    if (dn) w = philox4x32_10(make_uint4(gid, RES[tl * TM + m], (uint32_t)blk, PPO_TAG_ENVRESET), ekey);
+                    const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = blk * 4 + q;
+                        if (k < D) {
+                            const float sk = st[k];
+                            float ac = Ac[k * (TM + 1) + m];
+                            ac = ac < -1.f ? -1.f : (ac > 1.f ? 1.f : ac);
+                            float sn = __fadd_rn(__fadd_rn(__fmul_rn(0.9f, sk), __fmul_rn(0.1f, ac)), __fmul_rn(0.01f, xi[q]));
+                            if (k == 0) REW[tl * TM + m] = __fsub_rn(sn, sk);
+                            if (dn) sn = __fmul_rn(0.1f, __fsub_rn(__fmul_rn(2.0f, u32_to_unit(wv[q])), 1.0f));
+                            st[k] = sn;
+                            rw[k] = sn;
+                        }
+                    }
+                    if (blk == 0) DONE[tl * TM + m] = dn ? 1.f : 0.f;
+                }
+            }
+            __syncthreads();
+            if (tid < nv) {
+                const int m = tid;
+                TENV[tl * TM + m] += 1u;
+                if (DONE[tl * TM + m] != 0.f) RES[tl * TM + m] += 1u;
+                RET[tl * TM + m] = __fadd_rn(__fmul_rn(RET[tl * TM + m], a.norm_gamma), REW[tl * TM + m]);  // env_normalize.hpp:71
+            }
+            __syncthreads();
+            R_PROF();  // env step done
+            // -- batch moments of this tile (fp64 around the running mean), accumulated over the CTA's tiles
+            if (merge) {
+                if (tid < D) {
+                    for (int m = 0; m < nv; ++m) {
+                        const double x = (double)RAW[(tl * TM + m) * D + tid] - (double)pivot;
+                        ps += x;
+                        pq += x * x;
+                    }
+                } else if (tid == D) {
+                    for (int m = 0; m < nv; ++m) {
+                        const double r = (double)RET[tl * TM + m];
+                        ps += r;
+                        pq += r * r;
+                    }
+                }
+            }
+        }
+        if (merge) {
+            // -- RunningStatistics::update over ALL envs: partials -> grid barrier -> fixed-order total in every CTA
+            // partial layout [parity][column][cta]: the totals below read 32 consecutive CTAs per load instruction
+            double* mine = a.partial + (size_t)(t & 1) * 2 * (D + 1) * gridDim.x + blockIdx.x;
+            if (tid <= D) {
+                mine[(size_t)tid * gridDim.x] = ps;
+                mine[(size_t)(D + 1 + tid) * gridDim.x] = pq;
+            }
+            R_PROF();  // partial moments written
+            bar.sync();
+            R_PROF();  // grid barrier passed
+            const double* all = a.partial + (size_t)(t & 1) * 2 * (D + 1) * gridDim.x;
+            if (world == 1 || blockIdx.x == 0) {
+                // warp w sums columns w, w+8, ...: lane partials over the CTAs (independent loads, 5 columns x 4 in flight),
+                // then a butterfly — the same order in every CTA, so every CTA gets the same bits
+                constexpr int CPW = 5;  // columns per warp: 8 warps x 5 >= 2*(D+1) for D <= 19
+                double acc[CPW];
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) acc[i] = 0.0;
+#pragma unroll 4
+                for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32) {
+                    double x[CPW];
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        const int c = warp + (NTH / 32) * i;
+                        x[i] = (c < 2 * (D + 1) && b0 + lane < (int)gridDim.x) ? __ldcg(all + (size_t)c * gridDim.x + b0 + lane) : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) acc[i] += x[i];
+                }
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    const int c = warp + (NTH / 32) * i;
+                    const double v = warp_sum(acc[i]);
+                    if (lane == 0 && c < 2 * (D + 1)) csum[c] = v;
+                }
+                for (int c = (NTH / 32) * CPW + warp; c < 2 * (D + 1); c += NTH / 32) {  // D > 19: remaining columns
+                    double v = 0.0;
+                    for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(all + (size_t)c * gridDim.x + b);
+                    v = warp_sum(v);
+                    if (lane == 0) csum[c] = v;
+                }
+            }
+            __syncthreads();
+            if (world > 1) {
+                // CTA 0 publishes this rank's totals to every rank; every CTA then adds the `world` slots in rank order
+                const unsigned seq = seq0 + (unsigned)t + 1u;
+                if (blockIdx.x == 0) {
+                    if (tid < 2 * (D + 1))
+                        for (int dst = 0; dst < world; ++dst) reinterpret_cast<double*>(a.mbox.slot(dst, seq, a.mbox.rank))[tid] = csum[tid];
+                    __syncthreads();
+                    if (tid == 0) a.mbox.signal_all(PPO_MBOX_MOMENT_CHANNEL, seq);
+                }
+                if (tid == 0) a.mbox.wait_all(PPO_MBOX_MOMENT_CHANNEL, seq);
+                __syncthreads();
+                if (tid < 2 * (D + 1)) {
+                    double v = 0.0;
+                    for (int src = 0; src < world; ++src) v += __ldcg(reinterpret_cast<const double*>(a.mbox.slot(a.mbox.rank, seq, src)) + tid);
+                    csum[tid] = v;
+                }
+                __syncthreads();
+            }
+            R_PROF();  // totals
+            if (tid <= D) {
+                const int c = tid;
+                const bool is_ret = c == D;
+                if (is_ret ? a.upd_ret : a.upd_obs) {
+                    const double rows = (double)a.n_global;
+                    const double pv = is_ret ? 0.0 : (double)s_mean[c];
+                    const double m1 = csum[c] / rows;
+                    const double mean_d = pv + m1;
+                    double var_d = csum[D + 1 + c] / rows - m1 * m1;
+                    if (var_d < 0.0) var_d = 0.0;
+                    float mm = s_mean[c], vv = s_var[c];
+                    chan_merge(mm, vv, s_cnt[is_ret ? 1 : 0], (float)mean_d, (float)var_d, rows);
+                    s_mean[c] = mm;
+                    s_var[c] = vv;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (a.upd_obs) s_cnt[0] = (double)a.n_global + s_cnt[0];
+                if (a.upd_ret) s_cnt[1] = (double)a.n_global + s_cnt[1];
+            }
+        }
+        R_PROF();  // merged
+        if (tid <= D) s_inv[tid] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(s_var[tid], a.eps)));
+        __syncthreads();
+        // -- EnvNormalize::step post-processing (env_normalize.hpp:74-91)
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
+            for (int e = tid; e < TM * D; e += NTH) {
+                const int m = e / D, k = e - m * D;
+                float x = RAW[(tl * TM + m) * D + k];
+                if (a.norm_obs) {
+                    x = __fmul_rn(__fsub_rn(x, s_mean[k]), s_inv[k]);
+                    x = fminf(fmaxf(x, -a.clip_obs), a.clip_obs);
+                }
+                OBS[(tl * O + k) * TM + m] = (m < nv) ? x : 0.f;
+            }
+            if (tid < nv) {
+                const int m = tid;
+                const float raw = REW[tl * TM + m];
+                float r = raw;
+                if (a.norm_reward) {
+                    r = __fmul_rn(raw, s_inv[D]);
+                    r = fminf(fmaxf(r, -a.clip_rew), a.clip_rew);
+                }
+                const float dn = DONE[tl * TM + m];
+                RET[tl * TM + m] = __fmul_rn(RET[tl * TM + m], __fsub_rn(1.0f, dn));
+                DN[tl * TM + m] = dn;
+                const size_t idx = (size_t)t * a.n + r0 + m;
+                a.rew_store[idx] = r;
+                a.urew_store[idx] = raw;
+            }
+        }
+        __syncthreads();
+        R_PROF();  // applied
+    }
+
+    // ---- bootstrap value (runner.hpp:161-166) + GAE (runner.hpp:174-190) + state write-back
+    for (int tl = 0; tl < my_tiles; ++tl) {
+        const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
+        float* Xs = OBS + tl * O * TM;
+        if (tw == 1) f_fwd<TM, true>(Xs, O, sW + d.off[T_VF_FC0_W], sW + d.off[T_VF_FC0_B], d.H1, H1, half);
+        __syncthreads();
+        if (tw == 1) f_fwd<TM, true>(H1, d.H1, sW + d.off[T_VF_FC1_W], sW + d.off[T_VF_FC1_B], d.H2, H2, half);
+        __syncthreads();
+        if (tw == 1) f_fwd<TM, false>(H2, d.H2, sW + d.off[T_VF_W], sW + d.off[T_VF_B], 1, Vs, half);
+        __syncthreads();
+        if (tid < nv) LASTV[tl * TM + tid] = Vs[tid];
+        for (int e = tid; e < nv * D; e += NTH) {
+            const int m = e / D, k = e - m * D;
+            a.cur_obs[(size_t)r0 * O + e] = Xs[k * TM + m];
+            a.env.state[(size_t)r0 * D + e] = S[(tl * TM + m) * D + k];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < my_tiles * TM; e += NTH) {
+        const int tl = e / TM, m = e - tl * TM;
+        const int row = (tile0 + tl) * TM + m;
+        if (row >= a.n) continue;
+        a.ret[row] = RET[e];
+        a.cur_dones[row] = DN[e];
+        a.env.t_env[row] = TENV[e];
+        a.env.resets[row] = RES[e];
+        a.last_values[row] = LASTV[e];
+        const float gl = __fmul_rn(a.gamma, a.lam);
+        float last = 0.f, nextv = LASTV[e], nextnt = 1.0f - DN[e];
+#pragma unroll 8
+        for (int t = a.T - 1; t >= 0; --t) {
+            const size_t idx = (size_t)t * a.n + row;
+            const float v = a.val_store[idx];
+            const float delta = __fsub_rn(__fadd_rn(a.rew_store[idx], __fmul_rn(a.gamma, __fmul_rn(nextv, nextnt))), v);
+            last = __fadd_rn(delta, __fmul_rn(gl, __fmul_rn(nextnt, last)));
+            a.ret_store[idx] = __fadd_rn(last, v);
+            nextv = v;
+            nextnt = 1.0f - a.dones_store[idx];
+        }
+    }
+    if (blockIdx.x == 0) {
+        if (tid < D) {
+            a.st.obs_mean[tid] = s_mean[tid];
+            a.st.obs_var[tid] = s_var[tid];
+        } else if (tid == D) {
+            *a.st.ret_mean = s_mean[D];
+            *a.st.ret_var = s_var[D];
+            *a.st.obs_count = s_cnt[0];
+            *a.st.ret_count = s_cnt[1];
+            *a.step_ctr = step0 + (uint32_t)a.T;
+            *a.bar_gen = bar.gen;
+            if (world > 1 && merge) *a.mbox_seq = seq0 + (unsigned)a.T;
+        }
+    }
+}
+
+}  // namespace ppo

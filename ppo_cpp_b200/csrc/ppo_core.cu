@@ -17,6 +17,7 @@
 #include "kernels_misc.cuh"
 #include "kernels_mlp.cuh"
 #include "kernels_mlp2.cuh"
+#include "kernels_rollout.cuh"
 #include "kernels_umma.cuh"
 #include "meta_parser.h"
 
@@ -138,6 +139,10 @@ struct ppo_core {
     };
     std::vector<EpochGraph> graphs;
     EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
+    bool persistent_rollout = false;  // R family: the whole rollout as one cooperative kernel
+    int roll_grid = 0, roll_tpc = 0;
+    size_t roll_smem = 0;
+    double* roll_partial = nullptr;
 
     GlibcRand rng{1};
     std::vector<int> perm_host;
@@ -148,8 +153,32 @@ struct ppo_core {
     size_t scratch_floats = 0;
 
     ncclComm_t comm = nullptr;
+    // peer-memory mailbox (multi-GPU): this rank's allocation, the IPC mappings of the peers', device-resident
+    // barrier / sequence variables (sync_vars: see SV_*)
+    unsigned char* mbox_mem = nullptr;
+    unsigned char* mbox_peer[PPO_MAX_WORLD] = {};
+    size_t mbox_bytes = 0, mbox_grad_off = 0, mbox_grad_slot = 0;
+    bool mbox_ready = false;
+    unsigned* sync_vars = nullptr;
     ppo_counters ctr{};
 };
+// sync_vars layout: scalars first, then three barrier flag arrays of SV_MAXBLK words each
+enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_SCALARS = 16, SV_MAXBLK = 2048,
+       SV_COOP_FLAGS = SV_SCALARS, SV_ROLL_FLAGS = SV_COOP_FLAGS + SV_MAXBLK, SV_EPOCH_FLAGS = SV_ROLL_FLAGS + SV_MAXBLK,
+       SV_COUNT = SV_EPOCH_FLAGS + SV_MAXBLK };
+
+static PeerMailbox make_mailbox(const ppo_core* c, bool grads) {
+    PeerMailbox m{};
+    for (int r = 0; r < PPO_MAX_WORLD; ++r) m.base[r] = c->mbox_peer[r];
+    m.rank = c->desc.rank;
+    m.world = c->mbox_ready ? c->desc.world_size : 1;
+    m.data_off = grads ? c->mbox_grad_off : PPO_MBOX_FLAG_BYTES;
+    m.slot_bytes = grads ? c->mbox_grad_slot : PPO_MBOX_MOMENT_SLOT;
+    m.err = c->sync_vars + SV_ERR;
+    return m;
+}
+// single GPU, or multi-GPU with the peer mailboxes mapped: the persistent / cooperative kernels carry the exchanges
+static inline bool fast_path(const ppo_core* c) { return c->desc.world_size == 1 || c->mbox_ready; }
 
 #define LAUNCH(core, kernel, grid, block, smem, ...)                               \
     do {                                                                           \
@@ -243,6 +272,10 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int r = 0; r < PPO_MAX_WORLD; ++r)
+        if (c->mbox_peer[r] && r != c->desc.rank) cudaIpcCloseMemHandle(c->mbox_peer[r]);
+    if (c->mbox_mem) cudaFree(c->mbox_mem);
+    if (c->sync_vars) cudaFree(c->sync_vars);
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->rollout_graph.exec) cudaGraphExecDestroy(c->rollout_graph.exec);
@@ -250,7 +283,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
                         c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
                         c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
                         c->nrew, c->step_ctr, c->env.state, c->env.t_env, c->env.resets, c->perm_dev, c->gather,
-                        c->mbstats, c->partial, c->grad, c->loss_rows, c->loss_mean, c->gnorm, c->sq_partial, c->scratch};
+                        c->mbstats, c->partial, c->grad, c->loss_rows, c->loss_mean, c->gnorm, c->sq_partial, c->scratch,
+                        c->roll_partial};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < B_COUNT; ++i)
@@ -392,15 +426,61 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             int per_sm = 0, coop_ok = 0;
             cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, desc->device);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grad_reduce_adam_coop_kernel, 256, 0);
-            c->coop_grid = (c->PS + 63) / 64;
-            c->coop = coop_ok && desc->world_size == 1 && c->coop_grid <= per_sm * c->sm_count && getenv("PPO_DISABLE_COOP") == nullptr;
+            // cooperative reduce(+allreduce)+Adam: blocks own 64-column chunks, up to RA_MAXJ chunks each; multi-GPU runs
+            // use it once the peer mailboxes are mapped (fast_path), with one mailbox channel per block
+            const int nchunks = (c->PS + 63) / 64;
+            c->coop_grid = std::min(nchunks, std::min(per_sm * c->sm_count, PPO_MBOX_CHANNELS - 1));
+            c->coop = coop_ok && c->coop_grid > 0 && nchunks <= c->coop_grid * RA_MAXJ && getenv("PPO_DISABLE_COOP") == nullptr;
             if (c->coop && c->coop_grid > c->n_sq_blocks) {  // sq_partial is sized for 256-column blocks
                 cudaFree(c->sq_partial);
                 c->sq_partial = nullptr;
                 if (cudaMalloc(&c->sq_partial, sizeof(double) * c->coop_grid) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_partial) failed"); break; }
             }
-            c->use_graph = desc->world_size == 1 && getenv("PPO_DISABLE_GRAPH") == nullptr;
+            if (cudaMalloc(&c->sync_vars, sizeof(unsigned) * SV_COUNT) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sync_vars) failed"); break; }
+            cudaMemset(c->sync_vars, 0, sizeof(unsigned) * SV_COUNT);
+            if (desc->world_size > 1) {
+                if (desc->world_size > PPO_MAX_WORLD) { st = fail(PPO_ERR_UNSUPPORTED, "world_size %d > %d", desc->world_size, PPO_MAX_WORLD); break; }
+                c->mbox_grad_off = PPO_MBOX_FLAG_BYTES + 2 * (size_t)PPO_MAX_WORLD * PPO_MBOX_MOMENT_SLOT;
+                c->mbox_grad_slot = (((size_t)c->PS * sizeof(float)) + 255) & ~(size_t)255;
+                c->mbox_bytes = c->mbox_grad_off + 2 * (size_t)desc->world_size * c->mbox_grad_slot;
+                if (cudaMalloc(&c->mbox_mem, c->mbox_bytes) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(mailbox) failed"); break; }
+                cudaMemset(c->mbox_mem, 0, c->mbox_bytes);
+                c->mbox_peer[desc->rank] = c->mbox_mem;
+            }
+            c->use_graph = getenv("PPO_DISABLE_GRAPH") == nullptr;  // multi-GPU: only on the fast path (no NCCL inside a graph)
             c->graphs.resize(std::max(1, desc->noptepochs));
+            // R family: one CTA per tile of R_TM envs (x tpc tiles) for the whole rollout; needs the parameter vector in
+            // shared memory and all CTAs co-resident (grid barrier per env step)
+            if (coop_ok && c->d.O == c->d.A && getenv("PPO_DISABLE_PERSISTENT") == nullptr) {
+                const int ntiles = (desc->n_envs + R_TM - 1) / R_TM;
+                for (int tpc = 1; tpc <= 8 && !c->persistent_rollout; ++tpc) {
+                    RLayout L;
+                    L.init(c->d, tpc);
+                    if ((size_t)L.total_bytes > max_smem) break;
+                    const int grid = (ntiles + tpc - 1) / tpc;
+                    // when one CTA per SM is enough, ask for more than half of the shared memory so that the block scheduler
+                    // cannot put two CTAs on one SM (they would run at half speed and everybody waits at the step barrier)
+                    size_t smem = (size_t)L.total_bytes;
+                    if (grid <= c->sm_count) smem = std::max(smem, std::min(max_smem, (size_t)120 * 1024));
+                    if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                        cudaGetLastError();
+                        break;
+                    }
+                    int per = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rollout_persistent_kernel, R_NTH, smem);
+                    if (per > 0 && grid <= per * c->sm_count && grid <= SV_MAXBLK) {
+                        c->persistent_rollout = true;
+                        c->roll_grid = grid;
+                        c->roll_tpc = tpc;
+                        c->roll_smem = smem;
+                    }
+                }
+                if (c->persistent_rollout &&
+                    cudaMalloc(&c->roll_partial, sizeof(double) * 2 * (size_t)c->roll_grid * 2 * (c->d.O + 1)) != cudaSuccess) {
+                    st = fail(PPO_ERR_CUDA, "cudaMalloc(roll_partial) failed");
+                    break;
+                }
+            }
         }
     } while (0);
     if (st != PPO_OK) {
@@ -679,6 +759,53 @@ extern "C" int ppo_comm_init(ppo_core* c, const char id[PPO_COMM_ID_BYTES], int 
     memcpy(u.internal, id, PPO_COMM_ID_BYTES);
     TRY(nccl_check(g_nccl.CommInitRank(&c->comm, world_size, u, rank), "ncclCommInitRank"));
     return PPO_OK;
+}
+// peer mailboxes: cudaIpc handle of this rank's allocation / mapping of every peer's (one process per GPU, one node)
+extern "C" int ppo_comm_ipc_handle(ppo_core* c, char out[PPO_IPC_HANDLE_BYTES]) {
+    if (!c || !out) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (!c->mbox_mem) return fail(PPO_ERR_INVALID, "world_size is 1: no mailbox");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PPO_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    CU(cudaSetDevice(c->desc.device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->mbox_mem));
+    memcpy(out, &h, sizeof(h));
+    return PPO_OK;
+}
+extern "C" int ppo_comm_ipc_open(ppo_core* c, const char* handles, int world_size) {
+    if (!c || !handles) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (world_size != c->desc.world_size || !c->mbox_mem) return fail(PPO_ERR_INVALID, "world_size differs from the core's desc");
+    CU(cudaSetDevice(c->desc.device));
+    for (int r = 0; r < world_size; ++r) {
+        if (r == c->desc.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * PPO_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PPO_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (the NCCL path stays in use)", r, cudaGetErrorString(e));
+        }
+        c->mbox_peer[r] = static_cast<unsigned char*>(p);
+    }
+    c->mbox_ready = getenv("PPO_DISABLE_P2P") == nullptr;
+    return PPO_OK;
+}
+extern "C" int ppo_comm_set_p2p(ppo_core* c, int enable) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    if (enable) {
+        for (int r = 0; r < c->desc.world_size; ++r)
+            if (!c->mbox_peer[r]) return fail(PPO_ERR_INVALID, "mailbox of rank %d is not mapped (ppo_comm_ipc_open)", r);
+    }
+    c->mbox_ready = enable != 0 && c->desc.world_size > 1;
+    return PPO_OK;
+}
+// 1 when a peer-mailbox wait timed out since the last call (a peer died or was never launched)
+extern "C" int ppo_comm_error(ppo_core* c) {
+    if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    if (!c->sync_vars) return 0;
+    unsigned e = 0;
+    CU(cudaMemcpy(&e, c->sync_vars + SV_ERR, sizeof(e), cudaMemcpyDeviceToHost));
+    return e ? 1 : 0;
 }
 static int need_comm(ppo_core* c) {
     if (c->desc.world_size > 1 && !c->comm) return fail(PPO_ERR_COMM, "world_size %d but ppo_comm_init was not called", c->desc.world_size);
@@ -981,7 +1108,42 @@ static int rollout_synthetic_enqueue(ppo_core* c) {
 extern "C" int ppo_rollout_synthetic(ppo_core* c) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     CU(cudaSetDevice(c->desc.device));
-    if (!c->use_graph) return rollout_synthetic_enqueue(c);
+    if (c->persistent_rollout && fast_path(c)) {
+        const ppo_core_desc& D = c->desc;
+        RolloutArgs r{};
+        r.d = c->d; r.params = c->params; r.n = D.n_envs; r.T = D.n_steps; r.tpc = c->roll_tpc;
+        r.seed = D.seed; r.env_id0 = (uint32_t)D.env_offset; r.step_ctr = c->step_ctr; r.env = c->env; r.st = c->st; r.ret = c->ret;
+        r.norm_gamma = D.norm_gamma; r.clip_obs = D.clip_obs; r.clip_rew = D.clip_reward; r.eps = D.norm_epsilon;
+        r.norm_obs = D.norm_obs; r.norm_reward = D.norm_reward;
+        r.upd_obs = D.training && D.norm_obs; r.upd_ret = D.training && D.norm_reward;
+        r.partial = c->roll_partial; r.cur_obs = c->cur_obs; r.cur_dones = c->cur_dones; r.last_values = c->last_values;
+        r.obs_store = slab(c, B_OBS, 0); r.act_store = slab(c, B_ACTIONS, 0); r.val_store = slab(c, B_VALUES, 0);
+        r.nlp_store = slab(c, B_NEGLOGP, 0); r.dones_store = slab(c, B_DONES, 0); r.rew_store = slab(c, B_TRUE_REW, 0);
+        r.urew_store = slab(c, B_UNNORM_REW, 0); r.ret_store = slab(c, B_RETURNS, 0);
+        r.gamma = D.gamma; r.lam = D.lam;
+        r.bar_ctr = c->sync_vars + SV_ROLL_FLAGS; r.bar_gen = c->sync_vars + SV_ROLL_GEN;
+        r.n_global = D.n_envs * D.world_size;
+        r.mbox = make_mailbox(c, false); r.mbox_seq = c->sync_vars + SV_MOM_SEQ;
+        static long long* s_prof = nullptr;
+        if (getenv("PPO_ROLLOUT_PROF") && !s_prof) {
+            cudaMalloc(&s_prof, sizeof(long long) * 32);
+            cudaMemset(s_prof, 0, sizeof(long long) * 32);
+        }
+        r.prof = s_prof;
+        void* kargs[] = {&r};
+        CU(cudaLaunchCooperativeKernel((void*)rollout_persistent_kernel, dim3(c->roll_grid), dim3(R_NTH), kargs, c->roll_smem, c->stream));
+        c->ctr.kernel_launches++;
+        if (s_prof) {
+            long long h[32];
+            cudaStreamSynchronize(c->stream);
+            cudaMemcpy(h, s_prof, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "rollout phases (cycles):");
+            for (int i = 1; i < 32 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+            fprintf(stderr, "\n");
+        }
+        return PPO_OK;
+    }
+    if (!c->use_graph || !fast_path(c)) return rollout_synthetic_enqueue(c);
     // every launch argument of the rollout is a fixed device address (the Philox step counter lives on the device),
     // so the whole rollout is captured once and replayed; the training flag is baked into the captured launches
     ppo_core::EpochGraph& g = c->rollout_graph;
@@ -1136,16 +1298,19 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
     a.invB = 1.0f / (float)c->B_global;
     a.cliprange = cliprange;
     int train_grid = 0;
-    TRY(launch_train_kernel(c, a, !c->coop, &train_grid));
-    if (c->coop) {
+    const bool coop = c->coop && fast_path(c);
+    TRY(launch_train_kernel(c, a, !coop, &train_grid));
+    if (coop) {
         ReduceAdamArgs r{};
         r.partial = c->partial; r.G = train_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
+        r.bar_ctr = c->sync_vars + SV_COOP_FLAGS; r.bar_gen = c->sync_vars + SV_COOP_GEN;
+        r.mbox = make_mailbox(c, true); r.mbox_seq = c->sync_vars + SV_GRAD_SEQ;
         AdamArgs& ad = r.adam;
         ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
         ad.nblk = c->coop_grid; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
         ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
         ad.bpow_in = c->bpow + c->bpow_slot * 2; ad.bpow_out = c->bpow + (c->bpow_slot ^ 1) * 2;
-        ad.invB = a.invB; ad.inv_world = 1.0f;
+        ad.invB = a.invB; ad.inv_world = 1.0f / (float)W;
         ad.loss_row = c->loss_rows + (size_t)loss_row * 5; ad.gnorm_out = c->gnorm;
         void* kargs[] = {&r};
         CU(cudaLaunchCooperativeKernel((void*)grad_reduce_adam_coop_kernel, dim3(c->coop_grid), dim3(256), kargs, 0, c->stream));
@@ -1183,7 +1348,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         c->rng.random_shuffle(c->perm_host.data(), nb);  // compounded across epochs (ppo2.hpp:288)
         int* pinned = c->perm_pinned + (size_t)e * nb;
         memcpy(pinned, c->perm_host.data(), sizeof(int) * (size_t)nb);
-        if (!c->use_graph) {
+        if (!c->use_graph || !fast_path(c)) {
             TRY(prepare_epoch(c, pinned));
             for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
             continue;
@@ -1322,6 +1487,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
         if (c->fused) return "train_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "train_tile_kernel (fp32 FFMA, generic hidden sizes)";
     }
+    if (w == "rollout") return (c->persistent_rollout && fast_path(c)) ? "rollout_persistent_kernel (one cooperative launch per rollout)" : "per-step kernels";
     if (w == "policy") {
         if (c->fused) return "policy_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "policy_tile_kernel (fp32 FFMA, generic hidden sizes)";

@@ -1,0 +1,116 @@
+// Synchronisation primitives of the persistent kernels: a monotonic-counter grid barrier (all CTAs of a cooperative
+// launch) and the peer-memory mailbox used for the cross-GPU exchanges (VecNormalize moments, gradients) over
+// NVLink P2P stores — no NCCL call on the per-step / per-minibatch path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ppo {
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Grid barrier on a zero-initialised counter that only grows: generation g (1, 2, ...) completes when the counter
+// reaches g * nblocks.  All CTAs must be co-resident (cooperative launch).  One thread per CTA adds 1 after a
+// __threadfence and polls with plain volatile loads (an acquire load per poll iteration carries a fence each time:
+// measured 2x slower; per-CTA flag words polled by a warp: 4x slower), then fences once.  arrive/wait are split so that
+// independent work can sit between them; every thread of the CTA must call both (they contain __syncthreads).
+// `gen` = generations completed so far; it lives in device memory between launches so that a launch can be replayed
+// from a CUDA graph (wrap-around safe: only differences are compared).
+struct GridBarrier {
+    unsigned* ctr;
+    unsigned nblocks;
+    unsigned gen;
+    __device__ __forceinline__ void arrive() {
+        __syncthreads();  // all writes of this CTA issued
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(ctr, 1u);
+        }
+    }
+    __device__ __forceinline__ void wait() {
+        ++gen;
+        if (threadIdx.x == 0) {
+            const unsigned target = gen * nblocks;
+            while ((int)(*reinterpret_cast<volatile unsigned*>(ctr) - target) < 0) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void sync() {
+        arrive();
+        wait();
+    }
+};
+
+// Cross-GPU mailbox.  Every rank owns one device allocation, IPC-mapped into every peer of the node:
+//   flags   [channels][8] uint32          monotonic sequence numbers, one word per (channel, source rank)
+//   moments [2][world][512 B]             payload slots of the VecNormalize exchange, double-buffered by sequence parity
+//   grads   [2][world][PS floats]         payload slots of the gradient exchange
+// (a PeerMailbox value describes one payload region: data_off / slot_bytes)
+// A sender writes its payload into slot [seq & 1][my_rank] of EVERY rank (its own included) with plain stores
+// (NVLink P2P for the peers), fences system-wide and release-stores seq into flags[channel][my_rank] of that rank.
+// A receiver spins on its own flag words until all sources reached seq, then reads the slots in rank order — every
+// rank adds the same numbers in the same order, so replicated state stays bit-identical.  Two slots suffice: a sender
+// can be at most one sequence number ahead of the slowest receiver (it needs that receiver's next flag to go on).
+constexpr int PPO_MAX_WORLD = 8;
+constexpr int PPO_MBOX_CHANNELS = 1024;  // channel = cooperating CTA index (gradient slices); the last one carries the moments
+constexpr int PPO_MBOX_MOMENT_CHANNEL = PPO_MBOX_CHANNELS - 1;
+constexpr size_t PPO_MBOX_MOMENT_SLOT = 512;  // bytes: 2*(D+1)+1 doubles, D <= 32
+constexpr size_t PPO_MBOX_FLAG_BYTES = (size_t)PPO_MBOX_CHANNELS * PPO_MAX_WORLD * sizeof(unsigned);
+
+struct PeerMailbox {
+    unsigned char* base[PPO_MAX_WORLD];  // this rank's mapping of rank r's mailbox
+    int rank, world;
+    size_t data_off, slot_bytes;
+    unsigned* err;  // set to 1 when a wait timed out (a peer died): the caller reports PPO_ERR_COMM
+    __device__ __forceinline__ unsigned* flag(int r, int channel, int src) const {
+        return reinterpret_cast<unsigned*>(base[r]) + (size_t)channel * PPO_MAX_WORLD + src;
+    }
+    __device__ __forceinline__ unsigned char* slot(int r, unsigned seq, int src) const {
+        return base[r] + data_off + ((size_t)(seq & 1u) * world + src) * slot_bytes;
+    }
+    // one thread: publish "my payload for seq is complete" on `channel` to every rank
+    __device__ __forceinline__ void signal_all(int channel, unsigned seq) const {
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) st_release_sys(flag(r, channel, rank), seq);
+    }
+    // one thread: wait until every source rank published seq on `channel` (bounded: ~4 s)
+    __device__ __forceinline__ void wait_all(int channel, unsigned seq) const {
+        if (*reinterpret_cast<volatile unsigned*>(err)) return;  // a previous wait already timed out: do not stall again
+        const unsigned long long t0 = globaltimer_ns();
+        for (int src = 0; src < world; ++src) {
+            const unsigned* f = flag(rank, channel, src);
+            unsigned spins = 0;
+            while ((int)(*reinterpret_cast<const volatile unsigned*>(f) - seq) < 0) {
+                if (((++spins) & 0x3ffu) == 0u && globaltimer_ns() - t0 > 4000000000ull) {
+                    *err = 1u;
+                    return;
+                }
+            }
+        }
+        __threadfence_system();
+    }
+};
+
+}  // namespace ppo

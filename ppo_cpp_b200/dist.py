@@ -62,5 +62,22 @@ def setup_comm(core_module, core, rank: int, world: int):
     """Create the core's NCCL communicator: rank 0 makes the id, everyone joins."""
     if world == 1:
         return
+    import torch.distributed as dist
     uid = broadcast_bytes(core_module.comm_unique_id() if rank == 0 else None)
     core.comm_init(uid, rank, world)
+    # peer mailboxes: gather every rank's cudaIpc handle and map them (NVLink P2P); on failure the NCCL path stays
+    if os.environ.get("PPO_DISABLE_P2P"):
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, core.comm_ipc_handle())
+    ok = True
+    try:
+        core.comm_ipc_open(handles, world)
+    except Exception as ex:  # noqa: BLE001
+        ok = False
+        if rank == 0:
+            print(f"[ppo_cpp_b200] peer mailboxes unavailable, using NCCL for every exchange: {ex}", flush=True)
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):  # all or nothing: every rank must take the same path
+        core.comm_set_p2p(False)

@@ -16,18 +16,22 @@ from ppo_cpp_b200 import core  # noqa: E402
 from ppo_cpp_b200.dist import env_world, setup_comm  # noqa: E402
 
 
-def run(world, rank, device, n_envs_local, hidden, n_steps=32, nmb=4, epochs=2, updates=2):
+def run(world, rank, device, n_envs_local, hidden, n_steps=32, nmb=4, epochs=2, updates=2, p2p=True):
     c = core.PPOCore(device=device, hidden1=hidden[0], hidden2=hidden[1], n_envs=n_envs_local, n_steps=n_steps, nminibatches=nmb,
                      noptepochs=epochs, seed=99, rank=rank, world_size=world, env_offset=rank * n_envs_local,
                      n_envs_global=n_envs_local * world)
     c.init_orthogonal(5)
     setup_comm(core, c, rank, world)
+    if world > 1:
+        c.comm_set_p2p(p2p)  # True: peer mailboxes inside the persistent / cooperative kernels; False: NCCL for every exchange
+        assert ("persistent" in c.kernel_family("rollout")) == p2p or hidden[0] > 128
     c.shuffle_seed(42)
     c.synth_env_reset()
     losses = None
     for _ in range(updates):
         losses = c.learn_update_synthetic(3e-4, 0.2)
     out = dict(params=c.get_tensor("params"), losses=losses, stats=c.vecnorm_stats(), obs=c.rollout_get("obs"), returns=c.rollout_get("returns"))
+    assert not c.comm_error(), "a peer-mailbox wait timed out"
     c.close()
     return out
 
@@ -37,9 +41,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for hidden in ((4, 5), (64, 64)):
-        n_local = 32
-        sharded = run(world, rank, local, n_local, hidden)
+    for hidden, p2p in (((4, 5), True), ((64, 64), True), ((4, 5), False), ((64, 64), False)):
+        n_local = 48  # 1.5 tiles of the persistent rollout kernel per rank
+        sharded = run(world, rank, local, n_local, hidden, p2p=p2p)
+        tag = f"hidden {hidden} {'p2p mailbox' if p2p else 'nccl'}"
         if rank == 0:
             single = run(1, 0, local, n_local * world, hidden)
             moved = np.abs(single["params"]).max()
@@ -50,7 +55,7 @@ def main():
             obs1 = single["obs"].reshape(n_local * world, T, 18)[:n_local].reshape(-1, 18)
             dobs = np.abs(sharded["obs"] - obs1).max()
             same_count = sharded["stats"]["obs_count"] == single["stats"]["obs_count"]
-            print(f"hidden {hidden}: world {world}  param rel diff {dp:.2e}  loss diff {dl:.2e}  obs diff {dobs:.2e}  counts equal {same_count}")
+            print(f"{tag}: world {world}  param rel diff {dp:.2e}  loss diff {dl:.2e}  obs diff {dobs:.2e}  counts equal {same_count}")
             ok &= dp < 1e-5 and dl < 1e-5 and dobs < 1e-4 and same_count
         # every rank must hold bit-identical parameters after the replicated Adam
         t = torch.tensor(sharded["params"], device="cuda")
@@ -60,7 +65,7 @@ def main():
         flags = [None] * world
         dist.all_gather_object(flags, same)
         if rank == 0:
-            print(f"hidden {hidden}: replicas bit-identical {all(flags)}")
+            print(f"{tag}: replicas bit-identical {all(flags)}")
             ok &= all(flags)
     if rank == 0:
         print("MGPU_CHECK", "OK" if ok else "FAILED")

@@ -417,6 +417,42 @@ def test_rollout_synthetic_vs_oracle(core_mod, kat, init_weights, ckpt_weights, 
     c.close()
 
 
+@pytest.mark.parametrize("h1,h2,n_envs,n_steps", [(4, 5, 77, 40), (64, 64, 4096, 16), (64, 64, 33, 700), (4, 5, 40000, 6)])
+def test_rollout_persistent_equals_stepwise(core_mod, monkeypatch, h1, h2, n_envs, n_steps):
+    """The one-launch cooperative rollout kernel (R family) against the per-step kernels (policy step, env step,
+    VecNormalize moments/apply, GAE) over two consecutive rollouts: identical Philox streams and fp32 operation order;
+    only the fp64 summation order of the VecNormalize batch moments differs (sums are rounded to fp32 afterwards).
+    n_envs = 77 / 33 leave a ragged last tile, 40000 envs puts several tiles on one CTA, 700 steps cross every env's
+    episode boundary twice."""
+    rng = np.random.default_rng(5)
+    p = rand_params(rng, h1, h2)
+    res = []
+    for env in (None, "PPO_DISABLE_PERSISTENT"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=h1, hidden2=h2, n_envs=n_envs, n_steps=n_steps, nminibatches=1, noptepochs=1, seed=11)
+        assert ("persistent" in c.kernel_family("rollout")) == (env is None)
+        c.synth_env_reset()
+        c.rollout_synthetic()
+        first = {n: c.rollout_get(n) for n in ("dones", "obs")}
+        c.rollout_synthetic()
+        out = {n: c.rollout_get(n) for n in ("obs", "actions", "values", "neglogpacs", "dones", "true_rewards", "unnormalized_rewards", "returns")}
+        out["first_dones"], out["first_obs"] = first["dones"], first["obs"]
+        out["stats"] = c.vecnorm_stats()
+        res.append(out)
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    a, b = res
+    assert np.array_equal(a["dones"], b["dones"]) and np.array_equal(a["first_dones"], b["first_dones"])
+    assert np.array_equal(a["unnormalized_rewards"], b["unnormalized_rewards"]) or rel_err(a["unnormalized_rewards"], b["unnormalized_rewards"]) < 1e-5
+    for name in ("first_obs", "obs", "actions", "values", "neglogpacs", "true_rewards", "returns"):
+        assert rel_err(a[name], b[name]) < 2e-5, name
+    assert a["stats"]["obs_count"] == b["stats"]["obs_count"] and a["stats"]["ret_count"] == b["stats"]["ret_count"]
+    assert rel_err(a["stats"]["obs_mean"], b["stats"]["obs_mean"]) < 1e-5 and rel_err(a["stats"]["obs_var"], b["stats"]["obs_var"]) < 1e-5
+    assert rel_err(a["stats"]["ret_var"], b["stats"]["ret_var"]) < 1e-5
+
+
 def test_runner_host_env_protocol_equals_device_env(core_mod, ckpt_weights):
     """Runner::run through host buffers (act -> env.step on the host -> observe) with the oracle's synthetic env
     as the host env must reproduce the all-device rollout of the same seed."""
