@@ -502,75 +502,82 @@ struct ReduceAdamArgs {
     unsigned* mbox_seq; // device-resident sequence number of the gradient exchange
 };
 
-__global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const ReduceAdamArgs r) {
+// Body shared by the stand-alone cooperative kernel and the persistent epoch kernel (kernels_umma.cuh): `blk` of `nblk`
+// blocks of 256 threads.  b1p / b2p are the beta powers BEFORE this step.  Contains one grid barrier.
+__device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int blk, int nblk, GridBarrier& bar, unsigned seq,
+                                                   float b1p, float b2p, float* loss_row, long long* prof = nullptr) {
     __shared__ float part[4][64];
     __shared__ double red[8];
     __shared__ float s_scale;
     const AdamArgs& a = r.adam;
     const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
     const int nchunks = (r.PS + 63) >> 6;
-    GridBarrier bar{r.bar_ctr, gridDim.x, *r.bar_gen};
     const int world = r.mbox.world;
-    const unsigned seq = world > 1 ? (*r.mbox_seq + 1u) : 0u;
+    int pi = 0;
+#define RA_PROF()                                                   \
+    do {                                                            \
+        if (prof && threadIdx.x == 0 && pi < 8) prof[pi++] = clock64(); \
+    } while (0)
+    RA_PROF();
     float gsum[RA_MAXJ];
     double q = 0.0;
+    float acc[RA_MAXJ];
+    // phase 1: every load of this thread (all its chunks, 8 slabs at a time) is independent of the others
+#pragma unroll
+    for (int j = 0; j < RA_MAXJ; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int g0 = rg; g0 < r.G; g0 += 32) {
+        float v[RA_MAXJ][8];
+#pragma unroll
+        for (int j = 0; j < RA_MAXJ; ++j) {
+            const int c = (blk + j * nblk) * 64 + lane_c;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int g = g0 + 4 * u;
+                v[j][u] = (c < r.PS && g < r.G) ? __ldcg(r.partial + (size_t)g * r.PS + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RA_MAXJ; ++j)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[j] += v[j][u];
+    }
+    RA_PROF();
 #pragma unroll
     for (int j = 0; j < RA_MAXJ; ++j) {
         gsum[j] = 0.f;
-        const int chunk = blockIdx.x + j * gridDim.x;
+        const int chunk = blk + j * nblk;
         if (chunk >= nchunks) break;  // block-uniform
         const int c = chunk * 64 + lane_c;
-        float acc = 0.f;
-        if (c < r.PS) {
-            const float* p = r.partial + c;
-            int g = rg;
-#pragma unroll 1
-            for (; g + 28 < r.G; g += 32) {  // 8 independent loads in flight per thread
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(g + 4 * u) * r.PS];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc += v[u];
-            }
-            for (; g < r.G; g += 4) acc += p[(size_t)g * r.PS];
-        }
         __syncthreads();
-        part[rg][lane_c] = acc;
+        part[rg][lane_c] = acc[j];
         __syncthreads();
         if (rg == 0) {
             const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
             gsum[j] = (float)t;
-            if (world > 1 && c < r.PS) {
-                for (int dst = 0; dst < world; ++dst)
-                    reinterpret_cast<float*>(r.mbox.slot(dst, seq, r.mbox.rank))[c] = gsum[j];
+            if (world > 1 && c < r.PS) {  // LL store of (value, seq) into every rank's slot of this rank
+                for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gsum[j]), seq);
             }
         }
     }
-    if (world > 1) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            r.mbox.signal_all((int)blockIdx.x, seq);
-            r.mbox.wait_all((int)blockIdx.x, seq);
-        }
-        __syncthreads();
-        if (rg == 0) {
+    if (world > 1 && rg == 0) {
+        // allreduce: add the `world` values of every column in rank order (the same order on every rank)
 #pragma unroll
-            for (int j = 0; j < RA_MAXJ; ++j) {
-                const int chunk = blockIdx.x + j * gridDim.x;
-                if (chunk >= nchunks) break;
-                const int c = chunk * 64 + lane_c;
-                if (c < r.PS) {
-                    float t = 0.f;
-                    for (int src = 0; src < world; ++src) t += __ldcg(reinterpret_cast<const float*>(r.mbox.slot(r.mbox.rank, seq, src)) + c);
-                    gsum[j] = t;
-                }
+        for (int j = 0; j < RA_MAXJ; ++j) {
+            const int chunk = blk + j * nblk;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < r.PS) {
+                float t = 0.f;
+                for (int src = 0; src < world; ++src) t += __uint_as_float(r.mbox.ll_wait(seq, src, (size_t)c));
+                gsum[j] = t;
             }
         }
     }
     if (rg == 0) {
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j) {
-            const int chunk = blockIdx.x + j * gridDim.x;
+            const int chunk = blk + j * nblk;
             if (chunk >= nchunks) break;
             const int c = chunk * 64 + lane_c;
             if (c < r.PS) r.grad[c] = gsum[j];
@@ -580,11 +587,23 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const Reduce
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
     __syncthreads();
-    if (threadIdx.x == 0) r.sq_partial[blockIdx.x] = red[0] + red[1];  // warps 0,1 hold rg == 0
+    if (threadIdx.x == 0) r.sq_partial[blk] = red[0] + red[1];  // warps 0,1 hold rg == 0
+    // Adam state of this thread's columns: only this thread ever touches it, so it can be fetched ahead of the barrier
+    float am[RA_MAXJ], av[RA_MAXJ], ap[RA_MAXJ];
+#pragma unroll
+    for (int j = 0; j < RA_MAXJ; ++j) {
+        const int c = (blk + j * nblk) * 64 + lane_c;
+        const bool mine = rg == 0 && c < a.P;
+        am[j] = mine ? __ldcg(a.m + c) : 0.f;
+        av[j] = mine ? __ldcg(a.v + c) : 0.f;
+        ap[j] = mine ? __ldcg(a.params + c) : 0.f;
+    }
+    RA_PROF();
     bar.sync();
+    RA_PROF();
     if (threadIdx.x < 32) {
         double ss = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) ss += __ldcg(r.sq_partial + b);
+        for (int b = threadIdx.x; b < nblk; b += 32) ss += __ldcg(r.sq_partial + b);
         // fixed-order combine: lane partials summed by a butterfly (same order in every block and on every rank)
         ss = warp_sum(ss);
         if (threadIdx.x == 0) {
@@ -593,45 +612,54 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const Reduce
             float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
             if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
             s_scale = scale;
-            if (blockIdx.x == 0) {
-                *a.gnorm_out = gnorm;
-                *r.bar_gen = bar.gen;
-                if (world > 1) *r.mbox_seq = seq;
-            }
+            if (blk == 0) *a.gnorm_out = gnorm;
         }
     }
     __syncthreads();
+    RA_PROF();
     const int loss_chunk = (a.P >> 6);  // the chunk that holds column P (the loss sums start there)
-    if ((int)blockIdx.x == loss_chunk % (int)gridDim.x && threadIdx.x == 0) {
-        const float* Ls = r.grad + a.P;   // written above by this block (P + 8 <= PS may straddle into the next chunk:
-        float L[5];                        // read those through L2)
+    if (blk == loss_chunk % nblk && threadIdx.x == 0) {
+        const float* Ls = r.grad + a.P;  // columns P.. may straddle into another block's chunk: read through L2
+        float L[5];
         for (int k = 0; k < 5; ++k) L[k] = __ldcg(Ls + k);
-        a.loss_row[0] = L[L_PG] * a.invB;
-        a.loss_row[1] = 0.5f * (L[L_VF] * a.invB);
-        a.loss_row[2] = L[L_ENT] * a.inv_world;
-        a.loss_row[3] = 0.5f * (L[L_KL] * a.invB);
-        a.loss_row[4] = L[L_CLIP] * a.invB;
-        a.bpow_out[0] = __fmul_rn(a.bpow_in[0], a.beta1);
-        a.bpow_out[1] = __fmul_rn(a.bpow_in[1], a.beta2);
+        loss_row[0] = L[L_PG] * a.invB;
+        loss_row[1] = 0.5f * (L[L_VF] * a.invB);
+        loss_row[2] = L[L_ENT] * a.inv_world;
+        loss_row[3] = 0.5f * (L[L_KL] * a.invB);
+        loss_row[4] = L[L_CLIP] * a.invB;
     }
     if (rg == 0) {
-        const float b1p = a.bpow_in[0], b2p = a.bpow_in[1];
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j) {
-            const int chunk = blockIdx.x + j * gridDim.x;
+            const int chunk = blk + j * nblk;
             if (chunk >= nchunks) break;
             const int c = chunk * 64 + lane_c;
             if (c < a.P) {
                 const float g = __fmul_rn(gsum[j], s_scale);
-                float m = a.m[c], v = a.v[c];
+                float m = am[j], v = av[j];
                 m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
                 v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
                 a.m[c] = m;
                 a.v[c] = v;
-                a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+                a.params[c] = __fsub_rn(ap[j], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
             }
         }
+    }
+    RA_PROF();
+#undef RA_PROF
+}
+
+__global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const ReduceAdamArgs r) {
+    GridBarrier bar{r.bar_ctr, gridDim.x, *r.bar_gen};
+    const unsigned seq = r.mbox.world > 1 ? (*r.mbox_seq + 1u) : 0u;
+    const float b1p = r.adam.bpow_in[0], b2p = r.adam.bpow_in[1];
+    reduce_adam_device(r, (int)blockIdx.x, (int)gridDim.x, bar, seq, b1p, b2p, r.adam.loss_row);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        r.adam.bpow_out[0] = __fmul_rn(b1p, r.adam.beta1);
+        r.adam.bpow_out[1] = __fmul_rn(b2p, r.adam.beta2);
+        *r.bar_gen = bar.gen;
+        if (r.mbox.world > 1) *r.mbox_seq = seq;
     }
 }
 

@@ -43,6 +43,12 @@ struct RolloutArgs {
     int n_global;                 // envs over all ranks (rows of one VecNormalize batch)
     PeerMailbox mbox;             // multi-GPU: per-step exchange of the batch moments over NVLink P2P stores
     unsigned* mbox_seq;
+    // multi-GPU: the five train inputs (obs, actions, values, neglogp, returns) are stored into EVERY rank's buffers
+    // (byte offsets inside the IPC-mapped arena mbox.base[r]; rows of this rank start at row_off) — the rollout kernel
+    // performs the allgather of the rollout as it goes.  world == 1: the *_store pointers below are used.
+    size_t off_obs, off_act, off_val, off_nlp, off_ret;
+    size_t row_off;
+    unsigned* done_seq;  // sequence number of the end-of-rollout cross-rank barrier
     long long* prof;  // optional [32] phase timestamps of CTA 0 during env step 1 (PPO_ROLLOUT_PROF=1)
 };
 
@@ -52,6 +58,11 @@ struct RolloutArgs {
     } while (0)
 
 constexpr int R_TM = 32, R_NTH = 256;
+
+// rank r's copy of THIS rank's slab of a train-input buffer (row t = 0), or the local slab on a single GPU
+__device__ __forceinline__ float* rslab(const RolloutArgs& a, int r, size_t off, int width, float* local) {
+    return a.mbox.world > 1 ? reinterpret_cast<float*>(a.mbox.base[r] + off) + a.row_off * width : local;
+}
 
 struct RLayout {
     FLayout f;
@@ -117,6 +128,7 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
     GridBarrier bar{a.bar_ctr, gridDim.x, *a.bar_gen};
     const int world = a.mbox.world;
     const unsigned seq0 = world > 1 ? *a.mbox_seq : 0u;
+    const unsigned dseq0 = world > 1 ? *a.done_seq : 0u;
 
     // ---- one-time: weights, running statistics, per-env state
     stage_weights<NTH>(sW, a.params, d.P);
@@ -161,8 +173,8 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
             const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
             float* Xs = OBS + tl * O * TM;
             // -- store the observation the policy acts on (runner.hpp:75-78)
-            {
-                float* dst = a.obs_store + ((size_t)t * a.n + r0) * O;
+            for (int r = 0; r < world; ++r) {
+                float* dst = rslab(a, r, a.off_obs, O, a.obs_store) + ((size_t)t * a.n + r0) * O;
                 for (int e = tid; e < nv * O; e += NTH) {
                     const int m = e / O, k = e - m * O;
                     dst[e] = Xs[k * TM + m];
@@ -207,12 +219,14 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 }
                 const float nl = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, ss), __fmul_rn(PPO_HALF_LOG_2PI, (float)A)), sl);
                 const size_t idx = (size_t)t * a.n + row;
-                a.nlp_store[idx] = nl;
-                a.val_store[idx] = Vs[m];
+                for (int r = 0; r < world; ++r) {
+                    rslab(a, r, a.off_nlp, 1, a.nlp_store)[idx] = nl;
+                    rslab(a, r, a.off_val, 1, a.val_store)[idx] = Vs[m];
+                }
                 a.dones_store[idx] = DN[tl * TM + m];  // done flag of the previous env step (runner.hpp:110)
             }
-            {
-                float* dst = a.act_store + ((size_t)t * a.n + r0) * A;
+            for (int r = 0; r < world; ++r) {
+                float* dst = rslab(a, r, a.off_act, A, a.act_store) + ((size_t)t * a.n + r0) * A;
                 for (int e = tid; e < nv * A; e += NTH) {
                     const int m = e / A, j = e - m * A;
                     dst[e] = Ac[j * (TM + 1) + m];
@@ -323,17 +337,23 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
             if (world > 1) {
                 // CTA 0 publishes this rank's totals to every rank; every CTA then adds the `world` slots in rank order
                 const unsigned seq = seq0 + (unsigned)t + 1u;
-                if (blockIdx.x == 0) {
-                    if (tid < 2 * (D + 1))
-                        for (int dst = 0; dst < world; ++dst) reinterpret_cast<double*>(a.mbox.slot(dst, seq, a.mbox.rank))[tid] = csum[tid];
-                    __syncthreads();
-                    if (tid == 0) a.mbox.signal_all(PPO_MBOX_MOMENT_CHANNEL, seq);
+                // (LL words: 4 bytes of data + seq in one 8-byte store, no fence, the receivers poll the payload)
+                if (blockIdx.x == 0 && tid < 2 * (D + 1)) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(csum[tid]);
+                    for (int dst = 0; dst < world; ++dst) {
+                        uint2* sl = a.mbox.ll_slot(dst, seq, a.mbox.rank) + 2 * tid;
+                        ll_store(sl, (unsigned)bits, seq);
+                        ll_store(sl + 1, (unsigned)(bits >> 32), seq);
+                    }
                 }
-                if (tid == 0) a.mbox.wait_all(PPO_MBOX_MOMENT_CHANNEL, seq);
-                __syncthreads();
+                __syncthreads();  // CTA 0: csum has been read before it is overwritten below
                 if (tid < 2 * (D + 1)) {
                     double v = 0.0;
-                    for (int src = 0; src < world; ++src) v += __ldcg(reinterpret_cast<const double*>(a.mbox.slot(a.mbox.rank, seq, src)) + tid);
+                    for (int src = 0; src < world; ++src) {
+                        const unsigned lo = a.mbox.ll_wait(seq, src, (size_t)(2 * tid));
+                        const unsigned hi = a.mbox.ll_wait(seq, src, (size_t)(2 * tid + 1));
+                        v += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                    }
                     csum[tid] = v;
                 }
                 __syncthreads();
@@ -431,9 +451,22 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
             const float v = a.val_store[idx];
             const float delta = __fsub_rn(__fadd_rn(a.rew_store[idx], __fmul_rn(a.gamma, __fmul_rn(nextv, nextnt))), v);
             last = __fadd_rn(delta, __fmul_rn(gl, __fmul_rn(nextnt, last)));
-            a.ret_store[idx] = __fadd_rn(last, v);
+            const float rt = __fadd_rn(last, v);
+            for (int r = 0; r < world; ++r) rslab(a, r, a.off_ret, 1, a.ret_store)[idx] = rt;
             nextv = v;
             nextnt = 1.0f - a.dones_store[idx];
+        }
+    }
+    if (world > 1) {
+        // every rank's rows must have landed in every rank's buffers before anybody trains on them: system-scope fence
+        // per CTA, local grid barrier, then CTA 0 trades "rollout complete" flags with the peers
+        __syncthreads();
+        if (tid == 0) __threadfence_system();
+        bar.sync();
+        if (blockIdx.x == 0 && tid == 0) {
+            a.mbox.signal_all(PPO_MBOX_DONE_CHANNEL, dseq0 + 1u);
+            a.mbox.wait_all(PPO_MBOX_DONE_CHANNEL, dseq0 + 1u);
+            *a.done_seq = dseq0 + 1u;
         }
     }
     if (blockIdx.x == 0) {

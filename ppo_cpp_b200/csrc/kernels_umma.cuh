@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "kernels_misc.cuh"
 #include "kernels_mlp2.cuh"
 
 namespace ppo {
@@ -238,13 +239,26 @@ struct ObsRegs {
     }
 };
 
+// Persistent variant (PERSIST = true): ONE cooperative launch runs all the minibatches of an epoch.  Per minibatch:
+// weights re-staged from the (just updated) fp32 parameters -> tiles -> slabs | grid barrier | column reduce (+ peer
+// mailbox allreduce) + sum of squares | grid barrier | clip + Adam | grid barrier.  TMEM, mbarriers and the constant
+// operand blocks are set up once per epoch; 2 kernel launches per minibatch become 3 grid barriers.
+struct EpochArgs {
+    int M;                  // minibatches in this launch
+    int B;                  // slots per (global) minibatch
+    int rank_off;           // this rank processes slots [k*B + rank_off, k*B + rank_off + count)
+    const float2* mbstats;  // [M]
+    float* loss_rows;       // [M][5]
+    ReduceAdamArgs ra;
+};
+
 #define UMMA_PROF()                                                                                              \
     do {                                                                                                         \
         if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 32) a.prof[tower * 32 + prof_i++] = clock64();      \
     } while (0)
 
-template <int O, int A>
-__global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
+template <int O, int A, bool PERSIST>
+__global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, const EpochArgs ep) {
     static_assert(O % 2 == 0 && O >= 2 && O <= 30 && A % 2 == 0 && A >= 2 && A <= 32, "unsupported obs/act width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -273,9 +287,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
     long grow = 0;
     bool gvalid = false;
     float s_adv = 0.f, s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
+    int cur_slot0 = PERSIST ? ep.rank_off : a.slot0;
+    const float2* cur_mbstats = PERSIST ? ep.mbstats : a.mbstats;
     auto load_inputs = [&](int tile) {
-        const int s0 = a.slot0 + tile * TM;
-        const int nv = min(TM, a.slot0 + a.count - s0);
+        const int s0 = cur_slot0 + tile * TM;
+        const int nv = min(TM, cur_slot0 + a.count - s0);
         gvalid = tile < ntiles && gr < nv;
         grow = gvalid ? (long)(a.gather ? __ldg(a.gather + s0 + gr) : (s0 + gr)) : 0;
         xin.load(a.obs, grow, gh, gvalid);
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
             if (a.adv_direct) {
                 s_adv = __ldg(a.adv_direct + s0 + gr);
             } else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
-                const float2 st = __ldg(a.mbstats);
+                const float2 st = __ldg(cur_mbstats);
                 s_adv = __fdiv_rn(__fsub_rn(__fsub_rn(s_ret, s_oldv), st.x), st.y);
             }
         }
@@ -304,90 +320,23 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    {
-        // weights -> three bf16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
-        const float* P = a.params;
-        const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
-        const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
-        const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
-        float4 w1v[2][2], w0v[2];
-        float wpv[8];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {  // W1: 64 rows x 8 chunks = 512 tasks
-            const int e = tid + NTH * i, r = e >> 3, j = e & 7;
-            w1v[i][0] = __ldg(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j));
-            w1v[i][1] = __ldg(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j + 4));
-        }
-        {  // W0': rows < O weights, row O bias, rows up to 31 zero: 32 rows x 8 chunks = 256 tasks
-            const int r = tid >> 3, j = tid & 7;
-            const float* src = r < O ? (W0 + r * HID + 8 * j) : (B0 + 8 * j);
-            const bool nz = r <= O;
-            w0v[0] = nz ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            w0v[1] = nz ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (tower == 0) {  // Wpi [64 x A] -> chunks 0..3 of every row (columns >= A zero): 256 tasks
-            const int r = tid >> 2, j = tid & 3;
-            const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? __ldg(src + k) : 0.f;
-        }
-        float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
-        if (tid < HID) {
-            b1 = __ldg(P + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
-            wv = __ldg(P + d.off[T_VF_W] + tid);
-        }
-        if (tid < 32) {
-            ls = tid < A ? __ldg(P + d.off[T_LOGSTD] + tid) : 0.f;
-            bh = tid < A ? __ldg(P + d.off[T_PI_B] + tid) : 0.f;
-            bv = __ldg(P + d.off[T_VF_B]);
-        }
-        // ---- consume
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int e = tid + NTH * i, r = e >> 3, j = e & 7;
-            const float x[8] = {w1v[i][0].x, w1v[i][0].y, w1v[i][0].z, w1v[i][0].w, w1v[i][1].x, w1v[i][1].y, w1v[i][1].z, w1v[i][1].w};
-            store_chunk(smem + OFF_W1, W1_PIECE, chunk_off(r, j), x);
-        }
-        {
-            const int r = tid >> 3, j = tid & 7;
-            const float x[8] = {w0v[0].x, w0v[0].y, w0v[0].z, w0v[0].w, w0v[1].x, w0v[1].y, w0v[1].z, w0v[1].w};
-            store_chunk(smem + OFF_W0, W0_PIECE, chunk_off(r, j), x);
-        }
-        if (tower == 0) {
-            const int r = tid >> 2, j = tid & 3;
-            store_chunk(smem + OFF_WP, WP_PIECE, chunk_off(r, j), wpv);
-        } else {
-            for (int i = tid; i < 3 * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
-        }
-        // ones block: row 0 of each 8-row group = 1.0 (bf16 0x3F80), rows 1..7 = 0
-        if (tid < (int)ROW8_PIECE / 16) {
-            const uint32_t v = ((tid & 63) < 8) ? 0x3F803F80u : 0u;
-            reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
-        }
-        if (tid < HID) {
-            f32[F32_B1 + tid] = b1;
-            f32[F32_WV + tid] = wv;
-        }
-        if (tid < 32) {
-            f32[F32_BH + tid] = bh;
-            f32[F32_LS + tid] = ls;
-            f32[F32_SD + tid] = expf(ls);
-            f32[F32_ISD + tid] = 1.f / expf(ls);
-            const float sl = warp_sum(ls);  // lanes >= A contribute 0
-            if (tid == 0) {
-                f32[F32_MISC + 0] = bv;
-                f32[F32_MISC + 1] = sl;
-            }
-        }
+    // constant operand blocks: the V tower's dv rows (row 0 is rewritten per tile, rows 1..7 stay zero) and the ones block
+    // (row 0 of each 8-row group = 1.0 = bf16 0x3F80, rows 1..7 = 0)
+    if (tower != 0)
+        for (int i = tid; i < 3 * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < (int)ROW8_PIECE / 16) {
+        const uint32_t v = ((tid & 63) < 8) ? 0x3F803F80u : 0u;
+        reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
     }
-    xin.store(sY, gr, gh);
-    fence_async_smem();
+    // persistent state: grid barrier generation, mailbox sequence number, Adam's beta powers (every CTA tracks them)
+    GridBarrier bar{PERSIST ? ep.ra.bar_ctr : nullptr, 2u * gridDim.x, PERSIST ? *ep.ra.bar_gen : 0u};
+    unsigned mseq = (PERSIST && ep.ra.mbox.world > 1) ? *ep.ra.mbox_seq : 0u;
+    float b1p = PERSIST ? ep.ra.adam.bpow_in[0] : 0.f, b2p = PERSIST ? ep.ra.adam.bpow_in[1] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    UMMA_PROF();  // setup done, X' of the first tile staged
 
     // operand views
     const Operand opY_k = op_kmajor(sbase + OFF_Y, ACT_PIECE, TM);      // X' / dMU as A (m = sample)
@@ -412,9 +361,90 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
 
     const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
     uint32_t phA = 0, phB = 0;
-    float l_0 = 0.f, l_1 = 0.f, l_2 = 0.f, l_dbv = 0.f;  // pi: pg, kl, clipfrac sums; V: vf sum, dbv
-    bool accw = false;
+    float l_0, l_1, l_2, l_dbv;  // pi: pg, kl, clipfrac sums; V: vf sum, dbv (per minibatch)
+    bool accw;
     float h1r[32], h2r[32];
+
+    const int n_mb = PERSIST ? ep.M : 1;
+#define LDW(p) (PERSIST ? __ldcg(p) : __ldg(p))  // the persistent kernel re-reads parameters that it updates itself
+    for (int mb = 0; mb < n_mb; ++mb) {
+        {
+            // weights -> three bf16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
+            const float* P = a.params;
+            const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
+            const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
+            const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+            float4 w1v[2][2], w0v[2];
+            float wpv[8];
+    #pragma unroll
+            for (int i = 0; i < 2; ++i) {  // W1: 64 rows x 8 chunks = 512 tasks
+                const int e = tid + NTH * i, r = e >> 3, j = e & 7;
+                w1v[i][0] = LDW(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j));
+                w1v[i][1] = LDW(reinterpret_cast<const float4*>(W1 + r * HID + 8 * j + 4));
+            }
+            {  // W0': rows < O weights, row O bias, rows up to 31 zero: 32 rows x 8 chunks = 256 tasks
+                const int r = tid >> 3, j = tid & 7;
+                const float* src = r < O ? (W0 + r * HID + 8 * j) : (B0 + 8 * j);
+                const bool nz = r <= O;
+                w0v[0] = nz ? LDW(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w0v[1] = nz ? LDW(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (tower == 0) {  // Wpi [64 x A] -> chunks 0..3 of every row (columns >= A zero): 256 tasks
+                const int r = tid >> 2, j = tid & 3;
+                const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? LDW(src + k) : 0.f;
+            }
+            float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
+            if (tid < HID) {
+                b1 = LDW(P + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
+                wv = LDW(P + d.off[T_VF_W] + tid);
+            }
+            if (tid < 32) {
+                ls = tid < A ? LDW(P + d.off[T_LOGSTD] + tid) : 0.f;
+                bh = tid < A ? LDW(P + d.off[T_PI_B] + tid) : 0.f;
+                bv = LDW(P + d.off[T_VF_B]);
+            }
+            // ---- consume
+    #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int e = tid + NTH * i, r = e >> 3, j = e & 7;
+                const float x[8] = {w1v[i][0].x, w1v[i][0].y, w1v[i][0].z, w1v[i][0].w, w1v[i][1].x, w1v[i][1].y, w1v[i][1].z, w1v[i][1].w};
+                store_chunk(smem + OFF_W1, W1_PIECE, chunk_off(r, j), x);
+            }
+            {
+                const int r = tid >> 3, j = tid & 7;
+                const float x[8] = {w0v[0].x, w0v[0].y, w0v[0].z, w0v[0].w, w0v[1].x, w0v[1].y, w0v[1].z, w0v[1].w};
+                store_chunk(smem + OFF_W0, W0_PIECE, chunk_off(r, j), x);
+            }
+            if (tower == 0) {
+                const int r = tid >> 2, j = tid & 3;
+                store_chunk(smem + OFF_WP, WP_PIECE, chunk_off(r, j), wpv);
+            }
+            if (tid < HID) {
+                f32[F32_B1 + tid] = b1;
+                f32[F32_WV + tid] = wv;
+            }
+            if (tid < 32) {
+                f32[F32_BH + tid] = bh;
+                f32[F32_LS + tid] = ls;
+                f32[F32_SD + tid] = expf(ls);
+                f32[F32_ISD + tid] = 1.f / expf(ls);
+                const float sl = warp_sum(ls);  // lanes >= A contribute 0
+                if (tid == 0) {
+                    f32[F32_MISC + 0] = bv;
+                    f32[F32_MISC + 1] = sl;
+                }
+            }
+        }
+        xin.store(sY, gr, gh);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        UMMA_PROF();  // setup done, X' of the first tile staged
+        l_0 = l_1 = l_2 = l_dbv = 0.f;
+        accw = false;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // inputs of this tile (the registers are refilled with the next tile's before the end of the loop);
@@ -769,6 +799,35 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a) {
         }
     }
     UMMA_PROF();
+        if (PERSIST) {
+            // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
+            if (mb + 1 < n_mb) {  // the next minibatch's first tile: two dependent global loads, hidden behind the barriers
+                cur_slot0 = (mb + 1) * ep.B + ep.rank_off;
+                cur_mbstats = ep.mbstats + mb + 1;
+                load_inputs(blockIdx.x);
+            }
+            tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
+            bar.sync();
+            UMMA_PROF();  // barrier 1 passed
+            ++mseq;
+            reduce_adam_device(ep.ra, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), bar, mseq, b1p, b2p,
+                               ep.loss_rows + (size_t)mb * 5,
+                               (a.prof && blockIdx.x == 0 && mb == 1) ? a.prof + 64 + tower * 8 : nullptr);
+            b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
+            b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
+            UMMA_PROF();  // reduce + barrier 2 + Adam done
+            bar.sync();
+            tc_fence_after();
+            UMMA_PROF();  // barrier 3 passed
+        }
+    }  // minibatches
+#undef LDW
+    if (PERSIST && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        ep.ra.adam.bpow_out[0] = b1p;
+        ep.ra.adam.bpow_out[1] = b2p;
+        *ep.ra.bar_gen = bar.gen;
+        if (ep.ra.mbox.world > 1) *ep.ra.mbox_seq = mseq;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));

@@ -87,6 +87,7 @@ constexpr int F_TM_TRAIN = 64, F_NT_TRAIN = 512, F_TM_POLICY = 32, F_NT_POLICY =
 
 // ------------------------------------------------------------------------------------------------ the core
 enum { B_OBS, B_RETURNS, B_DONES, B_ACTIONS, B_VALUES, B_NEGLOGP, B_TRUE_REW, B_UNNORM_REW, B_COUNT };
+static inline bool is_global_buf(int b) { return b == B_OBS || b == B_RETURNS || b == B_ACTIONS || b == B_VALUES || b == B_NEGLOGP; }
 static const char* const kBufNames[B_COUNT] = {"obs", "returns", "dones", "actions", "values", "neglogpacs",
                                                "true_rewards", "unnormalized_rewards"};
 
@@ -136,9 +137,12 @@ struct ppo_core {
         float lr = 0.f, cliprange = 0.f;
         int bpow_slot = -1;
         uint64_t kernels = 0;
+        int flip = 0;  // beta-power slot parity change of one replay
     };
     std::vector<EpochGraph> graphs;
     EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
+    bool persistent_epoch = false;    // U family: all minibatches of an epoch in one cooperative launch
+    int epoch_grid = 0;
     bool persistent_rollout = false;  // R family: the whole rollout as one cooperative kernel
     int roll_grid = 0, roll_tpc = 0;
     size_t roll_smem = 0;
@@ -158,12 +162,14 @@ struct ppo_core {
     unsigned char* mbox_mem = nullptr;
     unsigned char* mbox_peer[PPO_MAX_WORLD] = {};
     size_t mbox_bytes = 0, mbox_grad_off = 0, mbox_grad_slot = 0;
+    size_t arena_off[8] = {};      // byte offsets of the five train-input buffers inside the arena
+    bool gathered = false;         // the train inputs of every rank are already in place (persistent rollout, P2P stores)
     bool mbox_ready = false;
     unsigned* sync_vars = nullptr;
     ppo_counters ctr{};
 };
 // sync_vars layout: scalars first, then three barrier flag arrays of SV_MAXBLK words each
-enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_SCALARS = 16, SV_MAXBLK = 2048,
+enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
        SV_COOP_FLAGS = SV_SCALARS, SV_ROLL_FLAGS = SV_COOP_FLAGS + SV_MAXBLK, SV_EPOCH_FLAGS = SV_ROLL_FLAGS + SV_MAXBLK,
        SV_COUNT = SV_EPOCH_FLAGS + SV_MAXBLK };
 
@@ -288,7 +294,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < B_COUNT; ++i)
-        if (c->buf[i]) cudaFree(c->buf[i]);
+        if (c->buf[i] && !(c->mbox_mem && is_global_buf(i))) cudaFree(c->buf[i]);
     if (c->perm_pinned) cudaFreeHost(c->perm_pinned);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -321,15 +327,33 @@ static int core_alloc(ppo_core* c) {
     c->n_batch_global = c->n_batch_local * W;
     c->B_global = c->n_batch_global / D.nminibatches;
     const int widths[B_COUNT] = {O, 1, 1, A, 1, 1, 1, 1};
+    c->PS = d.P + L_PAD;
+    if (W > 1) {
+        // one arena per rank, IPC-mapped by every peer: [mailbox flags | moment slots | gradient slots | the five train inputs].
+        // The persistent rollout kernel stores its rows straight into every rank's copy (NVLink P2P), so the buffers are
+        // already "allgathered" when the rollout ends.
+        if (W > PPO_MAX_WORLD) return fail(PPO_ERR_UNSUPPORTED, "world_size %d > %d", W, PPO_MAX_WORLD);
+        c->mbox_grad_off = PPO_MBOX_FLAG_BYTES + 2 * (size_t)PPO_MAX_WORLD * PPO_MBOX_MOMENT_SLOT;
+        c->mbox_grad_slot = (((size_t)c->PS * sizeof(uint2)) + 255) & ~(size_t)255;  // LL words: (value, seq)
+        size_t off = c->mbox_grad_off + 2 * (size_t)W * c->mbox_grad_slot;
+        for (int i = 0; i < B_COUNT; ++i) {
+            if (!is_global_buf(i)) continue;
+            c->arena_off[i] = off;
+            off += (((size_t)c->n_batch_global * widths[i] * sizeof(float)) + 255) & ~(size_t)255;
+        }
+        c->mbox_bytes = off;
+        CU(cudaMalloc(&c->mbox_mem, c->mbox_bytes));
+        CU(cudaMemsetAsync(c->mbox_mem, 0, c->mbox_bytes, c->stream));
+        c->mbox_peer[D.rank] = c->mbox_mem;
+    }
     for (int i = 0; i < B_COUNT; ++i) {
         c->buf_w[i] = widths[i];
-        // only the five train inputs are allgathered; the others stay local-sized
-        const bool global = (i == B_OBS || i == B_RETURNS || i == B_ACTIONS || i == B_VALUES || i == B_NEGLOGP);
-        ZA(c->buf[i], (size_t)(global ? c->n_batch_global : c->n_batch_local) * widths[i]);
+        // only the five train inputs are global ([rank][t][env_local][w] slabs); the others stay local-sized
+        if (W > 1 && is_global_buf(i)) c->buf[i] = reinterpret_cast<float*>(c->mbox_mem + c->arena_off[i]);
+        else ZA(c->buf[i], (size_t)(is_global_buf(i) ? c->n_batch_global : c->n_batch_local) * widths[i]);
     }
     ZA(c->perm_dev, c->n_batch_global); ZA(c->gather, c->n_batch_global);
     ZA(c->mbstats, D.nminibatches);
-    c->PS = d.P + L_PAD;
     c->max_train_grid = c->sm_count * 2;
     ZA(c->partial, (size_t)c->max_train_grid * c->PS); ZA(c->grad, c->PS);
     c->n_sq_blocks = (c->PS + 255) / 256;
@@ -412,15 +436,15 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
         }
         c->umma = c->d.H1 == umma::HID && c->d.H2 == umma::HID && c->d.O == 18 && c->d.A == 18 && umma::SMEM_BYTES <= max_smem &&
                   prop.major == 10 && getenv("PPO_DISABLE_UMMA") == nullptr && getenv("PPO_DISABLE_FUSED") == nullptr;
-        if (c->umma && cudaFuncSetAttribute(umma::train_umma_kernel<18, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) != cudaSuccess) {
+        if (c->umma && cudaFuncSetAttribute(umma::train_umma_kernel<18, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) != cudaSuccess) {
             st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(train_umma_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
         st = core_alloc(c);
         if (st != PPO_OK) break;
         if (c->umma && getenv("PPO_UMMA_PROF")) {
-            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 64) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
-            cudaMemset(c->umma_prof, 0, sizeof(long long) * 64);
+            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 96) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
+            cudaMemset(c->umma_prof, 0, sizeof(long long) * 96);
         }
         {
             int per_sm = 0, coop_ok = 0;
@@ -438,14 +462,24 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             }
             if (cudaMalloc(&c->sync_vars, sizeof(unsigned) * SV_COUNT) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sync_vars) failed"); break; }
             cudaMemset(c->sync_vars, 0, sizeof(unsigned) * SV_COUNT);
-            if (desc->world_size > 1) {
-                if (desc->world_size > PPO_MAX_WORLD) { st = fail(PPO_ERR_UNSUPPORTED, "world_size %d > %d", desc->world_size, PPO_MAX_WORLD); break; }
-                c->mbox_grad_off = PPO_MBOX_FLAG_BYTES + 2 * (size_t)PPO_MAX_WORLD * PPO_MBOX_MOMENT_SLOT;
-                c->mbox_grad_slot = (((size_t)c->PS * sizeof(float)) + 255) & ~(size_t)255;
-                c->mbox_bytes = c->mbox_grad_off + 2 * (size_t)desc->world_size * c->mbox_grad_slot;
-                if (cudaMalloc(&c->mbox_mem, c->mbox_bytes) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(mailbox) failed"); break; }
-                cudaMemset(c->mbox_mem, 0, c->mbox_bytes);
-                c->mbox_peer[desc->rank] = c->mbox_mem;
+            if (c->umma && coop_ok && getenv("PPO_DISABLE_PERSISTENT") == nullptr) {
+                const int per_rank = (int)(nbg / desc->nminibatches / desc->world_size);
+                const int ntiles = (per_rank + umma::TM - 1) / umma::TM;
+                const int grid = std::max(1, std::min(ntiles, c->sm_count / 2));
+                int per = 0;
+                if (cudaFuncSetAttribute(umma::train_umma_kernel<18, 18, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) == cudaSuccess)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, umma::train_umma_kernel<18, 18, true>, umma::NTH, umma::SMEM_BYTES);
+                else
+                    cudaGetLastError();
+                if (per > 0 && 2 * grid <= per * c->sm_count && nchunks <= 2 * grid * RA_MAXJ && 2 * grid <= PPO_MBOX_CHANNELS - 1) {
+                    c->persistent_epoch = true;
+                    c->epoch_grid = grid;
+                    if (2 * grid > std::max(c->coop_grid, c->n_sq_blocks)) {
+                        cudaFree(c->sq_partial);
+                        c->sq_partial = nullptr;
+                        if (cudaMalloc(&c->sq_partial, sizeof(double) * 2 * grid) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_partial) failed"); break; }
+                    }
+                }
             }
             c->use_graph = getenv("PPO_DISABLE_GRAPH") == nullptr;  // multi-GPU: only on the fast path (no NCCL inside a graph)
             c->graphs.resize(std::max(1, desc->noptepochs));
@@ -1038,6 +1072,7 @@ extern "C" int ppo_runner_reset(ppo_core* c, const float* raw_obs, ppo_mem mem) 
 }
 
 static int runner_act_device(ppo_core* c, int t) {
+    c->gathered = false;  // this rank's slab changes: the other ranks' copies are stale until the next allgather
     PolicyArgs a{};
     a.obs = c->cur_obs; a.n = c->desc.n_envs; a.eps = nullptr; a.mode = 0;
     a.action = c->cur_actions;
@@ -1123,7 +1158,10 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
         r.gamma = D.gamma; r.lam = D.lam;
         r.bar_ctr = c->sync_vars + SV_ROLL_FLAGS; r.bar_gen = c->sync_vars + SV_ROLL_GEN;
         r.n_global = D.n_envs * D.world_size;
-        r.mbox = make_mailbox(c, false); r.mbox_seq = c->sync_vars + SV_MOM_SEQ;
+        r.mbox = make_mailbox(c, false); r.mbox_seq = c->sync_vars + SV_MOM_SEQ; r.done_seq = c->sync_vars + SV_DONE_SEQ;
+        r.off_obs = c->arena_off[B_OBS]; r.off_act = c->arena_off[B_ACTIONS]; r.off_val = c->arena_off[B_VALUES];
+        r.off_nlp = c->arena_off[B_NEGLOGP]; r.off_ret = c->arena_off[B_RETURNS];
+        r.row_off = (size_t)D.rank * c->n_batch_local;
         static long long* s_prof = nullptr;
         if (getenv("PPO_ROLLOUT_PROF") && !s_prof) {
             cudaMalloc(&s_prof, sizeof(long long) * 32);
@@ -1133,6 +1171,7 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
         void* kargs[] = {&r};
         CU(cudaLaunchCooperativeKernel((void*)rollout_persistent_kernel, dim3(c->roll_grid), dim3(R_NTH), kargs, c->roll_smem, c->stream));
         c->ctr.kernel_launches++;
+        c->gathered = D.world_size > 1;  // the kernel stored this rank's rows into every rank's buffers
         if (s_prof) {
             long long h[32];
             cudaStreamSynchronize(c->stream);
@@ -1202,6 +1241,7 @@ extern "C" int ppo_rollout_set(ppo_core* c, const char* name, const float* in, s
     CU(cudaSetDevice(c->desc.device));
     const size_t n = (size_t)c->n_batch_local * c->buf_w[b];
     if (count != n) return fail(PPO_ERR_INVALID, "buffer '%s' has %zu floats, got %zu", name, n, count);
+    c->gathered = false;
     TRY(ensure_scratch(c, n));
     TRY(h2d(c, c->scratch, in, n));
     LAUNCH(c, import_flat_kernel, std::max(1, std::min(c->sm_count * 8, (int)((n + 255) / 256))), 256, 0, c->scratch,
@@ -1236,7 +1276,7 @@ extern "C" int ppo_host_random_shuffle(unsigned seed, int n, int epochs, int* pe
 }
 
 static int allgather_train_inputs(ppo_core* c) {
-    if (c->desc.world_size == 1) return PPO_OK;
+    if (c->desc.world_size == 1 || c->gathered) return PPO_OK;
     TRY(need_comm(c));
     const int ids[5] = {B_OBS, B_RETURNS, B_ACTIONS, B_VALUES, B_NEGLOGP};
     for (int b : ids) {
@@ -1269,7 +1309,7 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = tru
     if (c->umma) {  // tcgen05 path: one CTA per (tile of 128 samples, tower)
         const int ntiles = (a.count + umma::TM - 1) / umma::TM;
         grid = std::max(1, std::min(ntiles, c->sm_count / 2));
-        LAUNCH(c, (umma::train_umma_kernel<18, 18>), dim3(grid, 2), umma::NTH, umma::SMEM_BYTES, a);
+        LAUNCH(c, (umma::train_umma_kernel<18, 18, false>), dim3(grid, 2), umma::NTH, umma::SMEM_BYTES, a, umma::EpochArgs{});
     } else {
         const int tm = c->fused ? F_TM_TRAIN : c->tm;
         const int ntiles = (a.count + tm - 1) / tm;
@@ -1336,13 +1376,58 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
     return PPO_OK;
 }
 
+// all minibatches of epoch e in one cooperative launch (U family, persistent): see kernels_umma.cuh
+static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
+    const int W = c->desc.world_size, M = c->desc.nminibatches;
+    const int per_rank = c->B_global / W;
+    TrainArgs a{};
+    a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
+    a.gather = c->gather; a.mbstats = c->mbstats; a.adv_direct = nullptr; a.slot0 = 0; a.count = per_rank;
+    a.invB = 1.0f / (float)c->B_global; a.cliprange = cliprange;
+    a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef;
+    a.partial = c->partial; a.PS = c->PS; a.prof = c->umma_prof;
+    umma::EpochArgs ep{};
+    ep.M = M; ep.B = c->B_global; ep.rank_off = c->desc.rank * per_rank; ep.mbstats = c->mbstats;
+    ep.loss_rows = c->loss_rows + (size_t)e * M * 5;
+    ReduceAdamArgs& r = ep.ra;
+    r.partial = c->partial; r.G = c->epoch_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
+    r.bar_ctr = c->sync_vars + SV_EPOCH_FLAGS; r.bar_gen = c->sync_vars + SV_EPOCH_GEN;
+    r.mbox = make_mailbox(c, true); r.mbox_seq = c->sync_vars + SV_GRAD_SEQ;
+    AdamArgs& ad = r.adam;
+    ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
+    ad.nblk = 2 * c->epoch_grid; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
+    ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
+    ad.bpow_in = c->bpow + c->bpow_slot * 2; ad.bpow_out = c->bpow + (c->bpow_slot ^ 1) * 2;
+    ad.invB = a.invB; ad.inv_world = 1.0f / (float)W;
+    ad.loss_row = nullptr; ad.gnorm_out = c->gnorm;
+    void* kargs[] = {&a, &ep};
+    CU(cudaLaunchCooperativeKernel((void*)umma::train_umma_kernel<18, 18, true>, dim3(c->epoch_grid, 2), dim3(umma::NTH), kargs,
+                                   umma::SMEM_BYTES, c->stream));
+    c->ctr.kernel_launches++;
+    c->bpow_slot ^= 1;
+    return PPO_OK;
+}
+
 extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* mean_losses) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     CU(cudaSetDevice(c->desc.device));
     const int nb = c->n_batch_global, E = c->desc.noptepochs, M = c->desc.nminibatches;
+    static const bool timing = getenv("PPO_TIMING") != nullptr;
+    cudaEvent_t tg0 = nullptr, tg1 = nullptr;
+    if (timing) {
+        cudaEventCreate(&tg0); cudaEventCreate(&tg1);
+        cudaEventRecord(tg0, c->stream);
+    }
     TRY(allgather_train_inputs(c));
+    if (timing) cudaEventRecord(tg1, c->stream);
     // previous update's H2D copies out of the pinned permutation buffers must have finished
     CU(cudaStreamSynchronize(c->stream));
+    if (timing) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tg0, tg1);
+        fprintf(stderr, "[ppo timing] rank %d allgather of the rollout buffers: %.3f ms\n", c->desc.rank, ms);
+        cudaEventDestroy(tg0); cudaEventDestroy(tg1);
+    }
     for (int i = 0; i < nb; ++i) c->perm_host[i] = i;  // perm.setIdentity() once per update (ppo2.hpp:274-275)
     for (int e = 0; e < E; ++e) {
         c->rng.random_shuffle(c->perm_host.data(), nb);  // compounded across epochs (ppo2.hpp:288)
@@ -1350,7 +1435,9 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         memcpy(pinned, c->perm_host.data(), sizeof(int) * (size_t)nb);
         if (!c->use_graph || !fast_path(c)) {
             TRY(prepare_epoch(c, pinned));
-            for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
+            if (c->persistent_epoch && fast_path(c)) TRY(train_epoch_device(c, lr, cliprange, e));
+            else
+                for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
             continue;
         }
         ppo_core::EpochGraph& eg = c->graphs[e];
@@ -1364,11 +1451,14 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             int st = prepare_epoch(c, pinned);
-            for (int k = 0; k < M && st == PPO_OK; ++k) st = train_step_device(c, k, lr, cliprange, e * M + k);
+            if (st == PPO_OK && c->persistent_epoch && fast_path(c)) st = train_epoch_device(c, lr, cliprange, e);
+            else
+                for (int k = 0; k < M && st == PPO_OK; ++k) st = train_step_device(c, k, lr, cliprange, e * M + k);
             const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
             eg.kernels = c->ctr.kernel_launches - k0;
             c->ctr.kernel_launches = k0;  // nothing ran yet; replay accounts for them
             c->ctr.h2d_bytes = h0;
+            eg.flip = c->bpow_slot ^ slot0;
             c->bpow_slot = slot0;
             if (st != PPO_OK) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1384,7 +1474,23 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         c->ctr.graph_launches++;
         c->ctr.kernel_launches += eg.kernels;
         c->ctr.h2d_bytes += sizeof(int) * (size_t)nb;
-        if (M & 1) c->bpow_slot ^= 1;
+        c->bpow_slot ^= eg.flip;
+    }
+    if (c->umma_prof && c->persistent_epoch) {
+        static int printed = 0;
+        if (printed++ == 3) {
+            long long h[96];
+            cudaStreamSynchronize(c->stream);
+            cudaMemcpy(h, c->umma_prof, sizeof(h), cudaMemcpyDeviceToHost);
+            for (int t = 0; t < 2; ++t) {
+                fprintf(stderr, "umma epoch phases tower %d:", t);
+                for (int i = 1; i < 32 && h[t * 32 + i]; ++i) fprintf(stderr, " %lld", h[t * 32 + i] - h[t * 32 + i - 1]);
+                fprintf(stderr, "\n   reduce+adam (loads | chunks+sq+prefetch | barrier | norm | adam):");
+                for (int i = 1; i < 8 && h[64 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[64 + t * 8 + i] - h[64 + t * 8 + i - 1]);
+                fprintf(stderr, "\n");
+            }
+        }
+        cudaMemsetAsync(c->umma_prof, 0, sizeof(long long) * 96, c->stream);
     }
     if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
     CU(cudaGetLastError());
@@ -1483,6 +1589,8 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     if (!c || !which) return nullptr;
     const std::string w(which);
     if (w == "train") {
+        if (c->umma && c->persistent_epoch && fast_path(c))
+            return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";
         if (c->umma) return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators)";
         if (c->fused) return "train_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "train_tile_kernel (fp32 FFMA, generic hidden sizes)";

@@ -76,11 +76,25 @@ struct GridBarrier {
 constexpr int PPO_MAX_WORLD = 8;
 constexpr int PPO_MBOX_CHANNELS = 1024;  // channel = cooperating CTA index (gradient slices); the last one carries the moments
 constexpr int PPO_MBOX_MOMENT_CHANNEL = PPO_MBOX_CHANNELS - 1;
-constexpr size_t PPO_MBOX_MOMENT_SLOT = 512;  // bytes: 2*(D+1)+1 doubles, D <= 32
+constexpr int PPO_MBOX_DONE_CHANNEL = PPO_MBOX_CHANNELS - 2;  // end-of-rollout "my rows are in your buffers"
+constexpr size_t PPO_MBOX_MOMENT_SLOT = 2048;  // bytes: 2*(D+1) doubles as 2 LL words each, D <= 32
 constexpr size_t PPO_MBOX_FLAG_BYTES = (size_t)PPO_MBOX_CHANNELS * PPO_MAX_WORLD * sizeof(unsigned);
 
+// Low-latency ("LL") payload words: 4 bytes of data + the 4-byte sequence number in ONE 8-byte store.  An aligned
+// 8-byte store is a single transaction on NVLink, so data and flag become visible together: no fence and no separate
+// flag round trip (a __threadfence_system + flag exchange measured ~10 us per exchange between two B200s; this is one
+// NVLink one-way latency).  The receiver polls the payload words themselves.
+__device__ __forceinline__ void ll_store(uint2* p, unsigned data, unsigned seq) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
+}
+__device__ __forceinline__ uint2 ll_load(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 struct PeerMailbox {
-    unsigned char* base[PPO_MAX_WORLD];  // this rank's mapping of rank r's mailbox
+    unsigned char* base[PPO_MAX_WORLD];  // this rank's mapping of rank r's arena
     int rank, world;
     size_t data_off, slot_bytes;
     unsigned* err;  // set to 1 when a wait timed out (a peer died): the caller reports PPO_ERR_COMM
@@ -90,12 +104,29 @@ struct PeerMailbox {
     __device__ __forceinline__ unsigned char* slot(int r, unsigned seq, int src) const {
         return base[r] + data_off + ((size_t)(seq & 1u) * world + src) * slot_bytes;
     }
-    // one thread: publish "my payload for seq is complete" on `channel` to every rank
+    __device__ __forceinline__ uint2* ll_slot(int r, unsigned seq, int src) const { return reinterpret_cast<uint2*>(slot(r, seq, src)); }
+    // spin until word i of source `src` carries `seq` (bounded: ~4 s, then the error flag is raised and 0 returned)
+    __device__ __forceinline__ unsigned ll_wait(unsigned seq, int src, size_t i) const {
+        const uint2* p = ll_slot(rank, seq, src) + i;
+        uint2 v = ll_load(p);
+        if (v.y == seq) return v.x;
+        if (*reinterpret_cast<volatile unsigned*>(err)) return 0u;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (true) {
+            v = ll_load(p);
+            if (v.y == seq) return v.x;
+            if (((++spins) & 0x3ffu) == 0u && globaltimer_ns() - t0 > 4000000000ull) {
+                *err = 1u;
+                return 0u;
+            }
+        }
+    }
+    // fenced flag protocol (used once per rollout for "all my rows are in your buffers")
     __device__ __forceinline__ void signal_all(int channel, unsigned seq) const {
         __threadfence_system();
         for (int r = 0; r < world; ++r) st_release_sys(flag(r, channel, rank), seq);
     }
-    // one thread: wait until every source rank published seq on `channel` (bounded: ~4 s)
     __device__ __forceinline__ void wait_all(int channel, unsigned seq) const {
         if (*reinterpret_cast<volatile unsigned*>(err)) return;  // a previous wait already timed out: do not stall again
         const unsigned long long t0 = globaltimer_ns();

@@ -453,6 +453,35 @@ def test_rollout_persistent_equals_stepwise(core_mod, monkeypatch, h1, h2, n_env
     assert rel_err(a["stats"]["ret_var"], b["stats"]["ret_var"]) < 1e-5
 
 
+@pytest.mark.parametrize("n_envs,n_steps,nmb", [(256, 32, 2), (4096, 16, 8), (1000, 8, 2)])
+def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps, nmb):
+    """[64,64]: the persistent epoch kernel (all minibatches of an epoch in one cooperative launch: tcgen05 tiles, column
+    reduce, global norm, Adam, three grid barriers per minibatch) against the launch-per-minibatch path over two
+    updates.  Same arithmetic; only the partition of the sum-of-squares partials differs."""
+    rng = np.random.default_rng(8)
+    p = rand_params(rng, 64, 64)
+    res = []
+    for env in (None, "PPO_DISABLE_PERSISTENT"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=64, hidden2=64, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=3, seed=21)
+        assert ("persistent" in c.kernel_family("train")) == (env is None)
+        c.shuffle_seed(7)
+        c.synth_env_reset()
+        losses = [c.learn_update_synthetic(3e-4, 0.2) for _ in range(2)]
+        res.append(dict(losses=np.stack(losses), params=c.get_tensor("params"), m=c.get_tensor("adam_m"), v=c.get_tensor("adam_v"),
+                        b1=c.get_tensor("beta1_power"), b2=c.get_tensor("beta2_power")))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    a, b = res
+    moved = np.abs(a["params"] - p).max()
+    assert np.abs(a["params"] - b["params"]).max() < 1e-5 * moved + 1e-9
+    assert rel_err(a["losses"], b["losses"]) < 1e-5
+    assert rel_err(a["m"], b["m"]) < 1e-5 and rel_err(a["v"], b["v"]) < 1e-5
+    assert np.array_equal(a["b1"], b["b1"]) and np.array_equal(a["b2"], b["b2"])
+
+
 def test_runner_host_env_protocol_equals_device_env(core_mod, ckpt_weights):
     """Runner::run through host buffers (act -> env.step on the host -> observe) with the oracle's synthetic env
     as the host env must reproduce the all-device rollout of the same seed."""
