@@ -111,6 +111,7 @@ def load():
         "ppo_host_random_shuffle": ([C.c_uint, C.c_int, C.c_int, ip], C.c_int),
         "ppo_train_update": ([core, C.c_float, C.c_float, fp], C.c_int),
         "ppo_train_set_permutation": ([core, ip, C.c_int], C.c_int),
+        "ppo_train_get_permutation": ([core, C.c_int, ip, C.c_int], C.c_int),
         "ppo_train_minibatch": ([core, C.c_int, C.c_float, C.c_float, fp, fp], C.c_int),
         "ppo_advnorm": ([core, fp, fp, C.c_int, fp], C.c_int),
         "ppo_loss_grad": ([core, fp, fp, fp, fp, fp, fp, C.c_int, C.c_float, fp, fp], C.c_int),

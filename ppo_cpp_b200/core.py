@@ -89,6 +89,7 @@ class PPOCore:
         self.O, self.A = d.obs_dim, d.act_dim
         self.n_envs, self.n_steps = d.n_envs, d.n_steps
         self.n_batch = d.n_envs * d.n_steps
+        self.n_batch_global = self.n_batch * max(1, d.world_size)
         self.P = self.tensor_size("params_trainable")
         self.Pq = self.tensor_size("params")
 
@@ -263,6 +264,11 @@ class PPOCore:
     def train_set_permutation(self, perm):
         p = np.ascontiguousarray(perm, np.int32)
         _check(self.lib, self.lib.ppo_train_set_permutation(self._h, p.ctypes.data, p.size))
+
+    def train_get_permutation(self, epoch):
+        out = np.zeros(self.n_batch_global, np.int32)
+        _check(self.lib, self.lib.ppo_train_get_permutation(self._h, epoch, out.ctypes.data, out.size))
+        return out
 
     def train_minibatch(self, k, lr, cliprange):
         losses, grads = np.zeros(5, np.float32), np.zeros(self.P, np.float32)

@@ -43,6 +43,16 @@ public:
         }
     }
 
+    // the last 31 raw words, oldest first (x[k-31] .. x[k-1]): the whole generator state
+    void get_window(uint32_t out[31]) const {
+        for (int t = 0; t < 31; ++t) out[t] = ring_[(f_ + t) % 31];
+    }
+    void set_window(const uint32_t in[31]) {
+        for (int t = 0; t < 31; ++t) ring_[t] = in[t];
+        f_ = 0;   // slot f holds x[k-31], slot r = f - 3 holds x[k-3]
+        r_ = 28;
+    }
+
 private:
     uint32_t ring_[31];
     int f_ = 3, r_ = 0;

@@ -343,11 +343,15 @@ __global__ void build_gather_kernel(const int* __restrict__ perm, int n_batch, i
 
 // per-minibatch advantage statistics (ppo2.hpp:401-405): one CTA per minibatch.
 // mean = sum(ret-val)/B ; var = sum((adv-mean)^2)/B ; denom = float(sqrt(var) + 1e-8)
+// blockIdx.y = epoch when the gather lists / statistics of several epochs are laid out with the given strides
 __global__ void advnorm_stats_kernel(const float* __restrict__ ret, const float* __restrict__ val,
-                                     const int* __restrict__ gather, int B, float2* __restrict__ stats) {
+                                     const int* __restrict__ gather, int B, float2* __restrict__ stats,
+                                     size_t gather_stride = 0, int stats_stride = 0) {
     __shared__ double red[32];
     __shared__ float s_mean;
     const int k = blockIdx.x, tid = threadIdx.x;
+    if (gather) gather += (size_t)blockIdx.y * gather_stride;
+    stats += (size_t)blockIdx.y * stats_stride;
     const int* g = gather ? gather + (size_t)k * B : nullptr;
     double s = 0.0;
     for (int i = tid; i < B; i += blockDim.x) {

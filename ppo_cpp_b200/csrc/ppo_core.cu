@@ -18,6 +18,7 @@
 #include "kernels_mlp.cuh"
 #include "kernels_mlp2.cuh"
 #include "kernels_rollout.cuh"
+#include "kernels_shuffle.cuh"
 #include "kernels_umma.cuh"
 #include "meta_parser.h"
 
@@ -149,6 +150,17 @@ struct ppo_core {
     double* roll_partial = nullptr;
 
     GlibcRand rng{1};
+    // device-side std::random_shuffle (kernels_shuffle.cuh): generator window + work arrays for all epochs of an update
+    bool gpu_shuffle = false, rng_on_device = false;
+    uint32_t* rng_win = nullptr;
+    shuf::Tables* shuf_tab = nullptr;
+    int *sh_j = nullptr, *sh_cnt = nullptr, *sh_off = nullptr, *sh_cur = nullptr, *sh_list = nullptr, *sh_sigma = nullptr,
+        *sh_perm = nullptr, *sh_gather = nullptr, *sh_btot = nullptr;
+    float2* sh_mbstats = nullptr;
+    uint32_t* win_pinned = nullptr;
+    const int* cur_gather = nullptr;       // gather list / advantage statistics of the epoch being trained
+    const float2* cur_mbstats = nullptr;
+    EpochGraph update_graph;               // GPU-shuffle path: the whole update (permutations + all epochs) as one graph
     std::vector<int> perm_host;
     int* perm_pinned = nullptr;  // [noptepochs][n_batch_global]
     float* stage = nullptr;      // pinned staging
@@ -285,12 +297,15 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->rollout_graph.exec) cudaGraphExecDestroy(c->rollout_graph.exec);
+    if (c->update_graph.exec) cudaGraphExecDestroy(c->update_graph.exec);
+    if (c->win_pinned) cudaFreeHost(c->win_pinned);
     void* dev_ptrs[] = {c->params, c->adam_m, c->adam_v, c->bpow, c->st.obs_mean, c->st.obs_var, c->st.obs_count,
                         c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
                         c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
                         c->nrew, c->step_ctr, c->env.state, c->env.t_env, c->env.resets, c->perm_dev, c->gather,
                         c->mbstats, c->partial, c->grad, c->loss_rows, c->loss_mean, c->gnorm, c->sq_partial, c->scratch,
-                        c->roll_partial};
+                        c->roll_partial, c->rng_win, c->shuf_tab, c->sh_j, c->sh_cnt, c->sh_off, c->sh_cur, c->sh_list, c->sh_sigma,
+                        c->sh_perm, c->sh_gather, c->sh_btot, c->sh_mbstats};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < B_COUNT; ++i)
@@ -353,6 +368,25 @@ static int core_alloc(ppo_core* c) {
         else ZA(c->buf[i], (size_t)(is_global_buf(i) ? c->n_batch_global : c->n_batch_local) * widths[i]);
     }
     ZA(c->perm_dev, c->n_batch_global); ZA(c->gather, c->n_batch_global);
+    {
+        const long long E = D.noptepochs, nbg = c->n_batch_global;
+        c->gpu_shuffle = E >= 1 && nbg >= 2 && E * (nbg - 1) < 0x7fffffffLL && getenv("PPO_DISABLE_GPU_SHUFFLE") == nullptr;
+        if (c->gpu_shuffle) {
+            const size_t en = (size_t)E * nbg, en1 = (size_t)E * (nbg + 1);
+            const int nb = (int)((nbg + 1 + shuf::SCAN_TILE - 1) / shuf::SCAN_TILE);
+            ZA(c->rng_win, 31); ZA(c->shuf_tab, 1);
+            ZA(c->sh_j, en); ZA(c->sh_cnt, en1); ZA(c->sh_off, en1); ZA(c->sh_cur, en1); ZA(c->sh_list, en); ZA(c->sh_sigma, en);
+            ZA(c->sh_perm, en); ZA(c->sh_gather, en); ZA(c->sh_btot, (size_t)E * nb); ZA(c->sh_mbstats, (size_t)E * D.nminibatches);
+            CU(cudaMallocHost(&c->win_pinned, 31 * sizeof(uint32_t)));
+            static shuf::Tables host_tab;
+            static bool host_tab_ready = false;
+            if (!host_tab_ready) {
+                shuf::build_tables(host_tab);
+                host_tab_ready = true;
+            }
+            CU(cudaMemcpyAsync(c->shuf_tab, &host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, c->stream));
+        }
+    }
     ZA(c->mbstats, D.nminibatches);
     c->max_train_grid = c->sm_count * 2;
     ZA(c->partial, (size_t)c->max_train_grid * c->PS); ZA(c->grad, c->PS);
@@ -1255,6 +1289,7 @@ extern "C" int ppo_rollout_set(ppo_core* c, const char* name, const float* in, s
 extern "C" int ppo_shuffle_seed(ppo_core* c, unsigned seed) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     c->rng.srand(seed);
+    c->rng_on_device = false;  // the host object is authoritative again; the next device shuffle uploads its window
     return PPO_OK;
 }
 extern "C" int ppo_host_srand_rand(unsigned seed, int count, int* out) {
@@ -1292,8 +1327,10 @@ static int prepare_epoch(ppo_core* c, const int* perm_pinned_or_host) {
     CU(cudaMemcpyAsync(c->perm_dev, perm_pinned_or_host, sizeof(int) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
     c->ctr.h2d_bytes += sizeof(int) * (size_t)nb;
     LAUNCH(c, build_gather_kernel, (nb + 255) / 256, 256, 0, c->perm_dev, nb, c->desc.n_steps, c->desc.n_envs, c->gather);
-    LAUNCH(c, advnorm_stats_kernel, c->desc.nminibatches, 512, 0, c->buf[B_RETURNS], c->buf[B_VALUES], c->gather, c->B_global, c->mbstats);
+    LAUNCH(c, advnorm_stats_kernel, c->desc.nminibatches, 512, 0, c->buf[B_RETURNS], c->buf[B_VALUES], c->gather, c->B_global, c->mbstats, (size_t)0, 0);
     CU(cudaGetLastError());
+    c->cur_gather = c->gather;
+    c->cur_mbstats = c->mbstats;
     return PPO_OK;
 }
 
@@ -1330,8 +1367,8 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
     const int per_rank = c->B_global / W;
     TrainArgs a{};
     a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
-    a.gather = c->gather;
-    a.mbstats = c->mbstats + k;
+    a.gather = c->cur_gather;
+    a.mbstats = c->cur_mbstats + k;
     a.adv_direct = nullptr;
     a.slot0 = k * c->B_global + c->desc.rank * per_rank;
     a.count = per_rank;
@@ -1376,18 +1413,53 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
     return PPO_OK;
 }
 
+// GPU-shuffle path: every epoch's permutation, gather list and advantage statistics from device kernels
+// (kernels_shuffle.cuh), then the epochs back to back.  Nothing here waits for the host.
+static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int loss_row);
+static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e);
+static int enqueue_update_gpu_shuffle(ppo_core* c, float lr, float cliprange) {
+    const int n = c->n_batch_global, E = c->desc.noptepochs, M = c->desc.nminibatches;
+    const long long total = (long long)E * (n - 1);
+    CU(cudaMemsetAsync(c->sh_cnt, 0, sizeof(int) * (size_t)E * (n + 1), c->stream));
+    const int draw_threads = (int)((total + shuf::L - 1) / shuf::L);
+    LAUNCH(c, shuf::shuffle_draw_kernel, (std::max(draw_threads, E) + 127) / 128, 128, 0, c->rng_win, c->shuf_tab, n, E, c->sh_j);
+    LAUNCH(c, shuf::shuffle_advance_kernel, 1, 32, 0, c->rng_win, c->shuf_tab, (unsigned long long)total);
+    const dim3 gn((n + 255) / 256, E);
+    LAUNCH(c, shuf::shuffle_count_kernel, gn, 256, 0, c->sh_j, n, c->sh_cnt);
+    const int nb = (n + 1 + shuf::SCAN_TILE - 1) / shuf::SCAN_TILE;
+    LAUNCH(c, shuf::shuffle_scan_totals_kernel, dim3(nb, E), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot);
+    LAUNCH(c, shuf::shuffle_scan_blocks_kernel, E, shuf::SCAN_TILE, 0, nb, c->sh_btot);
+    LAUNCH(c, shuf::shuffle_scan_final_kernel, dim3(nb, E), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot, c->sh_off, c->sh_cur);
+    LAUNCH(c, shuf::shuffle_scatter_kernel, gn, 256, 0, c->sh_j, n, c->sh_cur, c->sh_list);
+    LAUNCH(c, shuf::shuffle_resolve_kernel, gn, 256, 0, c->sh_j, c->sh_off, c->sh_list, n, c->sh_sigma);
+    for (int e = 0; e < E; ++e)
+        LAUNCH(c, shuf::shuffle_compose_kernel, (n + 255) / 256, 256, 0, e ? c->sh_perm + (size_t)(e - 1) * n : (const int*)nullptr,
+               c->sh_sigma + (size_t)e * n, n, c->desc.n_steps, c->desc.n_envs, c->sh_perm + (size_t)e * n, c->sh_gather + (size_t)e * n);
+    LAUNCH(c, advnorm_stats_kernel, dim3(M, E), 512, 0, c->buf[B_RETURNS], c->buf[B_VALUES], c->sh_gather, c->B_global, c->sh_mbstats, (size_t)n, M);
+    CU(cudaGetLastError());
+    for (int e = 0; e < E; ++e) {
+        c->cur_gather = c->sh_gather + (size_t)e * n;
+        c->cur_mbstats = c->sh_mbstats + (size_t)e * M;
+        if (c->persistent_epoch && fast_path(c)) TRY(train_epoch_device(c, lr, cliprange, e));
+        else
+            for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
+    }
+    c->perm_set = true;  // cur_gather / cur_mbstats describe the last epoch
+    return PPO_OK;
+}
+
 // all minibatches of epoch e in one cooperative launch (U family, persistent): see kernels_umma.cuh
 static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
     const int W = c->desc.world_size, M = c->desc.nminibatches;
     const int per_rank = c->B_global / W;
     TrainArgs a{};
     a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
-    a.gather = c->gather; a.mbstats = c->mbstats; a.adv_direct = nullptr; a.slot0 = 0; a.count = per_rank;
+    a.gather = c->cur_gather; a.mbstats = c->cur_mbstats; a.adv_direct = nullptr; a.slot0 = 0; a.count = per_rank;
     a.invB = 1.0f / (float)c->B_global; a.cliprange = cliprange;
     a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef;
     a.partial = c->partial; a.PS = c->PS; a.prof = c->umma_prof;
     umma::EpochArgs ep{};
-    ep.M = M; ep.B = c->B_global; ep.rank_off = c->desc.rank * per_rank; ep.mbstats = c->mbstats;
+    ep.M = M; ep.B = c->B_global; ep.rank_off = c->desc.rank * per_rank; ep.mbstats = c->cur_mbstats;
     ep.loss_rows = c->loss_rows + (size_t)e * M * 5;
     ReduceAdamArgs& r = ep.ra;
     r.partial = c->partial; r.G = c->epoch_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
@@ -1420,13 +1492,69 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
     }
     TRY(allgather_train_inputs(c));
     if (timing) cudaEventRecord(tg1, c->stream);
-    // previous update's H2D copies out of the pinned permutation buffers must have finished
-    CU(cudaStreamSynchronize(c->stream));
+    // host-shuffle path: the previous update's H2D copies out of the pinned permutation buffers must have finished
+    if (!(c->gpu_shuffle && fast_path(c)) || timing) CU(cudaStreamSynchronize(c->stream));
     if (timing) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, tg0, tg1);
         fprintf(stderr, "[ppo timing] rank %d allgather of the rollout buffers: %.3f ms\n", c->desc.rank, ms);
         cudaEventDestroy(tg0); cudaEventDestroy(tg1);
+    }
+    if (c->gpu_shuffle && fast_path(c) && E > 0) {
+        // the generator state moves to the device (once; ppo_shuffle_seed moves it back to the host object)
+        if (!c->rng_on_device) {
+            c->rng.get_window(c->win_pinned);
+            CU(cudaMemcpyAsync(c->rng_win, c->win_pinned, 31 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->rng_on_device = true;
+        }
+        ppo_core::EpochGraph& ug = c->update_graph;
+        if (!c->use_graph) {
+            TRY(enqueue_update_gpu_shuffle(c, lr, cliprange));
+        } else {
+            if (!ug.exec || ug.lr != lr || ug.cliprange != cliprange || ug.bpow_slot != c->bpow_slot) {
+                if (ug.exec) {
+                    cudaGraphExecDestroy(ug.exec);
+                    ug.exec = nullptr;
+                }
+                const int slot0 = c->bpow_slot;
+                const uint64_t k0 = c->ctr.kernel_launches;
+                cudaGraph_t graph = nullptr;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                const int st = enqueue_update_gpu_shuffle(c, lr, cliprange);
+                const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                ug.kernels = c->ctr.kernel_launches - k0;
+                c->ctr.kernel_launches = k0;
+                ug.flip = c->bpow_slot ^ slot0;
+                c->bpow_slot = slot0;
+                if (st != PPO_OK) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return st;
+                }
+                if (ce != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaStreamEndCapture(update) failed: %s", cudaGetErrorString(ce));
+                const cudaError_t ie = cudaGraphInstantiate(&ug.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaGraphInstantiate(update) failed: %s", cudaGetErrorString(ie));
+                ug.lr = lr; ug.cliprange = cliprange; ug.bpow_slot = slot0;
+            }
+            CU(cudaGraphLaunch(ug.exec, c->stream));
+            c->ctr.graph_launches++;
+            c->ctr.kernel_launches += ug.kernels;
+            c->bpow_slot ^= ug.flip;
+        }
+        if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
+        CU(cudaGetLastError());
+        if (mean_losses) {
+            TRY(d2h(c, mean_losses, c->loss_mean, 5));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        return PPO_OK;
+    }
+    if (c->rng_on_device) {  // host path after a device shuffle: bring the generator state back
+        CU(cudaMemcpyAsync(c->win_pinned, c->rng_win, 31 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->rng.set_window(c->win_pinned);
+        c->rng_on_device = false;
     }
     for (int i = 0; i < nb; ++i) c->perm_host[i] = i;  // perm.setIdentity() once per update (ppo2.hpp:274-275)
     for (int e = 0; e < E; ++e) {
@@ -1497,6 +1625,21 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
     if (mean_losses) {
         TRY(d2h(c, mean_losses, c->loss_mean, 5));
         CU(cudaStreamSynchronize(c->stream));
+    }
+    return PPO_OK;
+}
+
+extern "C" int ppo_train_get_permutation(ppo_core* c, int epoch, int* out, int n) {
+    if (!c || !out) return fail(PPO_ERR_INVALID, "NULL argument");
+    if (n != c->n_batch_global) return fail(PPO_ERR_INVALID, "permutation has %d entries, n_batch is %d", c->n_batch_global, n);
+    if (epoch < 0 || epoch >= c->desc.noptepochs) return fail(PPO_ERR_INVALID, "epoch %d out of range", epoch);
+    CU(cudaSetDevice(c->desc.device));
+    if (c->gpu_shuffle && fast_path(c)) {
+        CU(cudaMemcpyAsync(out, c->sh_perm + (size_t)epoch * n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    } else {
+        CU(cudaStreamSynchronize(c->stream));
+        memcpy(out, c->perm_pinned + (size_t)epoch * n, sizeof(int) * (size_t)n);
     }
     return PPO_OK;
 }
@@ -1628,7 +1771,7 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
                 const int k = i % c->desc.nminibatches, per_rank = c->B_global / W;
                 TrainArgs a{};
                 a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
-                a.gather = c->gather; a.mbstats = c->mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
+                a.gather = c->cur_gather; a.mbstats = c->cur_mbstats + k; a.slot0 = k * c->B_global + c->desc.rank * per_rank; a.count = per_rank;
                 a.invB = 1.0f / (float)c->B_global; a.cliprange = 0.2f;
                 a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef / (float)W; a.vf_coef = c->desc.vf_coef; a.partial = c->partial; a.PS = c->PS;
                 if (w == "train_fwdbwd") {

@@ -482,6 +482,56 @@ def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps
     assert np.array_equal(a["b1"], b["b1"]) and np.array_equal(a["b2"], b["b2"])
 
 
+@pytest.mark.parametrize("n_envs,n_steps,epochs,seed", [(1, 2, 1, 1), (3, 7, 4, 42), (16, 64, 3, 7), (257, 33, 2, 123456), (4096, 64, 10, 42)])
+def test_device_random_shuffle_bit_exact(core_mod, n_envs, n_steps, epochs, seed):
+    """The permutations built on the device (parallel glibc rand() stream by polynomial jump-ahead + parallel resolution
+    of the swap chain, kernels_shuffle.cuh) must equal std::srand(seed) + std::random_shuffle bit for bit: every epoch of
+    an update (compounded, ppo2.hpp:274-288) and the continuation of the rand() stream into the next update."""
+    n = n_envs * n_steps
+    nmb = next(m for m in (4, 3, 1) if n % m == 0 and n // m >= 2) if n >= 64 else 1
+    c = make_core(core_mod, None, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=epochs, seed=3)
+    c.init_orthogonal(1)
+    c.shuffle_seed(seed)
+    c.synth_env_reset()
+    c.rollout_synthetic()
+    c.train_update(1e-4, 0.2)
+    want = core_mod.host_random_shuffle(seed, n, epochs)
+    for e in range(epochs):
+        assert np.array_equal(c.train_get_permutation(e), want[e]), f"update 0 epoch {e}"
+    # second update: identity again, the rand() stream goes on where the first update stopped
+    c.train_update(1e-4, 0.2)
+    if n <= 20000:
+        stream = core_mod.host_rand(seed, 2 * epochs * (n - 1))[epochs * (n - 1):]
+        a = np.arange(n, dtype=np.int32)
+        k = 0
+        for e in range(epochs):
+            for i in range(1, n):
+                j = int(stream[k]) % (i + 1)
+                k += 1
+                a[i], a[j] = a[j], a[i]
+            assert np.array_equal(c.train_get_permutation(e), a), f"update 1 epoch {e}"
+    c.close()
+
+
+def test_device_shuffle_equals_host_shuffle_training(core_mod, monkeypatch):
+    """Same training run with the permutations from the device kernels and from the host restatement."""
+    rng = np.random.default_rng(4)
+    p = rand_params(rng, 64, 64)
+    res = []
+    for env in (None, "PPO_DISABLE_GPU_SHUFFLE"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=64, hidden2=64, n_envs=512, n_steps=16, nminibatches=4, noptepochs=3, seed=21)
+        c.shuffle_seed(99)
+        c.synth_env_reset()
+        losses = [c.learn_update_synthetic(3e-4, 0.2) for _ in range(3)]
+        res.append((np.stack(losses), c.get_tensor("params")))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
 def test_runner_host_env_protocol_equals_device_env(core_mod, ckpt_weights):
     """Runner::run through host buffers (act -> env.step on the host -> observe) with the oracle's synthetic env
     as the host env must reproduce the all-device rollout of the same seed."""
