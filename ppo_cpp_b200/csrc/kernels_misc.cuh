@@ -530,13 +530,13 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
 #pragma unroll
     for (int j = 0; j < RA_MAXJ; ++j) acc[j] = 0.f;
 #pragma unroll 1
-    for (int g0 = rg; g0 < r.G; g0 += 32) {
-        float v[RA_MAXJ][8];
+    for (int g0 = rg; g0 < r.G; g0 += 64) {  // 16 slabs x RA_MAXJ chunks in flight per thread: one L2 round trip for G <= 64
+        float v[RA_MAXJ][16];
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j) {
             const int c = (blk + j * nblk) * 64 + lane_c;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const int g = g0 + 4 * u;
                 v[j][u] = (c < r.PS && g < r.G) ? __ldcg(r.partial + (size_t)g * r.PS + c) : 0.f;
             }
@@ -544,7 +544,7 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc[j] += v[j][u];
+            for (int u = 0; u < 16; ++u) acc[j] += v[j][u];
     }
     RA_PROF();
 #pragma unroll

@@ -286,27 +286,34 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     ObsRegs<O> xin;
     long grow = 0;
     bool gvalid = false;
-    float s_adv = 0.f, s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
+    float s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
     int cur_slot0 = PERSIST ? ep.rank_off : a.slot0;
     const float2* cur_mbstats = PERSIST ? ep.mbstats : a.mbstats;
-    auto load_inputs = [&](int tile) {
-        const int s0 = cur_slot0 + tile * TM;
-        const int nv = min(TM, cur_slot0 + a.count - s0);
+    // input staging is split so that the two dependent global round trips (gather index -> rows) can be issued early and
+    // consumed late: load_index, then load_rows (addresses need the index), the arithmetic happens at the tile's start
+    float s_advd = 0.f;
+    float2 s_st = make_float2(0.f, 1.f);
+    int in_s0 = 0;
+    auto load_index = [&](int tile) {
+        in_s0 = cur_slot0 + tile * TM;
+        const int nv = min(TM, cur_slot0 + a.count - in_s0);
         gvalid = tile < ntiles && gr < nv;
-        grow = gvalid ? (long)(a.gather ? __ldg(a.gather + s0 + gr) : (s0 + gr)) : 0;
+        grow = gvalid ? (long)(a.gather ? __ldg(a.gather + in_s0 + gr) : (in_s0 + gr)) : 0;
+    };
+    auto load_rows = [&]() {
         xin.load(a.obs, grow, gh, gvalid);
-        s_adv = s_ret = s_oldn = s_oldv = 0.f;
+        s_ret = s_oldn = s_oldv = s_advd = 0.f;
         if (gh == 0 && gvalid) {
             s_ret = __ldg(a.ret + grow);
             s_oldv = __ldg(a.val + grow);
             s_oldn = __ldg(a.nlp + grow);
-            if (a.adv_direct) {
-                s_adv = __ldg(a.adv_direct + s0 + gr);
-            } else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
-                const float2 st = __ldg(cur_mbstats);
-                s_adv = __fdiv_rn(__fsub_rn(__fsub_rn(s_ret, s_oldv), st.x), st.y);
-            }
+            if (a.adv_direct) s_advd = __ldg(a.adv_direct + in_s0 + gr);
+            else s_st = __ldg(cur_mbstats);
         }
+    };
+    auto load_inputs = [&](int tile) {
+        load_index(tile);
+        load_rows();
     };
     load_inputs(blockIdx.x);
 
@@ -449,7 +456,9 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // inputs of this tile (the registers are refilled with the next tile's before the end of the loop);
         // gr == row for both column halves, so grow is the rollout row of this thread's sample
-        const float c_adv = s_adv, c_ret = s_ret, c_oldn = s_oldn, c_oldv = s_oldv;
+        const float c_ret = s_ret, c_oldn = s_oldn, c_oldv = s_oldv;
+        // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
+        const float c_adv = (gh == 0 && gvalid) ? (a.adv_direct ? s_advd : __fdiv_rn(__fsub_rn(__fsub_rn(s_ret, s_oldv), s_st.x), s_st.y)) : 0.f;
         const long c_grow = grow;
         const bool valid = gvalid;
 
@@ -707,6 +716,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         }
     }
 
+    if (PERSIST && mb + 1 < n_mb) {  // gather index of the next minibatch's first tile: in flight during the flush
+        cur_slot0 = (mb + 1) * ep.B + ep.rank_off;
+        cur_mbstats = ep.mbstats + mb + 1;
+        load_index(blockIdx.x);
+    }
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
     // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15)
@@ -801,11 +815,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     UMMA_PROF();
         if (PERSIST) {
             // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
-            if (mb + 1 < n_mb) {  // the next minibatch's first tile: two dependent global loads, hidden behind the barriers
-                cur_slot0 = (mb + 1) * ep.B + ep.rank_off;
-                cur_mbstats = ep.mbstats + mb + 1;
-                load_inputs(blockIdx.x);
-            }
+            if (mb + 1 < n_mb) load_rows();  // next minibatch's first tile (index issued before the flush): lands during the barriers
             tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
             bar.sync();
             UMMA_PROF();  // barrier 1 passed
