@@ -1,0 +1,272 @@
+// "S family": train kernel for the reference's own tiny networks (the shipped graph is MLP [4,5], 334 trainable
+// parameters) — one THREAD per sample, everything in registers.
+//
+// Replaces the loss / autodiff sub-graph of one PPO2::_train_step (ppo2/ppo2.hpp:430-470, GRAPH:6889-23699); math and
+// TF tie-breaking rules are those of SURVEY §3.5b, identical to the tile kernels.
+//
+// Why a separate family: a [4,5] layer is a 4x5 matrix — the tile kernels (4x4 register tiles over a 64-sample tile,
+// one __syncthreads per layer) leave 250 of 256 threads idle in most phases and reach 1 % of the HBM roofline on the
+// C5 buffer (profiles/r1_v4_c5_microbench.jsonl).  Here
+//   * the parameter vector sits in shared memory and is read with LDS.128 broadcasts (one load per 4 FMAs),
+//   * a thread loads its gathered observation / action rows (2 x 72 B), runs both towers forward, the loss, and the
+//     hand-derived backward pass out of registers (all loops unrolled at compile time: dims are template parameters),
+//   * the P per-sample gradient contributions are summed over the 32 samples of a warp by a transpose through shared
+//     memory, 32 parameters at a time: lane l ends up with the warp's sum of contribution l.  Each lane therefore owns
+//     P/32 accumulators (11 for [4,5]) for the whole grid-stride loop,
+//   * warps are combined through shared memory in a fixed order and the CTA writes one slab of the usual layout, so the
+//     cooperative reduce + clip + Adam kernel is shared with the other families.
+#pragma once
+#include "kernels_mlp.cuh"
+
+namespace ppo {
+namespace small {
+
+constexpr int NTH = 128;
+
+// v[0..31] per lane  ->  returns (in every lane l) the sum over the 32 lanes of their v[l], through a per-warp
+// [32][TR_LD] shared-memory tile: 32 conflict-free scalar stores (lane-consecutive addresses), 8 LDS.128 of the lane's
+// own row (row stride 36 floats: the 8 lanes of a quarter-warp hit disjoint bank groups), 32 adds in a fixed order.
+// (A shuffle butterfly needs 31 SHFL + 62 FSEL + warp-sync bookkeeping per 32 values: 2.5x the instructions.)
+constexpr int TR_LD = 36;
+__device__ __forceinline__ float transpose_reduce32(const float (&v)[32], float* tile, int lane) {
+    __syncwarp();  // previous readers of the tile are done
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tile[i * TR_LD + lane] = v[i];
+    __syncwarp();
+    const float4* row = reinterpret_cast<const float4*>(tile + lane * TR_LD);
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 t = row[q];
+        s += t.x;
+        s += t.y;
+        s += t.z;
+        s += t.w;
+    }
+    return s;
+}
+
+template <int O, int A, int H1, int H2>
+struct Dims {
+    // offsets of the 13 trainable tensors in the flat parameter vector (device_common.cuh order)
+    static constexpr int PI0W = 0, PI0B = PI0W + O * H1, VF0W = PI0B + H1, VF0B = VF0W + O * H1, PI1W = VF0B + H1,
+                         PI1B = PI1W + H1 * H2, VF1W = PI1B + H2, VF1B = VF1W + H1 * H2, VFW = VF1B + H2, VFB = VFW + H2,
+                         PIW = VFB + 1, PIB = PIW + H2 * A, LS = PIB + A, P = LS + A;
+    static constexpr int GROUPS = (P + 31) / 32;
+};
+
+template <int O, int A, int H1, int H2>
+__global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
+    using D = Dims<O, A, H1, H2>;
+    static_assert(O % 2 == 0 && A % 2 == 0, "rows are read as float2");
+    __shared__ __align__(16) float sW[(D::P + 3 + 4) & ~3];
+    __shared__ float s_part[NTH / 32][D::GROUPS * 32 + 4];
+    __shared__ __align__(16) float s_tile[NTH / 32][32 * TR_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < D::P; i += NTH) sW[i] = __ldg(a.params + i);
+    __syncthreads();
+
+    float sd[A], isd[A];
+    float sum_ls = 0.f;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        const float ls = sW[D::LS + j];
+        sd[j] = expf(ls);
+        isd[j] = 1.f / sd[j];
+        sum_ls += ls;
+    }
+    const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+    float accg[D::GROUPS];
+#pragma unroll
+    for (int g = 0; g < D::GROUPS; ++g) accg[g] = 0.f;
+    float l_pg = 0.f, l_vf = 0.f, l_kl = 0.f, l_cf = 0.f;
+
+    const int nwarp_tiles = (a.count + 31) / 32;
+    for (int wt = blockIdx.x * (NTH / 32) + warp; wt < nwarp_tiles; wt += gridDim.x * (NTH / 32)) {
+        const int slot = a.slot0 + wt * 32 + lane;
+        const bool valid = wt * 32 + lane < a.count;
+        float x[O], act[A];
+        float adv = 0.f, R = 0.f, oldn = 0.f, oldv = 0.f;
+        {
+            const long row = valid ? (long)(a.gather ? __ldg(a.gather + slot) : slot) : 0;
+            const float2* xs = reinterpret_cast<const float2*>(a.obs + row * O);
+            const float2* as = reinterpret_cast<const float2*>(a.act + row * A);
+#pragma unroll
+            for (int k = 0; k < O / 2; ++k) {
+                const float2 v = valid ? __ldg(xs + k) : make_float2(0.f, 0.f);
+                x[2 * k] = v.x;
+                x[2 * k + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < A / 2; ++j) {
+                const float2 v = valid ? __ldg(as + j) : make_float2(0.f, 0.f);
+                act[2 * j] = v.x;
+                act[2 * j + 1] = v.y;
+            }
+            if (valid) {
+                R = __ldg(a.ret + row);
+                oldv = __ldg(a.val + row);
+                oldn = __ldg(a.nlp + row);
+                if (a.adv_direct) {
+                    adv = __ldg(a.adv_direct + slot);
+                } else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
+                    const float2 st = __ldg(a.mbstats);
+                    adv = __fdiv_rn(__fsub_rn(__fsub_rn(R, oldv), st.x), st.y);
+                }
+            }
+        }
+        // ---- forward, both towers (GRAPH:6889-9187)
+        float h1[H1], g1[H1], h2[H2], g2[H2], mu[A];
+#pragma unroll
+        for (int n = 0; n < H1; ++n) {
+            float sp = 0.f, sv = 0.f;
+#pragma unroll
+            for (int k = 0; k < O; ++k) {
+                sp = fmaf(x[k], sW[D::PI0W + k * H1 + n], sp);
+                sv = fmaf(x[k], sW[D::VF0W + k * H1 + n], sv);
+            }
+            h1[n] = tanhf(sp + sW[D::PI0B + n]);
+            g1[n] = tanhf(sv + sW[D::VF0B + n]);
+        }
+#pragma unroll
+        for (int n = 0; n < H2; ++n) {
+            float sp = 0.f, sv = 0.f;
+#pragma unroll
+            for (int k = 0; k < H1; ++k) {
+                sp = fmaf(h1[k], sW[D::PI1W + k * H2 + n], sp);
+                sv = fmaf(g1[k], sW[D::VF1W + k * H2 + n], sv);
+            }
+            h2[n] = tanhf(sp + sW[D::PI1B + n]);
+            g2[n] = tanhf(sv + sW[D::VF1B + n]);
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < H2; ++k) v = fmaf(g2[k], sW[D::VFW + k], v);
+        v += sW[D::VFB];
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < H2; ++k) s = fmaf(h2[k], sW[D::PIW + k * A + j], s);
+            mu[j] = s + sW[D::PIB + j];
+        }
+        // ---- loss stage (GRAPH:9428-11446) and dL/dmu, dL/dlogstd contributions, dL/dv
+        float dmu[A], dls[A], dv = 0.f;
+        {
+            float z[A], ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                z[j] = (act[j] - mu[j]) * isd[j];
+                ss += z[j] * z[j];
+            }
+            float g_nlp = 0.f;
+            if (valid) {
+                const float nlp = (0.5f * ss + PPO_HALF_LOG_2PI * (float)A) + sum_ls;
+                const float ratio = expf(oldn - nlp);                          // GRAPH:10423-10447
+                const float pg1 = -adv * ratio;
+                const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);          // clip_by_value = max(min(x,hi),lo)
+                const bool take1 = pg1 >= pg2;                                 // ties -> unclipped branch
+                g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
+                l_pg += take1 ? pg1 : pg2;
+                const float dn = nlp - oldn;
+                l_kl += dn * dn;
+                l_cf += (fabsf(ratio - 1.f) > a.cliprange) ? 1.f : 0.f;
+                // value loss (GRAPH:10213-10400)
+                const float dvo = v - oldv;
+                const float vc = oldv + fmaxf(fminf(dvo, a.cliprange), -a.cliprange);
+                const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+                const bool tk = l1 >= l2;  // ties -> unclipped branch
+                l_vf += tk ? l1 : l2;
+                const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
+                dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (v - R) : (inr ? 2.f * (vc - R) : 0.f));
+            }
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                dmu[j] = g_nlp * (-z[j] * isd[j]);
+                dls[j] = g_nlp * (1.f - z[j] * z[j]);
+            }
+        }
+        // ---- backward through the towers (TanhGrad(y, dy) = dy * (1 - y^2))
+        float dp2[H2], dg2[H2], dp1[H1], dg1[H1];
+#pragma unroll
+        for (int k = 0; k < H2; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) s = fmaf(dmu[j], sW[D::PIW + k * A + j], s);
+            dp2[k] = s * (1.f - h2[k] * h2[k]);
+            dg2[k] = dv * sW[D::VFW + k] * (1.f - g2[k] * g2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < H1; ++k) {
+            float sp = 0.f, sv = 0.f;
+#pragma unroll
+            for (int n = 0; n < H2; ++n) {
+                sp = fmaf(dp2[n], sW[D::PI1W + k * H2 + n], sp);
+                sv = fmaf(dg2[n], sW[D::VF1W + k * H2 + n], sv);
+            }
+            dp1[k] = sp * (1.f - h1[k] * h1[k]);
+            dg1[k] = sv * (1.f - g1[k] * g1[k]);
+        }
+        // ---- per-sample gradient contributions, 32 parameters at a time, summed over the warp's 32 samples
+#pragma unroll
+        for (int g = 0; g < D::GROUPS; ++g) {
+            float c[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int idx = 32 * g + i;  // compile-time constant after unrolling
+                float val = 0.f;
+                if (idx < D::PI0B) val = x[(idx - D::PI0W) / H1] * dp1[(idx - D::PI0W) % H1];
+                else if (idx < D::VF0W) val = dp1[idx - D::PI0B];
+                else if (idx < D::VF0B) val = x[(idx - D::VF0W) / H1] * dg1[(idx - D::VF0W) % H1];
+                else if (idx < D::PI1W) val = dg1[idx - D::VF0B];
+                else if (idx < D::PI1B) val = h1[(idx - D::PI1W) / H2] * dp2[(idx - D::PI1W) % H2];
+                else if (idx < D::VF1W) val = dp2[idx - D::PI1B];
+                else if (idx < D::VF1B) val = g1[(idx - D::VF1W) / H2] * dg2[(idx - D::VF1W) % H2];
+                else if (idx < D::VFW) val = dg2[idx - D::VF1B];
+                else if (idx < D::VFB) val = g2[idx - D::VFW] * dv;
+                else if (idx < D::PIW) val = dv;
+                else if (idx < D::PIB) val = h2[(idx - D::PIW) / A] * dmu[(idx - D::PIW) % A];
+                else if (idx < D::LS) val = dmu[idx - D::PIB];
+                else if (idx < D::P) val = dls[idx - D::LS];
+                c[i] = val;
+            }
+            accg[g] += transpose_reduce32(c, s_tile[warp], lane);
+        }
+    }
+
+    // ---- CTA combine (fixed order over the warps) -> slab
+    float* my = a.partial + (size_t)blockIdx.x * a.PS;
+#pragma unroll
+    for (int g = 0; g < D::GROUPS; ++g) s_part[warp][32 * g + lane] = accg[g];
+    float v4[4] = {l_pg, l_vf, l_kl, l_cf};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v4[q] = warp_sum(v4[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_part[warp][D::GROUPS * 32 + q] = v4[q];
+    }
+    __syncthreads();
+    for (int i = tid; i < D::P; i += NTH) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NTH / 32; ++w) s += s_part[w][i];
+        // d(-ent_coef*entropy)/dlogstd_j = -ent_coef, once (a.ent_coef is pre-divided by the number of ranks)
+        if (blockIdx.x == 0 && i >= D::LS) s -= a.ent_coef;
+        my[i] = s;
+    }
+    if (tid == 0) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < NTH / 32; ++w)
+            for (int q = 0; q < 4; ++q) t[q] += s_part[w][D::GROUPS * 32 + q];
+        float* Lp = my + D::P;
+        Lp[L_PG] = t[0]; Lp[L_VF] = t[1]; Lp[L_KL] = t[2]; Lp[L_CLIP] = t[3];
+        float ent = 0.f;
+        if (blockIdx.x == 0)
+            for (int j = 0; j < A; ++j) ent += sW[D::LS + j] + PPO_HALF_LOG_2PIE;  // GRAPH:10021-10180
+        Lp[L_ENT] = ent;
+        Lp[5] = 0.f; Lp[6] = 0.f; Lp[7] = 0.f;
+    }
+}
+
+}  // namespace small
+}  // namespace ppo

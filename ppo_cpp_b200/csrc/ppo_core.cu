@@ -19,6 +19,7 @@
 #include "kernels_mlp2.cuh"
 #include "kernels_rollout.cuh"
 #include "kernels_shuffle.cuh"
+#include "kernels_small.cuh"
 #include "kernels_umma.cuh"
 #include "meta_parser.h"
 
@@ -100,6 +101,7 @@ struct ppo_core {
     int tm = 64;          // tile size of the generic (T family) MLP kernels
     bool fused = false;   // F family usable: weights + one tile fit in shared memory, H1 % 4 == H2 % 4 == 0
     size_t fused_train_smem = 0, fused_policy_smem = 0;
+    bool small = false;   // S family (thread per sample, registers): the reference's own [4,5] net with 18/18 obs/act
     bool umma = false;    // U family (tcgen05) train kernel usable: H1 == H2 == 64, obs/act 18/18
     int max_train_grid = 0;
     int prof_train_grid = 0;
@@ -474,6 +476,7 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(train_umma_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        c->small = c->d.O == 18 && c->d.A == 18 && c->d.H1 == 4 && c->d.H2 == 5 && getenv("PPO_DISABLE_SMALL") == nullptr;
         st = core_alloc(c);
         if (st != PPO_OK) break;
         if (c->umma && getenv("PPO_UMMA_PROF")) {
@@ -1343,7 +1346,11 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = tru
     a.PS = c->PS;
     int grid;
     a.prof = c->umma_prof;
-    if (c->umma) {  // tcgen05 path: one CTA per (tile of 128 samples, tower)
+    if (c->small) {  // thread per sample, gradient sums by transposing warp butterflies
+        const int nblocks = (a.count + small::NTH - 1) / small::NTH;
+        grid = std::max(1, std::min(nblocks, c->max_train_grid));
+        LAUNCH(c, (small::train_small_kernel<18, 18, 4, 5>), grid, small::NTH, 0, a);
+    } else if (c->umma) {  // tcgen05 path: one CTA per (tile of 128 samples, tower)
         const int ntiles = (a.count + umma::TM - 1) / umma::TM;
         grid = std::max(1, std::min(ntiles, c->sm_count / 2));
         LAUNCH(c, (umma::train_umma_kernel<18, 18, false>), dim3(grid, 2), umma::NTH, umma::SMEM_BYTES, a, umma::EpochArgs{});
@@ -1732,6 +1739,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     if (!c || !which) return nullptr;
     const std::string w(which);
     if (w == "train") {
+        if (c->small) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums)";
         if (c->umma && c->persistent_epoch && fast_path(c))
             return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";
         if (c->umma) return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators)";

@@ -292,6 +292,37 @@ def test_kernel_families_agree(core_mod, monkeypatch, B):
         assert rel_err(res[0][3][sl], res[2][3][sl]) < 1e-5, f"gradient tensor {t}"
 
 
+@pytest.mark.parametrize("B", [1, 31, 64, 1000, 50000])
+def test_small_family_equals_tile_family(core_mod, monkeypatch, init_weights, B):
+    """The reference's [4,5] net trains on the thread-per-sample S family by default; the generic tile (T) family must
+    give the same loss and gradient (both are also checked against the oracle).  B = 1 / 31 / 1000 leave ragged warps,
+    B = 50000 makes every warp loop over several 32-sample tiles."""
+    rng = np.random.default_rng(17 + B)
+    _, flat = init_weights
+    p = flat + (0.1 * rng.standard_normal(flat.size)).astype(np.float32)
+    obs = rng.standard_normal((B, 18)).astype(np.float32)
+    eps = rng.standard_normal((B, 18)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    res = []
+    for env in (None, "PPO_DISABLE_SMALL"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, n_envs=4, n_steps=8, nminibatches=4)
+        assert ("train_small_kernel" in c.kernel_family("train")) == (env is None)
+        act, val, nlp = c.policy_step(obs, eps)
+        g, l = c.loss_grad(obs, act, adv, val + 0.1, nlp + 0.01, val - 0.05, 0.2)
+        res.append((g, l))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    assert rel_err(res[0][1], res[1][1]) < 5e-6
+    o = ol.Oracle(h1=4, h2=5)
+    for t in range(13):
+        sl = slice(o.offset(t), o.offset(t + 1))
+        # two fp32 evaluation orders of a sum with cancellation (the 1e-5 bar is against the fp64 oracle, tests above)
+        assert rel_err(res[0][0][sl], res[1][0][sl]) < 3e-5, f"gradient tensor {t}"
+
+
 # ------------------------------------------------------------------ minibatch step / whole update (a9-a11)
 def _oracle_learner(kat, flat, n_envs, n_steps, nmb, epochs, env_kind, seed=77, shuffle_seed=42, h1=4, h2=5, lr=3.9e-4, cr=0.2):
     c = kat["consts"]
