@@ -475,9 +475,19 @@ struct AdamArgs {
 
 __global__ void adam_kernel(const AdamArgs a) {
     __shared__ float s_scale;
+    __shared__ double s_ss[256];
+    {  // sum of the per-block partials in a fixed order: strided per thread, then a tree (every block does the same)
+        double t = 0.0;
+        for (int b = threadIdx.x; b < a.nblk; b += blockDim.x) t += a.sq_partial[b];
+        s_ss[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o && threadIdx.x + o < blockDim.x) s_ss[threadIdx.x] += s_ss[threadIdx.x + o];
+            __syncthreads();
+        }
+    }
     if (threadIdx.x == 0) {
-        double ss = 0.0;
-        for (int b = 0; b < a.nblk; ++b) ss += a.sq_partial[b];
+        const double ss = s_ss[0];
         const float gnorm = (float)sqrt(ss);  // sqrt(2 * sum L2Loss(g_i))
         const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
         float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));

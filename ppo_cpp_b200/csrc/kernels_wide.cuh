@@ -1,0 +1,629 @@
+// "W family": layer-wise tcgen05 train path for wide hidden layers (H1 == H2 == H, H a multiple of 128; [256,256] is
+// BASELINE.json's C4 net).  Same math as train_tile_kernel (loss / autodiff sub-graph of PPO2::_train_step,
+// ppo2/ppo2.hpp:430-470, GRAPH:6889-23699; tie-breaking rules of SURVEY §3.5b).
+//
+// Why layer-wise: one 128-sample tile of a 256-wide activation is 192 KB as a split-bf16 MMA operand, so the fused
+// one-CTA-per-tile scheme of the U family ([64,64], kernels_umma.cuh) cannot keep two activations plus the weights in
+// shared memory, and a 256 x 256 weight gradient is all of TMEM.  Here every layer of forward and backward is one
+// GEMM over the whole minibatch; activations travel between the GEMMs as *operand images* in global memory (L2 /
+// HBM): the bytes are already laid out as the SWIZZLE_128B shared-memory blocks the tensor core reads, three bf16
+// pieces per fp32 value (x = p0 + p1 + p2, six products per fp32 product as in the U family), so a GEMM stage is
+// filled by plain bulk copies (cp.async.bulk, the non-tensor TMA path) with no address arithmetic per element.
+//   image of a [rows x 64k] matrix: [tile of 128 rows][piece 0..2][column block of 64][16 KB block]
+//   block: row r, 16-byte chunk j (8 bf16) at (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)
+// The same block serves as K-major operand (forward: act x W, backward: dY x W^T) and as MN-major operand
+// (weight gradients: act^T x dY reduced over the samples).
+//
+// Kernels (one minibatch = 17 launches, all captured in the update's CUDA graph):
+//   wide_prep_weights_kernel   fp32 parameters -> weight images (W0' with the bias as an extra input row, W1, heads)
+//   wide_gather_kernel         minibatch rows of the rollout buffer -> X' image (obs | 1)
+//   wgemm_kernel               persistent, warp-specialised (bulk-copy producer / MMA issuer / 4 epilogue warps),
+//                              2-stage shared-memory ring, double-buffered TMEM accumulators (main + cross product)
+//       mode FWD   C = A(K-major image) x W(MN-major view)      Z1, Z2, head
+//       mode BWD   C = A(K-major image) x W^T(K-major view)     dH2, dH1
+//       mode DW    slab[kgroup] = A^T(MN-major) x B(MN-major) over a range of samples (split-K): dW1, dWhead, dW0'
+//   wide_act_kernel            H = tanh(Z + b) -> image
+//   wide_loss_kernel           policy / value losses per sample, dL/dmu, dL/dlogstd terms, dL/dv -> dY image
+//   wide_dact_kernel           dP = dH * (1 - H^2) -> image, column sums (bias gradients) per tile
+//   wide_fold_kernel           per-tile column / loss sums -> slab 0 (zeros in the other slabs)
+// The slabs then go through the same reduce (+ cross-GPU exchange) + global-norm clip + Adam kernel as every family.
+#pragma once
+#include "kernels_umma.cuh"
+
+namespace ppo {
+namespace wide {
+
+using umma::chunk_off;
+using umma::smem_u32;
+
+constexpr int TM = 128;            // samples per tile
+constexpr int GEMM_NTH = 192;      // warp 0: producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr uint32_t BLK16 = 16384;  // [128 x 64] bf16 block
+constexpr uint32_t BLK8 = 8192;    // [64 x 64]
+constexpr uint32_t STAGE_A = 3 * BLK16, STAGE_B = 3 * BLK16, STAGE = STAGE_A + STAGE_B;
+constexpr int NSTAGE = 2;
+constexpr uint32_t GEMM_SMEM = NSTAGE * STAGE + 128 + 1024;  // + barriers + alignment slack
+constexpr int COLPART = 64;        // floats per tile written by the loss kernel
+constexpr int CP_DBPI = 0, CP_DLS = 18, CP_DBV = 36, CP_PG = 37, CP_VF = 38, CP_KL = 39, CP_CLIP = 40;
+
+// byte geometry of the images for hidden width H and NT tiles
+struct Geom {
+    int H, nb, NT, Bpad;
+    size_t act_piece, act_tile, act_tower;  // activation images [tower][tile][piece][nb][16 KB]
+    size_t x_tile;                          // X' image [tile][piece][16 KB]
+    size_t dy_tile, dy_tower;               // dY image [tower][tile][piece][16 KB]
+    size_t w0_piece, w0_tower;              // [tower][piece][nb][4 KB]  (32 input rows x 64 outputs)
+    size_t w1_piece, w1_tower;              // [tower][piece][co][ri][8 KB]
+    size_t wh_piece, wh_tower;              // [tower][piece][ri][8 KB]  (64 inputs x 64 head columns)
+    size_t z_tower, mu_tower;               // fp32 results, in floats
+    int cap;
+    // ntiles tiles in use; the tower strides come from the allocation's capacity, so that a region never changes owner
+    __host__ void init(int h, int ntiles, int cap_tiles) {
+        H = h; nb = h / 64; NT = ntiles; Bpad = ntiles * TM;
+        act_piece = (size_t)nb * BLK16; act_tile = 3 * act_piece; act_tower = (size_t)cap_tiles * act_tile;
+        x_tile = 3 * (size_t)BLK16;
+        dy_tile = 3 * (size_t)BLK16; dy_tower = (size_t)cap_tiles * dy_tile;
+        w0_piece = (size_t)nb * 4096; w0_tower = 3 * w0_piece;
+        w1_piece = (size_t)nb * nb * BLK8; w1_tower = 3 * w1_piece;
+        wh_piece = (size_t)nb * BLK8; wh_tower = 3 * wh_piece;
+        z_tower = (size_t)cap_tiles * TM * h;
+        mu_tower = (size_t)cap_tiles * TM * 64;
+        cap = cap_tiles;
+    }
+};
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_DW = 2 };
+enum { DW_W1 = 0, DW_HEAD = 1, DW_W0 = 2 };
+
+struct DwProb {
+    const uint8_t* A; size_t a_tower, a_tile, a_piece;  // M side: image whose features become the rows of the result
+    const uint8_t* B; size_t b_tower, b_tile, b_piece;  // N side
+    int m_blks, n_blks, n_tile, kind, task0, ntasks;
+};
+
+struct GemmArgs {
+    int mode, ntasks;
+    // FWD / BWD
+    const uint8_t* A; size_t a_tower, a_tile, a_piece;
+    int kblocks, ksteps;
+    const uint8_t* B; size_t b_tower, b_piece, b_kb, b_g;
+    uint32_t b_bytes;
+    int n_tile, n_blks, m_tiles;
+    float* C; size_t c_tower; int ldc;
+    // DW
+    DwProb dw[3];
+    int n_dw, KG, HT;     // split-K groups, half tiles (64 samples) in the minibatch
+    float* partial; int PS;
+    int H, O, A_dim;
+    int off_w1[2], off_w0[2], off_b0[2], off_piw, off_vfw;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// mbarrier wait with a time bound: a pipeline bug must end in an error, not in a hung GPU
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!done && (spin & 0xfffu) == 0xfffu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();  // ~2 s
+        }
+    }
+}
+
+struct Task {
+    int tower, m, n, kg, prob;
+};
+
+__device__ __forceinline__ Task decode_task(const GemmArgs& g, int t) {
+    Task k{};
+    if (g.mode != MODE_DW) {
+        k.n = t % g.n_blks; t /= g.n_blks;
+        k.m = t % g.m_tiles; t /= g.m_tiles;
+        k.tower = t;
+    } else {
+        int p = 0;
+        while (p + 1 < g.n_dw && t >= g.dw[p + 1].task0) ++p;
+        const DwProb& P = g.dw[p];
+        t -= P.task0;
+        k.prob = p;
+        k.kg = t % g.KG; t /= g.KG;
+        k.n = t % P.n_blks; t /= P.n_blks;
+        k.m = t % P.m_blks; t /= P.m_blks;
+        k.tower = t;
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + NSTAGE * STAGE;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + NSTAGE * STAGE + 96);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#define BAR_FULL(s) (bar0 + 8u * (s))
+#define BAR_EMPTY(s) (bar0 + 16u + 8u * (s))
+#define BAR_ACCFULL(b) (bar0 + 32u + 8u * (b))
+#define BAR_ACCEMPTY(b) (bar0 + 48u + 8u * (b))
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_FULL(s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_EMPTY(s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_ACCFULL(s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(BAR_ACCEMPTY(s)));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const bool dwm = g.mode == MODE_DW;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer: bulk copies global image -> stage
+        if (umma::elect_one()) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < g.ntasks; t += gridDim.x) {
+                const Task k = decode_task(g, t);
+                int kb0 = 0, kb1 = g.kblocks;
+                if (dwm) {
+                    kb0 = (int)(((long long)k.kg * g.HT) / g.KG);
+                    kb1 = (int)(((long long)(k.kg + 1) * g.HT) / g.KG);
+                }
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                    mbar_wait_b(BAR_EMPTY(s), ph ^ 1u);
+                    const uint32_t sA = sbase + s * STAGE, sB = sA + STAGE_A;
+                    if (!dwm) {
+                        const int NG = g.mode == MODE_FWD ? g.n_tile / 64 : 1;
+                        mbar_expect_tx(BAR_FULL(s), 3u * (BLK16 + (uint32_t)NG * g.b_bytes));
+                        const uint8_t* a = g.A + k.tower * g.a_tower + (size_t)k.m * g.a_tile + (size_t)kb * BLK16;
+                        const uint8_t* b = g.B + k.tower * g.b_tower + (size_t)kb * g.b_kb;
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            bulk_g2s(sA + p * BLK16, a + p * g.a_piece, BLK16, BAR_FULL(s));
+                            for (int q = 0; q < NG; ++q)
+                                bulk_g2s(sB + (uint32_t)(p * NG + q) * g.b_bytes, b + p * g.b_piece + (size_t)(k.n * NG + q) * g.b_g, g.b_bytes, BAR_FULL(s));
+                        }
+                    } else {
+                        const DwProb& P = g.dw[k.prob];
+                        const int NG = P.n_tile / 64, tile = kb >> 1, sh = kb & 1;
+                        mbar_expect_tx(BAR_FULL(s), 3u * (2u + (uint32_t)NG) * BLK8);
+                        const uint8_t* a = P.A + k.tower * P.a_tower + (size_t)tile * P.a_tile + (size_t)sh * BLK8;
+                        const uint8_t* b = P.B + k.tower * P.b_tower + (size_t)tile * P.b_tile + (size_t)sh * BLK8;
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            for (int q = 0; q < 2; ++q)
+                                bulk_g2s(sA + (uint32_t)(p * 2 + q) * BLK8, a + p * P.a_piece + (size_t)(k.m * 2 + q) * BLK16, BLK8, BAR_FULL(s));
+                            for (int q = 0; q < NG; ++q)
+                                bulk_g2s(sB + (uint32_t)(p * NG + q) * BLK8, b + p * P.b_piece + (size_t)(k.n * NG + q) * BLK16, BLK8, BAR_FULL(s));
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (umma::elect_one()) {
+            uint32_t it = 0, tc = 0;
+            for (int t = blockIdx.x; t < g.ntasks; t += gridDim.x, ++tc) {
+                const Task k = decode_task(g, t);
+                int kb0 = 0, kb1 = g.kblocks, n_tile = g.n_tile, ksteps = g.ksteps;
+                if (dwm) {
+                    kb0 = (int)(((long long)k.kg * g.HT) / g.KG);
+                    kb1 = (int)(((long long)(k.kg + 1) * g.HT) / g.KG);
+                    n_tile = g.dw[k.prob].n_tile;
+                    ksteps = 4;
+                }
+                const int NG = n_tile / 64;
+                // operand geometry in the stage (16-byte units)
+                uint32_t a_lbo, a_piece, a_ks, b_lbo, b_piece, b_ks;
+                int a_mn, b_mn;
+                if (g.mode == MODE_FWD) {
+                    a_mn = 0; a_lbo = 16; a_piece = BLK16 >> 4; a_ks = 2;
+                    b_mn = 1; b_lbo = g.b_bytes; b_piece = (uint32_t)(NG * g.b_bytes) >> 4; b_ks = 2048 >> 4;
+                } else if (g.mode == MODE_BWD) {
+                    a_mn = 0; a_lbo = 16; a_piece = BLK16 >> 4; a_ks = 2;
+                    b_mn = 0; b_lbo = 16; b_piece = g.b_bytes >> 4; b_ks = 2;
+                } else {
+                    a_mn = 1; a_lbo = BLK8; a_piece = (2 * BLK8) >> 4; a_ks = 2048 >> 4;
+                    b_mn = 1; b_lbo = BLK8; b_piece = (uint32_t)(NG * BLK8) >> 4; b_ks = 2048 >> 4;
+                }
+                const uint32_t idesc = umma::make_idesc(128, n_tile, a_mn, b_mn);
+                const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+                mbar_wait_b(BAR_ACCEMPTY(ab), aph ^ 1u);
+                umma::tc_fence_after();
+                const uint32_t dm = tmem + ab * 256u, dc = dm + 128u;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                    mbar_wait_b(BAR_FULL(s), ph);
+                    umma::tc_fence_after();
+                    const uint32_t sA = sbase + s * STAGE, sB = sA + STAGE_A;
+                    const uint64_t ad = umma::make_desc(sA, a_lbo, 1024), bd = umma::make_desc(sB, b_lbo, 1024);
+#pragma unroll 4
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t a = ad + (uint64_t)(ks * a_ks), b = bd + (uint64_t)(ks * b_ks);
+                        const uint32_t acc = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        umma::mma_bf16(dm, a, b, idesc, acc);
+                        umma::mma_bf16(dc, a, b + b_piece, idesc, acc);
+                        umma::mma_bf16(dc, a + a_piece, b, idesc, 1u);
+                        umma::mma_bf16(dc, a + a_piece, b + b_piece, idesc, 1u);
+                        umma::mma_bf16(dc, a, b + 2 * b_piece, idesc, 1u);
+                        umma::mma_bf16(dc, a + 2 * a_piece, b, idesc, 1u);
+                    }
+                    umma::umma_commit(BAR_EMPTY(s));  // the stage is free once these MMAs have read it
+                }
+                umma::umma_commit(BAR_ACCFULL(ab));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: TMEM -> fp32 result
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tc = 0;
+        for (int t = blockIdx.x; t < g.ntasks; t += gridDim.x, ++tc) {
+            const Task k = decode_task(g, t);
+            const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+            mbar_wait_b(BAR_ACCFULL(ab), aph);
+            umma::tc_fence_after();
+            const uint32_t dm = tlane + ab * 256u, dc = dm + 128u;
+            float v[32];
+            if (!dwm) {
+                float* dst = g.C + k.tower * g.c_tower + ((size_t)k.m * TM + row) * g.ldc + (size_t)k.n * g.n_tile;
+                for (int c0 = 0; c0 < g.n_tile; c0 += 32) {
+                    umma::tmem_ld32_sum(dm + c0, dc + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            } else {
+                const DwProb& P = g.dw[k.prob];
+                float* slab = g.partial + (size_t)k.kg * g.PS;
+                const int r = k.m * TM + row;  // feature index of the M side
+                for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+                    if (P.kind != DW_W1 && c0 > 0) break;  // heads and X' use the first 32 columns only
+                    umma::tmem_ld32_sum(dm + c0, dc + c0, v);
+                    if (P.kind == DW_W1) {  // dW1[k_in = r][n_out]
+                        float* dst = slab + g.off_w1[k.tower] + (size_t)r * g.H + (size_t)k.n * P.n_tile + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) dst[i] = v[i];  // slabs are PS floats apart (odd): no vector stores
+                    } else if (P.kind == DW_HEAD) {  // pi: dWpi[r][j]; V: dwv[r]
+                        if (k.tower == 0) {
+                            float* dst = slab + g.off_piw + (size_t)r * g.A_dim;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < g.A_dim) dst[j] = v[j];
+                        } else {
+                            slab[g.off_vfw + r] = v[0];
+                        }
+                    } else {  // dW0'^T[n_out = r][k_in = j]: j < O weights, j == O bias
+                        float* dw = slab + g.off_w0[k.tower] + r;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < g.O) dw[(size_t)j * g.H] = v[j];
+                            else if (j == g.O) slab[g.off_b0[k.tower] + r] = v[j];
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_ACCEMPTY(ab));
+        }
+    }
+#undef BAR_FULL
+#undef BAR_EMPTY
+#undef BAR_ACCFULL
+#undef BAR_ACCEMPTY
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise kernels
+struct WideBufs {
+    Geom G;
+    uint8_t *X, *H1, *H2, *dP2, *dP1, *dY;  // images
+    uint8_t *W0, *W1, *WH;                  // weight images
+    float *Z, *MU;                          // fp32 GEMM results: [2][Bpad x H], [2][Bpad x 64]
+    float *colloss;                         // [NT][COLPART]
+    float *colb1;                           // [2][NT][H]
+};
+
+// fp32 parameters -> weight images.  One thread per 16-byte chunk.
+__global__ void wide_prep_weights_kernel(const float* __restrict__ P, const NetDims d, const WideBufs w) {
+    const Geom& G = w.G;
+    const int nb = G.nb, H = G.H;
+    const int n_w0 = 2 * nb * 32 * 8, n_w1 = 2 * nb * nb * 64 * 8, n_wh = 2 * nb * 64 * 8;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_w0 + n_w1 + n_wh; e += gridDim.x * blockDim.x) {
+        float x[8];
+        uint8_t* dst;
+        size_t piece;
+        if (e < n_w0) {
+            int t = e;
+            const int j = t & 7; t >>= 3;
+            const int r = t & 31; t >>= 5;
+            const int nbk = t % nb, tower = t / nb;
+            const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
+            const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+            const int n = nbk * 64 + 8 * j;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = r < d.O ? __ldg(W0 + (size_t)r * H + n + i) : (r == d.O ? __ldg(B0 + n + i) : 0.f);
+            dst = w.W0 + tower * G.w0_tower + (size_t)nbk * 4096 + chunk_off(r, j);
+            piece = G.w0_piece;
+        } else if (e < n_w0 + n_w1) {
+            int t = e - n_w0;
+            const int j = t & 7; t >>= 3;
+            const int r = t & 63; t >>= 6;
+            const int ri = t % nb; t /= nb;
+            const int co = t % nb, tower = t / nb;
+            const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W] + (size_t)(ri * 64 + r) * H + co * 64 + 8 * j;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldg(W1 + i);
+            dst = w.W1 + tower * G.w1_tower + (size_t)(co * nb + ri) * BLK8 + chunk_off(r, j);
+            piece = G.w1_piece;
+        } else {
+            int t = e - n_w0 - n_w1;
+            const int j = t & 7; t >>= 3;
+            const int r = t & 63; t >>= 6;
+            const int ri = t % nb, tower = t / nb;
+            const int k = ri * 64 + r;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = 8 * j + i;
+                x[i] = tower == 0 ? (c < d.A ? __ldg(P + d.off[T_PI_W] + (size_t)k * d.A + c) : 0.f) : (c == 0 ? __ldg(P + d.off[T_VF_W] + k) : 0.f);
+            }
+            dst = w.WH + tower * G.wh_tower + (size_t)ri * BLK8 + chunk_off(r, j);
+            piece = G.wh_piece;
+        }
+        umma::store_chunk(dst, (uint32_t)piece, 0, x);
+    }
+}
+
+// minibatch rows -> X' image: [obs | 1 | 0 ...]; rows past the minibatch are zero (they then contribute nothing:
+// the loss kernel masks them and every gradient flows through dY).  Only the chunks that can be non-zero are written.
+__global__ void wide_gather_kernel(const TrainArgs a, const WideBufs w) {
+    const Geom& G = w.G;
+    const int O = a.d.O, nj = O / 8 + 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < G.Bpad * nj; e += gridDim.x * blockDim.x) {
+        const int row = e / nj, j = e % nj;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        if (row < a.count) {
+            const long src = a.gather ? (long)__ldg(a.gather + a.slot0 + row) : (long)(a.slot0 + row);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = 8 * j + i;
+                x[i] = c < O ? __ldg(a.obs + src * O + c) : (c == O ? 1.f : 0.f);
+            }
+        }
+        umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
+    }
+}
+
+// H = tanh(Z + b) -> image.  Thread per (tower, row, 8 columns).
+__global__ void wide_act_kernel(const float* __restrict__ Z, const float* __restrict__ P, int off_b_pi, int off_b_vf, uint8_t* img, const Geom G) {
+    const int H = G.H, h8 = H / 8;
+    const long total = 2L * G.Bpad * h8;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int j8 = (int)(e % h8);
+        const long rr = e / h8;
+        const int row = (int)(rr % G.Bpad), tower = (int)(rr / G.Bpad);
+        const float4* src = reinterpret_cast<const float4*>(Z + tower * G.z_tower + (size_t)row * H + 8 * j8);
+        const float4 z0 = __ldg(src), z1 = __ldg(src + 1);
+        float x[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        const int ob = tower ? off_b_vf : off_b_pi;
+        if (ob >= 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] += __ldg(P + ob + 8 * j8 + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = tanhf(x[i]);
+        uint8_t* blk = img + tower * G.act_tower + (size_t)(row >> 7) * G.act_tile + (size_t)(j8 >> 3) * BLK16;
+        umma::store_chunk(blk, (uint32_t)G.act_piece, chunk_off(row & 127, j8 & 7), x);
+    }
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 q, float* x) {
+    x[0] = __uint_as_float(q.x << 16); x[1] = __uint_as_float(q.x & 0xffff0000u);
+    x[2] = __uint_as_float(q.y << 16); x[3] = __uint_as_float(q.y & 0xffff0000u);
+    x[4] = __uint_as_float(q.z << 16); x[5] = __uint_as_float(q.z & 0xffff0000u);
+    x[6] = __uint_as_float(q.w << 16); x[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
+// dP = dH * (1 - H^2) -> image (TanhGrad, GRAPH:20925-23699); H is read back from its image (p0 + p1 + p2 is exact).
+// grid = (tiles, towers), 256 threads: thread = (8 columns j8, row lane); H / 8 divides 256 (H = 128, 256, 512, 1024).
+// Optional column sums over the tile's rows (bias gradients), summed in a fixed order.
+__global__ void __launch_bounds__(256) wide_dact_kernel(const float* __restrict__ dH, const uint8_t* __restrict__ Himg, uint8_t* dPimg,
+                                                        float* __restrict__ colsum, const Geom G) {
+    __shared__ float s_red[2048];  // [row lane][H]
+    const int H = G.H, h8 = H / 8, tile = blockIdx.x, tower = blockIdx.y;
+    const int lanes = 256 / h8;
+    const int j8 = (int)(threadIdx.x % h8), rl = threadIdx.x / h8;
+    float cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+    const size_t boff = tower * G.act_tower + (size_t)tile * G.act_tile + (size_t)(j8 >> 3) * BLK16;
+    for (int r = rl; r < TM; r += lanes) {
+        const float4* src = reinterpret_cast<const float4*>(dH + tower * G.z_tower + ((size_t)tile * TM + r) * H + 8 * j8);
+        const float4 d0 = __ldg(src), d1 = __ldg(src + 1);
+        const uint32_t co = chunk_off(r, j8 & 7);
+        float h0[8], h1[8], h2[8], x[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + co)), h0);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + G.act_piece + co)), h1);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + 2 * G.act_piece + co)), h2);
+        const float dh[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float h = (h0[i] + h1[i]) + h2[i];
+            x[i] = dh[i] * (1.f - h * h);
+            cs[i] += x[i];
+        }
+        umma::store_chunk(dPimg + boff, (uint32_t)G.act_piece, co, x);
+    }
+    if (colsum) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_red[rl * H + 8 * j8 + i] = cs[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += 256) {
+            float t = 0.f;
+            for (int l = 0; l < lanes; ++l) t += s_red[l * H + c];
+            colsum[((size_t)tower * G.cap + tile) * H + c] = t;
+        }
+    }
+}
+
+// Losses and head gradients per sample (GRAPH:9428-11446, 10213-10400), one thread per sample, one CTA per tile.
+// MU buffer: pi rows hold mu - b (columns 0..A-1), V rows hold v - b (column 0).
+template <int A>
+__global__ void __launch_bounds__(TM) wide_loss_kernel(const TrainArgs a, const WideBufs w) {
+    __shared__ float s_red[4][COLPART];
+    const Geom& G = w.G;
+    const NetDims& d = a.d;
+    const int tile = blockIdx.x, r = threadIdx.x, row = tile * TM + r, lane = r & 31, wp = r >> 5;
+    const bool valid = row < a.count;
+    const float* P = a.params;
+    float dmu[32], dls[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dmu[j] = dls[j] = 0.f;
+    float l_pg = 0.f, l_vf = 0.f, l_kl = 0.f, l_cf = 0.f, dv = 0.f;
+    if (valid) {
+        const long src = a.gather ? (long)__ldg(a.gather + a.slot0 + row) : (long)(a.slot0 + row);
+        const float ret = __ldg(a.ret + src), oldv = __ldg(a.val + src), oldn = __ldg(a.nlp + src);
+        float adv;
+        if (a.adv_direct) adv = __ldg(a.adv_direct + a.slot0 + row);
+        else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
+            const float2 st = __ldg(a.mbstats);
+            adv = __fdiv_rn(__fsub_rn(__fsub_rn(ret, oldv), st.x), st.y);
+        }
+        const float* mu = w.MU + (size_t)row * 64;
+        const float* act = a.act + src * A;
+        const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+        float z[A], isd[A];
+        float ss = 0.f, sl = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const float ls = __ldg(P + d.off[T_LOGSTD] + j);
+            isd[j] = 1.f / expf(ls);
+            z[j] = (__ldg(act + j) - (mu[j] + __ldg(P + d.off[T_PI_B] + j))) * isd[j];
+            ss += z[j] * z[j];
+            sl += ls;
+        }
+        const float nlp = (0.5f * ss + PPO_HALF_LOG_2PI * (float)A) + sl;
+        const float ratio = expf(oldn - nlp);
+        const float pg1 = -adv * ratio;
+        const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);  // clip_by_value = max(min(x,hi),lo)
+        const bool take1 = pg1 >= pg2;                          // ties -> unclipped branch
+        l_pg = take1 ? pg1 : pg2;
+        const float dn = nlp - oldn;
+        l_kl = dn * dn;
+        l_cf = (fabsf(ratio - 1.f) > a.cliprange) ? 1.f : 0.f;
+        const float g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            dmu[j] = g_nlp * (-z[j] * isd[j]);
+            dls[j] = g_nlp * (1.f - z[j] * z[j]);
+        }
+        // value head
+        const float v = w.MU[G.mu_tower + (size_t)row * 64] + __ldg(P + d.off[T_VF_B]);
+        const float dvo = v - oldv;
+        const float vc = oldv + fmaxf(fminf(dvo, a.cliprange), -a.cliprange);
+        const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+        const bool tk = l1 >= l2;  // ties -> unclipped branch
+        l_vf = tk ? l1 : l2;
+        const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
+        dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (v - ret) : (inr ? 2.f * (vc - ret) : 0.f));
+    }
+    // dY images: pi = [dMU (32 columns) | dLS (32 columns)], V = [dv | 0 ...]
+    uint8_t* ypi = w.dY + (size_t)tile * G.dy_tile;
+    uint8_t* yv = w.dY + G.dy_tower + (size_t)tile * G.dy_tile;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        umma::store_chunk(ypi, BLK16, chunk_off(r, j), dmu + 8 * j);
+        umma::store_chunk(ypi, BLK16, chunk_off(r, 4 + j), dls + 8 * j);
+    }
+    {
+        float x[8] = {dv, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        umma::store_chunk(yv, BLK16, chunk_off(r, 0), x);
+    }
+    // per-tile sums: bias / logstd gradients and the loss terms
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        const float s0 = warp_sum(dmu[j]), s1 = warp_sum(dls[j]);
+        if (lane == 0) {
+            s_red[wp][CP_DBPI + j] = s0;
+            s_red[wp][CP_DLS + j] = s1;
+        }
+    }
+    {
+        const float t0 = warp_sum(dv), t1 = warp_sum(l_pg), t2 = warp_sum(l_vf), t3 = warp_sum(l_kl), t4 = warp_sum(l_cf);
+        if (lane == 0) {
+            s_red[wp][CP_DBV] = t0; s_red[wp][CP_PG] = t1; s_red[wp][CP_VF] = t2; s_red[wp][CP_KL] = t3; s_red[wp][CP_CLIP] = t4;
+        }
+    }
+    __syncthreads();
+    if (r <= CP_CLIP) w.colloss[(size_t)tile * COLPART + r] = ((s_red[0][r] + s_red[1][r]) + s_red[2][r]) + s_red[3][r];
+}
+
+// per-tile sums -> slab 0; the same columns of the other slabs are zero (the GEMMs own every weight column of every slab).
+// One warp per output column: lanes stride over the tiles, fixed-order butterfly in double.
+__global__ void wide_fold_kernel(const TrainArgs a, const WideBufs w, int nslabs) {
+    const Geom& G = w.G;
+    const NetDims& d = a.d;
+    const int H = G.H, A = d.A, lane = threadIdx.x & 31;
+    const int n = 2 * H + 2 * A + 1 + L_PAD;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += (gridDim.x * blockDim.x) >> 5) {
+        double t = 0.0;
+        int col;
+        const float* src = nullptr;
+        size_t stride = 0;
+        if (e < 2 * H) {
+            const int tower = e / H, c = e % H;
+            src = w.colb1 + (size_t)tower * G.cap * H + c; stride = H;
+            col = d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + c;
+        } else if (e < 2 * H + 2 * A + 1) {
+            const int c = e - 2 * H;  // colloss columns 0 .. 2A: dbpi, dlogstd, dbv
+            src = w.colloss + c; stride = COLPART;
+            col = c < A ? d.off[T_PI_B] + c : (c < 2 * A ? d.off[T_LOGSTD] + c - A : d.off[T_VF_B]);
+        } else {
+            const int l = e - (2 * H + 2 * A + 1);
+            col = d.P + l;
+            const int sc = l == L_PG ? CP_PG : l == L_VF ? CP_VF : l == L_KL ? CP_KL : l == L_CLIP ? CP_CLIP : -1;
+            if (sc >= 0) { src = w.colloss + sc; stride = COLPART; }
+        }
+        if (src)
+            for (int i = lane; i < G.NT; i += 32) t += (double)src[(size_t)i * stride];
+        t = warp_sum(t);
+        if (lane == 0) {
+            if (e >= 2 * H + A && e < 2 * H + 2 * A) t -= (double)a.ent_coef;  // d(-ent_coef * entropy)/dlogstd_j (ent_coef is pre-divided by the world size)
+            if (col == d.P + L_ENT)  // every rank adds it; the Adam kernel scales the summed row by 1 / world_size
+                for (int j = 0; j < A; ++j) t += (double)(__ldg(a.params + d.off[T_LOGSTD] + j) + PPO_HALF_LOG_2PIE);
+            a.partial[col] = (float)t;
+            for (int s = 1; s < nslabs; ++s) a.partial[(size_t)s * a.PS + col] = 0.f;
+        }
+    }
+}
+
+}  // namespace wide
+}  // namespace ppo

@@ -21,6 +21,7 @@
 #include "kernels_shuffle.cuh"
 #include "kernels_small.cuh"
 #include "kernels_umma.cuh"
+#include "kernels_wide.cuh"
 #include "meta_parser.h"
 
 using namespace ppo;
@@ -103,6 +104,10 @@ struct ppo_core {
     size_t fused_train_smem = 0, fused_policy_smem = 0;
     bool small = false;   // S family (thread per sample, registers): the reference's own [4,5] net with 18/18 obs/act
     bool umma = false;    // U family (tcgen05) train kernel usable: H1 == H2 == 64, obs/act 18/18
+    bool wide = false;    // W family (tcgen05, layer-wise GEMMs over operand images): H1 == H2 in {128, 256, 512, 1024}
+    wide::WideBufs wb{};
+    void* wide_mem = nullptr;
+    int wide_cap = 0;     // capacity of the W-family buffers in tiles of 128 samples
     int max_train_grid = 0;
     int prof_train_grid = 0;
     long long* umma_prof = nullptr;  // PPO_UMMA_PROF=1: phase timestamps of the U-family train kernel
@@ -295,6 +300,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     for (int r = 0; r < PPO_MAX_WORLD; ++r)
         if (c->mbox_peer[r] && r != c->desc.rank) cudaIpcCloseMemHandle(c->mbox_peer[r]);
     if (c->mbox_mem) cudaFree(c->mbox_mem);
+    if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -318,6 +324,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     delete c;
 }
 
+static int ensure_wide(ppo_core* c, int tiles);
 static int core_alloc(ppo_core* c) {
     const ppo_core_desc& D = c->desc;
     const NetDims& d = c->d;
@@ -477,8 +484,21 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             break;
         }
         c->small = c->d.O == 18 && c->d.A == 18 && c->d.H1 == 4 && c->d.H2 == 5 && getenv("PPO_DISABLE_SMALL") == nullptr;
+        {
+            const int H = c->d.H1;
+            c->wide = c->d.H1 == c->d.H2 && (H == 128 || H == 256 || H == 512 || H == 1024) && c->d.O == 18 && c->d.A == 18 &&
+                      wide::GEMM_SMEM <= max_smem && prop.major == 10 && getenv("PPO_DISABLE_WIDE") == nullptr;
+            if (c->wide && cudaFuncSetAttribute(wide::wgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::GEMM_SMEM) != cudaSuccess) {
+                st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(wgemm_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
         st = core_alloc(c);
         if (st != PPO_OK) break;
+        if (c->wide) {
+            st = ensure_wide(c, (int)((nbg / desc->nminibatches / desc->world_size + wide::TM - 1) / wide::TM));
+            if (st != PPO_OK) break;
+        }
         if (c->umma && getenv("PPO_UMMA_PROF")) {
             if (cudaMalloc(&c->umma_prof, sizeof(long long) * 96) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
             cudaMemset(c->umma_prof, 0, sizeof(long long) * 96);
@@ -1337,6 +1357,119 @@ static int prepare_epoch(ppo_core* c, const int* perm_pinned_or_host) {
     return PPO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ W family (kernels_wide.cuh)
+// One allocation holds every operand image and fp32 result of a minibatch of up to `tiles` tiles.  Zero-filled: the
+// chunks of the X' and dY images that no kernel writes must read as zeros.
+static int ensure_wide(ppo_core* c, int tiles) {
+    if (tiles <= c->wide_cap) return PPO_OK;
+    if (c->wide_mem) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(c->wide_mem));
+        c->wide_mem = nullptr;
+        c->wide_cap = 0;
+    }
+    wide::Geom G;
+    G.init(c->d.H1, tiles, tiles);
+    const size_t R = (size_t)tiles * wide::TM, H = (size_t)G.H;
+    const size_t sizes[] = {(size_t)tiles * G.x_tile, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.dy_tower,
+                            2 * G.w0_tower, 2 * G.w1_tower, 2 * G.wh_tower, 2 * R * H * sizeof(float), 2 * R * 64 * sizeof(float),
+                            (size_t)tiles * wide::COLPART * sizeof(float), 2 * (size_t)tiles * H * sizeof(float)};
+    size_t off[14], total = 0;
+    for (int i = 0; i < 13; ++i) {
+        off[i] = total;
+        total += (sizes[i] + 1023) & ~(size_t)1023;
+    }
+    CU(cudaMalloc(&c->wide_mem, total));
+    CU(cudaMemsetAsync(c->wide_mem, 0, total, c->stream));
+    uint8_t* base = static_cast<uint8_t*>(c->wide_mem);
+    wide::WideBufs& w = c->wb;
+    w.X = base + off[0]; w.H1 = base + off[1]; w.H2 = base + off[2]; w.dP2 = base + off[3]; w.dP1 = base + off[4]; w.dY = base + off[5];
+    w.W0 = base + off[6]; w.W1 = base + off[7]; w.WH = base + off[8];
+    w.Z = reinterpret_cast<float*>(base + off[9]); w.MU = reinterpret_cast<float*>(base + off[10]);
+    w.colloss = reinterpret_cast<float*>(base + off[11]); w.colb1 = reinterpret_cast<float*>(base + off[12]);
+    c->wide_cap = tiles;
+    return PPO_OK;
+}
+
+static void launch_wgemm(ppo_core* c, const wide::GemmArgs& g) {
+    const int grid = std::max(1, std::min(g.ntasks, c->sm_count));
+    LAUNCH(c, wide::wgemm_kernel, grid, wide::GEMM_NTH, wide::GEMM_SMEM, g);
+}
+
+// loss forward + backward of one minibatch shard -> KG gradient slabs (split-K groups of the weight-gradient GEMMs)
+static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
+    using namespace wide;
+    const int NT = (a.count + TM - 1) / TM;
+    TRY(ensure_wide(c, NT));
+    WideBufs w = c->wb;
+    Geom& G = w.G;
+    G.init(c->d.H1, NT, c->wide_cap);
+    const int H = G.H, nb = G.nb;
+    const NetDims& d = c->d;
+    {
+        const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
+        LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w);
+        LAUNCH(c, wide_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a, w);
+    }
+    const int ew_grid = (int)std::min<long>((2L * G.Bpad * (H / 8) + 255) / 256, (long)c->sm_count * 16);
+    GemmArgs g{};
+    // ---- layer 0: Z1 = X' W0'
+    g.mode = MODE_FWD;
+    g.A = w.X; g.a_tower = 0; g.a_tile = G.x_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
+    g.B = w.W0; g.b_tower = G.w0_tower; g.b_piece = G.w0_piece; g.b_kb = 0; g.b_g = 4096; g.b_bytes = 4096;
+    g.n_tile = 128; g.n_blks = H / 128; g.m_tiles = NT; g.ntasks = 2 * NT * g.n_blks;
+    g.C = w.Z; g.c_tower = G.z_tower; g.ldc = H;
+    launch_wgemm(c, g);
+    LAUNCH(c, wide_act_kernel, ew_grid, 256, 0, w.Z, a.params, -1, -1, w.H1, G);
+    // ---- layer 1: Z2 = H1 W1 (+ b1 in the activation kernel)
+    g.A = w.H1; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
+    g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
+    launch_wgemm(c, g);
+    LAUNCH(c, wide_act_kernel, ew_grid, 256, 0, w.Z, a.params, d.off[T_PI_FC1_B], d.off[T_VF_FC1_B], w.H2, G);
+    // ---- heads: [mu | v] = H2 WH
+    g.A = w.H2;
+    g.B = w.WH; g.b_tower = G.wh_tower; g.b_piece = G.wh_piece; g.b_kb = BLK8; g.b_g = 0; g.b_bytes = BLK8;
+    g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT;
+    g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
+    launch_wgemm(c, g);
+    LAUNCH(c, (wide_loss_kernel<18>), NT, TM, 0, a, w);
+    // ---- dH2 = dY WH^T, dP2 = dH2 (1 - H2^2)
+    g.mode = MODE_BWD;
+    g.A = w.dY; g.a_tower = G.dy_tower; g.a_tile = G.dy_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
+    g.B = w.WH; g.b_kb = 0; g.b_g = BLK16; g.b_bytes = BLK16;
+    g.n_tile = 128; g.n_blks = H / 128; g.ntasks = 2 * NT * g.n_blks;
+    g.C = w.Z; g.c_tower = G.z_tower; g.ldc = H;
+    launch_wgemm(c, g);
+    LAUNCH(c, wide_dact_kernel, dim3(NT, 2), 256, 0, w.Z, w.H2, w.dP2, w.colb1, G);
+    // ---- dH1 = dP2 W1^T, dP1 = dH1 (1 - H1^2)
+    g.A = w.dP2; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
+    g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = (size_t)nb * BLK8; g.b_g = BLK16; g.b_bytes = BLK16;
+    launch_wgemm(c, g);
+    LAUNCH(c, wide_dact_kernel, dim3(NT, 2), 256, 0, w.Z, w.H1, w.dP1, (float*)nullptr, G);
+    // ---- weight gradients, split over KG groups of samples: dW1 = H1^T dP2, dWhead = H2^T dY, dW0'^T = dP1^T X'
+    GemmArgs q{};
+    q.mode = MODE_DW;
+    q.HT = 2 * NT;
+    q.KG = std::min(16, q.HT);
+    q.partial = a.partial; q.PS = a.PS; q.H = H; q.O = d.O; q.A_dim = d.A;
+    q.off_w1[0] = d.off[T_PI_FC1_W]; q.off_w1[1] = d.off[T_VF_FC1_W];
+    q.off_w0[0] = d.off[T_PI_FC0_W]; q.off_w0[1] = d.off[T_VF_FC0_W];
+    q.off_b0[0] = d.off[T_PI_FC0_B]; q.off_b0[1] = d.off[T_VF_FC0_B];
+    q.off_piw = d.off[T_PI_W]; q.off_vfw = d.off[T_VF_W];
+    q.n_dw = 3;
+    const int mb = H / 128;
+    q.dw[0] = DwProb{w.H1, G.act_tower, G.act_tile, G.act_piece, w.dP2, G.act_tower, G.act_tile, G.act_piece, mb, H / 128, 128, DW_W1, 0, 2 * mb * (H / 128) * q.KG};
+    q.dw[1] = DwProb{w.H2, G.act_tower, G.act_tile, G.act_piece, w.dY, G.dy_tower, G.dy_tile, BLK16, mb, 1, 64, DW_HEAD, 0, 2 * mb * q.KG};
+    q.dw[2] = DwProb{w.dP1, G.act_tower, G.act_tile, G.act_piece, w.X, 0, G.x_tile, BLK16, mb, 1, 64, DW_W0, 0, 2 * mb * q.KG};
+    q.dw[1].task0 = q.dw[0].ntasks;
+    q.dw[2].task0 = q.dw[1].task0 + q.dw[1].ntasks;
+    q.ntasks = q.dw[2].task0 + q.dw[2].ntasks;
+    launch_wgemm(c, q);
+    LAUNCH(c, wide_fold_kernel, (2 * H + 2 * d.A + 1 + L_PAD + 7) / 8, 256, 0, a, w, q.KG);
+    *slabs_out = q.KG;
+    return PPO_OK;
+}
+
 static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = true, int* grid_out = nullptr) {
     a.d = c->d;
     a.params = c->params;
@@ -1346,7 +1479,9 @@ static int launch_train_kernel(ppo_core* c, TrainArgs& a, bool with_reduce = tru
     a.PS = c->PS;
     int grid;
     a.prof = c->umma_prof;
-    if (c->small) {  // thread per sample, gradient sums by transposing warp butterflies
+    if (c->wide) {  // layer-wise tcgen05 GEMMs; the slabs are the split-K groups of the weight-gradient GEMMs
+        TRY(launch_wide_train(c, a, &grid));
+    } else if (c->small) {  // thread per sample, gradient sums by transposing warp butterflies
         const int nblocks = (a.count + small::NTH - 1) / small::NTH;
         grid = std::max(1, std::min(nblocks, c->max_train_grid));
         LAUNCH(c, (small::train_small_kernel<18, 18, 4, 5>), grid, small::NTH, 0, a);
@@ -1739,6 +1874,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     if (!c || !which) return nullptr;
     const std::string w(which);
     if (w == "train") {
+        if (c->wide) return "wgemm_kernel (tcgen05.mma kind::f16, bf16x3 split operand images, layer-wise GEMMs with bulk-copy pipeline)";
         if (c->small) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums)";
         if (c->umma && c->persistent_epoch && fast_path(c))
             return "train_umma_kernel (tcgen05.mma kind::f16, bf16x3 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";

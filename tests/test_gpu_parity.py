@@ -323,6 +323,78 @@ def test_small_family_equals_tile_family(core_mod, monkeypatch, init_weights, B)
         assert rel_err(res[0][0][sl], res[1][0][sl]) < 3e-5, f"gradient tensor {t}"
 
 
+@pytest.mark.parametrize("H,B", [(256, 128), (256, 300), (128, 1000), (256, 5000), (128, 77)])
+def test_wide_family_vs_oracle_and_tile_family(core_mod, monkeypatch, H, B):
+    """[256,256] (BASELINE.json C4) and the other wide nets train on the W family: every layer of forward and backward is
+    a tcgen05 GEMM over the whole minibatch, activations travel as split-bf16 operand images (kernels_wide.cuh).
+    Checked against the fp64 oracle (the 1e-5 bar, every gradient tensor separately) and against the generic fp32 tile
+    (T) family.  B = 300 / 1000 / 5000 / 77 leave a ragged last tile; 5000 gives each split-K group several tiles."""
+    rng = np.random.default_rng(1000 * H + B)
+    p = rand_params(rng, H, H)
+    o = ol.Oracle(h1=H, h2=H)
+    obs = rng.standard_normal((B, 18)).astype(np.float32)
+    _, v64, _, m64 = o.policy_step(p, obs, None, "f64")
+    std = np.exp(p[o.offset(12):o.offset(13)].astype(np.float64))
+    act = (m64 + std * rng.standard_normal((B, 18))).astype(np.float32)
+    z = (act - m64) / std
+    old_nlp = (0.5 * (z * z).sum(1) + 18 * 0.9189385175704956 + np.log(std).sum() + 0.1 * rng.standard_normal(B)).astype(np.float32)
+    old_v = (v64 + 0.3 * rng.standard_normal(B)).astype(np.float32)
+    ret = (v64 + 0.5 * rng.standard_normal(B)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    res = []
+    for env in (None, "PPO_DISABLE_WIDE"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=H, hidden2=H, n_envs=4, n_steps=8, nminibatches=4)
+        assert ("wgemm_kernel" in c.kernel_family("train")) == (env is None)
+        res.append(c.loss_grad(obs, act, adv, ret, old_nlp, old_v, 0.2))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    g64, l64 = o.loss_grad(p, obs, act, adv, ret, old_nlp, old_v, 0.2, "f64")
+    (gw, lw), (gt, lt) = res
+    assert np.allclose(lw, l64, rtol=TOL, atol=1e-7)
+    assert rel_err(gw, g64) < TOL
+    for t in range(13):
+        sl = slice(o.offset(t), o.offset(t + 1))
+        if t == 9:
+            # vf/b is ONE number, (vf_coef / B) * sum_i c_i (v_i - R_i): a sum with cancellation whose fp32 evaluation is only
+            # good to eps * sum|terms| whatever the kernel; bound the error by that instead of by the cancelled result
+            atol = 2.0 ** -23 * 0.5 * float(np.mean(np.abs(v64 - ret)))
+            assert abs(float(gw[sl][0]) - float(g64[sl][0])) < TOL * abs(float(g64[sl][0])) + atol
+            continue
+        assert rel_err(gw[sl], g64[sl]) < TOL, f"gradient tensor {t} vs the fp64 oracle"
+        assert rel_err(gw[sl], gt[sl]) < 3e-5, f"gradient tensor {t} vs the T family"
+
+
+def test_wide_family_training_equals_tile_family(core_mod, monkeypatch):
+    """One whole update of a [256,256] net (device shuffle, advantage statistics, W-family minibatch steps with a ragged
+    last tile, slabs -> reduce + clip + Adam, 8 dependent steps) against the same update on the T family.  The two
+    evaluate the gradients in different fp32 orders (each within 1e-5 of the fp64 oracle, test above) and Adam's
+    g / (sqrt(v) + eps) magnifies that for the parameters whose gradient is near eps, hence the looser bound here:
+    this test is about the plumbing (slab layout, split-K groups, folded bias / loss columns)."""
+    rng = np.random.default_rng(31)
+    p = rand_params(rng, 256, 256)
+    res = []
+    for env in (None, "PPO_DISABLE_WIDE"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=256, hidden2=256, n_envs=100, n_steps=32, nminibatches=4, noptepochs=2, seed=21)
+        c.shuffle_seed(7)
+        c.synth_env_reset()
+        losses = c.learn_update_synthetic(3e-4, 0.2)
+        res.append(dict(losses=losses, params=c.get_tensor("params"), m=c.get_tensor("adam_m"), v=c.get_tensor("adam_v")))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    a, b = res
+    moved = np.abs(a["params"] - p).max()
+    assert moved > 1e-4
+    assert np.abs(a["params"] - b["params"]).max() < 5e-3 * moved
+    assert rel_err(a["losses"], b["losses"]) < 1e-4
+    assert rel_err(a["m"], b["m"]) < 1e-4 and rel_err(a["v"], b["v"]) < 1e-4
+
+
 # ------------------------------------------------------------------ minibatch step / whole update (a9-a11)
 def _oracle_learner(kat, flat, n_envs, n_steps, nmb, epochs, env_kind, seed=77, shuffle_seed=42, h1=4, h2=5, lr=3.9e-4, cr=0.2):
     c = kat["consts"]
