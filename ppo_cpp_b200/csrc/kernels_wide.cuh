@@ -14,17 +14,16 @@
 // The same block serves as K-major operand (forward: act x W, backward: dY x W^T) and as MN-major operand
 // (weight gradients: act^T x dY reduced over the samples).
 //
-// Kernels (one minibatch = 17 launches, all captured in the update's CUDA graph):
+// Kernels (one minibatch = 11 launches + reduce + Adam, all captured in the update's CUDA graph):
 //   wide_prep_weights_kernel   fp32 parameters -> weight images (W0' with the bias as an extra input row, W1, heads)
 //   wide_gather_kernel         minibatch rows of the rollout buffer -> X' image (obs | 1)
-//   wgemm_kernel               persistent, warp-specialised (bulk-copy producer / MMA issuer / 4 epilogue warps),
+//   wgemm_kernel               persistent, warp-specialised (bulk-copy producer / MMA issuer / 8 epilogue warps),
 //                              2-stage shared-memory ring, double-buffered TMEM accumulators (main + cross product)
 //       mode FWD   C = A(K-major image) x W(MN-major view)      Z1, Z2, head
 //       mode BWD   C = A(K-major image) x W^T(K-major view)     dH2, dH1
 //       mode DW    slab[kgroup] = A^T(MN-major) x B(MN-major) over a range of samples (split-K): dW1, dWhead, dW0'
-//   wide_act_kernel            H = tanh(Z + b) -> image
+//       epilogues: fp32 result | H = tanh(acc + b) -> image | dP = acc * (1 - H^2) -> image + column sums (bias gradient)
 //   wide_loss_kernel           policy / value losses per sample, dL/dmu, dL/dlogstd terms, dL/dv -> dY image
-//   wide_dact_kernel           dP = dH * (1 - H^2) -> image, column sums (bias gradients) per tile
 //   wide_fold_kernel           per-tile column / loss sums -> slab 0 (zeros in the other slabs)
 // The slabs then go through the same reduce (+ cross-GPU exchange) + global-norm clip + Adam kernel as every family.
 #pragma once
@@ -37,12 +36,13 @@ using umma::chunk_off;
 using umma::smem_u32;
 
 constexpr int TM = 128;            // samples per tile
-constexpr int GEMM_NTH = 192;      // warp 0: producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int GEMM_NTH = 320;      // warp 0: producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quarter)
 constexpr uint32_t BLK16 = 16384;  // [128 x 64] bf16 block
 constexpr uint32_t BLK8 = 8192;    // [64 x 64]
 constexpr uint32_t STAGE_A = 3 * BLK16, STAGE_B = 3 * BLK16, STAGE = STAGE_A + STAGE_B;
 constexpr int NSTAGE = 2;
-constexpr uint32_t GEMM_SMEM = NSTAGE * STAGE + 128 + 1024;  // + barriers + alignment slack
+constexpr uint32_t EPI_STAGE = 4096;  // per epilogue warp: 32 rows x 128 B of an image block, staged for a bulk store
+constexpr uint32_t GEMM_SMEM = NSTAGE * STAGE + 128 + 8 * EPI_STAGE + 1024;  // + barriers + epilogue staging + alignment slack
 constexpr int COLPART = 64;        // floats per tile written by the loss kernel
 constexpr int CP_DBPI = 0, CP_DLS = 18, CP_DBV = 36, CP_PG = 37, CP_VF = 38, CP_KL = 39, CP_CLIP = 40;
 
@@ -74,6 +74,7 @@ struct Geom {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_DW = 2 };
 enum { DW_W1 = 0, DW_HEAD = 1, DW_W0 = 2 };
+enum { EPI_STORE = 0, EPI_ACT = 1, EPI_DACT = 2 };  // fp32 result | tanh(acc + b) -> image | acc * (1 - H^2) -> image (+ column sums)
 
 struct DwProb {
     const uint8_t* A; size_t a_tower, a_tile, a_piece;  // M side: image whose features become the rows of the result
@@ -90,6 +91,13 @@ struct GemmArgs {
     uint32_t b_bytes;
     int n_tile, n_blks, m_tiles;
     float* C; size_t c_tower; int ldc;
+    // fused epilogues (FWD / BWD): activation images [tower][tile][piece][nb][16 KB]
+    int epi;
+    const float* P; int bias_off[2];          // EPI_ACT: bias per tower (offset into P, or -1)
+    uint8_t* img_out;
+    size_t img_tower, img_tile, img_piece;
+    float* colsum; int cap;                   // EPI_DACT: [tower][tile * 4 + lane quarter][H] partial column sums, or NULL
+    float* gbuf;                              // 1 - H^2 as fp32, [tower][tile][column][128 rows]: written by EPI_ACT, read by EPI_DACT
     // DW
     DwProb dw[3];
     int n_dw, KG, HT;     // split-K groups, half tiles (64 samples) in the minibatch
@@ -123,6 +131,28 @@ __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
             else if (now - t0 > 4000000000LL) __trap();  // ~2 s
         }
     }
+}
+
+// x[c] summed over the 32 lanes, for 32 columns at once (31 shuffles): lane l returns the sum of column l.  Fixed order.
+__device__ __forceinline__ float colsum32(float (&x)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? x[i] : x[i + o];
+            const float keep = up ? x[i + o] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return x[0];
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 q, float* x) {
+    x[0] = __uint_as_float(q.x << 16); x[1] = __uint_as_float(q.x & 0xffff0000u);
+    x[2] = __uint_as_float(q.y << 16); x[3] = __uint_as_float(q.y & 0xffff0000u);
+    x[4] = __uint_as_float(q.z << 16); x[5] = __uint_as_float(q.z & 0xffff0000u);
+    x[6] = __uint_as_float(q.w << 16); x[7] = __uint_as_float(q.w & 0xffff0000u);
 }
 
 struct Task {
@@ -166,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_FULL(s)));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_EMPTY(s)));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(BAR_ACCFULL(s)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(BAR_ACCEMPTY(s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(BAR_ACCEMPTY(s)));
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -278,21 +308,101 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue: TMEM -> fp32 result
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        // ------------------------------------------------------------ epilogue: TMEM -> result
+        // warp (2 + e): TMEM lane quarter q = warp & 3 (the quarter a warp may read), column half e >> 2 of the tile.
+        // Image epilogues: a warp owns 32 rows x 64 columns = one contiguous 4 KB slice of a [128 x 64] image block per
+        // piece; it is assembled in shared memory (same swizzle, conflict-free) and leaves as ONE bulk store - storing the
+        // 16-byte chunks from the row-per-thread TMEM layout costs 32 L1 requests per instruction and was the bound.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        uint8_t* stg = smem + NSTAGE * STAGE + 128 + (uint32_t)(warp - 2) * EPI_STAGE;
+        const uint32_t stg_u32 = smem_u32(stg);
         uint32_t tc = 0;
         for (int t = blockIdx.x; t < g.ntasks; t += gridDim.x, ++tc) {
             const Task k = decode_task(g, t);
             const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+            float v[64];
+            if (!dwm && g.epi != EPI_STORE) {
+                // ---- H = tanh(acc + b) or dP = acc * (1 - H^2), 64 columns = column block cb of the layer
+                const int col0 = k.n * g.n_tile + 64 * half;
+                const size_t boff = k.tower * g.img_tower + (size_t)k.m * g.img_tile + (size_t)(col0 >> 6) * BLK16 + (size_t)q * EPI_STAGE;
+                float* gp = g.gbuf + (((size_t)k.tower * g.cap + k.m) * g.H + col0) * TM + row;
+                float gr[64];
+                if (g.epi == EPI_DACT) {  // requested before the accumulator is waited for
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) gr[i] = __ldg(gp + (size_t)i * TM);
+                }
+                mbar_wait_b(BAR_ACCFULL(ab), aph);
+                umma::tc_fence_after();
+                const uint32_t dm = tlane + ab * 256u + 64u * half, dc = dm + 128u;
+                umma::tmem_ld32_sum(dm, dc, v);
+                umma::tmem_ld32_sum(dm + 32, dc + 32, v + 32);
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_ACCEMPTY(ab));  // the accumulator is in registers: the MMA warp may go on
+                if (g.epi == EPI_ACT) {
+                    const int ob = g.bias_off[k.tower];
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        v[i] = tanhf(ob >= 0 ? v[i] + __ldg(g.P + ob + col0 + i) : v[i]);
+                        gp[(size_t)i * TM] = 1.f - v[i] * v[i];
+                    }
+                } else {  // TanhGrad (GRAPH:20925-23699)
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] *= gr[i];
+                    if (g.colsum) {  // bias gradient: column sums over this warp's 32 rows
+                        float* cs = g.colsum + (((size_t)k.tower * g.cap + k.m) * 4 + q) * g.H + col0 + lane;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float w32[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) w32[i] = v[32 * hh + i];
+                            cs[32 * hh] = colsum32(w32, lane);
+                        }
+                    }
+                }
+                // three bf16 pieces, one after the other through the staging slice: piece p = bf16(x), x -= piece
+#pragma unroll 1
+                for (int p = 0; p < 3; ++p) {
+                    if (p) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 pk;
+                        uint32_t* w4 = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(&b2);
+                            w4[i] = u;
+                            v[8 * j + 2 * i] -= __uint_as_float(u << 16);
+                            v[8 * j + 2 * i + 1] -= __uint_as_float(u & 0xffff0000u);
+                        }
+                        *reinterpret_cast<uint4*>(stg + chunk_off(lane, j)) = pk;
+                    }
+                    umma::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.img_out + boff + (size_t)p * g.img_piece),
+                                     "r"(stg_u32), "r"(EPI_STAGE)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                continue;
+            }
             mbar_wait_b(BAR_ACCFULL(ab), aph);
             umma::tc_fence_after();
             const uint32_t dm = tlane + ab * 256u, dc = dm + 128u;
-            float v[32];
-            if (!dwm) {
+            if (!dwm) {  // EPI_STORE: fp32 result
+                const int ncols = g.n_tile >> 1, cbeg = half * ncols;
                 float* dst = g.C + k.tower * g.c_tower + ((size_t)k.m * TM + row) * g.ldc + (size_t)k.n * g.n_tile;
-                for (int c0 = 0; c0 < g.n_tile; c0 += 32) {
+                for (int c0 = cbeg; c0 < cbeg + ncols; c0 += 32) {
                     umma::tmem_ld32_sum(dm + c0, dc + c0, v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -301,14 +411,17 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
                 const DwProb& P = g.dw[k.prob];
                 float* slab = g.partial + (size_t)k.kg * g.PS;
                 const int r = k.m * TM + row;  // feature index of the M side
-                for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
-                    if (P.kind != DW_W1 && c0 > 0) break;  // heads and X' use the first 32 columns only
-                    umma::tmem_ld32_sum(dm + c0, dc + c0, v);
-                    if (P.kind == DW_W1) {  // dW1[k_in = r][n_out]
+                if (P.kind == DW_W1) {  // dW1[k_in = r][n_out]
+                    const int ncols = P.n_tile >> 1, cbeg = half * ncols;
+                    for (int c0 = cbeg; c0 < cbeg + ncols; c0 += 32) {
+                        umma::tmem_ld32_sum(dm + c0, dc + c0, v);
                         float* dst = slab + g.off_w1[k.tower] + (size_t)r * g.H + (size_t)k.n * P.n_tile + c0;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dst[i] = v[i];  // slabs are PS floats apart (odd): no vector stores
-                    } else if (P.kind == DW_HEAD) {  // pi: dWpi[r][j]; V: dwv[r]
+                    }
+                } else if (half == 0) {  // heads and X' use the first 32 columns only
+                    umma::tmem_ld32_sum(dm, dc, v);
+                    if (P.kind == DW_HEAD) {  // pi: dWpi[r][j]; V: dwv[r]
                         if (k.tower == 0) {
                             float* dst = slab + g.off_piw + (size_t)r * g.A_dim;
 #pragma unroll
@@ -330,6 +443,7 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR_ACCEMPTY(ab));
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 #undef BAR_FULL
 #undef BAR_EMPTY
@@ -345,9 +459,9 @@ struct WideBufs {
     Geom G;
     uint8_t *X, *H1, *H2, *dP2, *dP1, *dY;  // images
     uint8_t *W0, *W1, *WH;                  // weight images
-    float *Z, *MU;                          // fp32 GEMM results: [2][Bpad x H], [2][Bpad x 64]
+    float *G1, *G2, *MU;                    // G: 1 - H^2 per layer, fp32 [2][cap][H][128]; MU: fp32 head results [2][cap * 128 x 64]
     float *colloss;                         // [NT][COLPART]
-    float *colb1;                           // [2][NT][H]
+    float *colb1;                           // [2][cap * 4][H]: per (tile, lane quarter) column sums of dP2
 };
 
 // fp32 parameters -> weight images.  One thread per 16-byte chunk.
@@ -419,78 +533,6 @@ __global__ void wide_gather_kernel(const TrainArgs a, const WideBufs w) {
             }
         }
         umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
-    }
-}
-
-// H = tanh(Z + b) -> image.  Thread per (tower, row, 8 columns).
-__global__ void wide_act_kernel(const float* __restrict__ Z, const float* __restrict__ P, int off_b_pi, int off_b_vf, uint8_t* img, const Geom G) {
-    const int H = G.H, h8 = H / 8;
-    const long total = 2L * G.Bpad * h8;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int j8 = (int)(e % h8);
-        const long rr = e / h8;
-        const int row = (int)(rr % G.Bpad), tower = (int)(rr / G.Bpad);
-        const float4* src = reinterpret_cast<const float4*>(Z + tower * G.z_tower + (size_t)row * H + 8 * j8);
-        const float4 z0 = __ldg(src), z1 = __ldg(src + 1);
-        float x[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-        const int ob = tower ? off_b_vf : off_b_pi;
-        if (ob >= 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] += __ldg(P + ob + 8 * j8 + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = tanhf(x[i]);
-        uint8_t* blk = img + tower * G.act_tower + (size_t)(row >> 7) * G.act_tile + (size_t)(j8 >> 3) * BLK16;
-        umma::store_chunk(blk, (uint32_t)G.act_piece, chunk_off(row & 127, j8 & 7), x);
-    }
-}
-
-__device__ __forceinline__ void unpack_bf16x8(const uint4 q, float* x) {
-    x[0] = __uint_as_float(q.x << 16); x[1] = __uint_as_float(q.x & 0xffff0000u);
-    x[2] = __uint_as_float(q.y << 16); x[3] = __uint_as_float(q.y & 0xffff0000u);
-    x[4] = __uint_as_float(q.z << 16); x[5] = __uint_as_float(q.z & 0xffff0000u);
-    x[6] = __uint_as_float(q.w << 16); x[7] = __uint_as_float(q.w & 0xffff0000u);
-}
-
-// dP = dH * (1 - H^2) -> image (TanhGrad, GRAPH:20925-23699); H is read back from its image (p0 + p1 + p2 is exact).
-// grid = (tiles, towers), 256 threads: thread = (8 columns j8, row lane); H / 8 divides 256 (H = 128, 256, 512, 1024).
-// Optional column sums over the tile's rows (bias gradients), summed in a fixed order.
-__global__ void __launch_bounds__(256) wide_dact_kernel(const float* __restrict__ dH, const uint8_t* __restrict__ Himg, uint8_t* dPimg,
-                                                        float* __restrict__ colsum, const Geom G) {
-    __shared__ float s_red[2048];  // [row lane][H]
-    const int H = G.H, h8 = H / 8, tile = blockIdx.x, tower = blockIdx.y;
-    const int lanes = 256 / h8;
-    const int j8 = (int)(threadIdx.x % h8), rl = threadIdx.x / h8;
-    float cs[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
-    const size_t boff = tower * G.act_tower + (size_t)tile * G.act_tile + (size_t)(j8 >> 3) * BLK16;
-    for (int r = rl; r < TM; r += lanes) {
-        const float4* src = reinterpret_cast<const float4*>(dH + tower * G.z_tower + ((size_t)tile * TM + r) * H + 8 * j8);
-        const float4 d0 = __ldg(src), d1 = __ldg(src + 1);
-        const uint32_t co = chunk_off(r, j8 & 7);
-        float h0[8], h1[8], h2[8], x[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + co)), h0);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + G.act_piece + co)), h1);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(Himg + boff + 2 * G.act_piece + co)), h2);
-        const float dh[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float h = (h0[i] + h1[i]) + h2[i];
-            x[i] = dh[i] * (1.f - h * h);
-            cs[i] += x[i];
-        }
-        umma::store_chunk(dPimg + boff, (uint32_t)G.act_piece, co, x);
-    }
-    if (colsum) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s_red[rl * H + 8 * j8 + i] = cs[i];
-        __syncthreads();
-        for (int c = threadIdx.x; c < H; c += 256) {
-            float t = 0.f;
-            for (int l = 0; l < lanes; ++l) t += s_red[l * H + c];
-            colsum[((size_t)tower * G.cap + tile) * H + c] = t;
-        }
     }
 }
 
@@ -600,7 +642,7 @@ __global__ void wide_fold_kernel(const TrainArgs a, const WideBufs w, int nslabs
         size_t stride = 0;
         if (e < 2 * H) {
             const int tower = e / H, c = e % H;
-            src = w.colb1 + (size_t)tower * G.cap * H + c; stride = H;
+            src = w.colb1 + (size_t)tower * G.cap * 4 * H + c; stride = H;
             col = d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + c;
         } else if (e < 2 * H + 2 * A + 1) {
             const int c = e - 2 * H;  // colloss columns 0 .. 2A: dbpi, dlogstd, dbv
@@ -612,8 +654,9 @@ __global__ void wide_fold_kernel(const TrainArgs a, const WideBufs w, int nslabs
             const int sc = l == L_PG ? CP_PG : l == L_VF ? CP_VF : l == L_KL ? CP_KL : l == L_CLIP ? CP_CLIP : -1;
             if (sc >= 0) { src = w.colloss + sc; stride = COLPART; }
         }
+        const int nsrc = e < 2 * H ? 4 * G.NT : G.NT;
         if (src)
-            for (int i = lane; i < G.NT; i += 32) t += (double)src[(size_t)i * stride];
+            for (int i = lane; i < nsrc; i += 32) t += (double)src[(size_t)i * stride];
         t = warp_sum(t);
         if (lane == 0) {
             if (e >= 2 * H + A && e < 2 * H + 2 * A) t -= (double)a.ent_coef;  // d(-ent_coef * entropy)/dlogstd_j (ent_coef is pre-divided by the world size)

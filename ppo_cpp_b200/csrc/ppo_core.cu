@@ -1373,9 +1373,9 @@ static int ensure_wide(ppo_core* c, int tiles) {
     const size_t R = (size_t)tiles * wide::TM, H = (size_t)G.H;
     const size_t sizes[] = {(size_t)tiles * G.x_tile, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.dy_tower,
                             2 * G.w0_tower, 2 * G.w1_tower, 2 * G.wh_tower, 2 * R * H * sizeof(float), 2 * R * 64 * sizeof(float),
-                            (size_t)tiles * wide::COLPART * sizeof(float), 2 * (size_t)tiles * H * sizeof(float)};
+                            (size_t)tiles * wide::COLPART * sizeof(float), 2 * 4 * (size_t)tiles * H * sizeof(float), 2 * R * H * sizeof(float)};
     size_t off[14], total = 0;
-    for (int i = 0; i < 13; ++i) {
+    for (int i = 0; i < 14; ++i) {
         off[i] = total;
         total += (sizes[i] + 1023) & ~(size_t)1023;
     }
@@ -1385,7 +1385,8 @@ static int ensure_wide(ppo_core* c, int tiles) {
     wide::WideBufs& w = c->wb;
     w.X = base + off[0]; w.H1 = base + off[1]; w.H2 = base + off[2]; w.dP2 = base + off[3]; w.dP1 = base + off[4]; w.dY = base + off[5];
     w.W0 = base + off[6]; w.W1 = base + off[7]; w.WH = base + off[8];
-    w.Z = reinterpret_cast<float*>(base + off[9]); w.MU = reinterpret_cast<float*>(base + off[10]);
+    w.G1 = reinterpret_cast<float*>(base + off[9]); w.MU = reinterpret_cast<float*>(base + off[10]);
+    w.G2 = reinterpret_cast<float*>(base + off[13]);
     w.colloss = reinterpret_cast<float*>(base + off[11]); w.colb1 = reinterpret_cast<float*>(base + off[12]);
     c->wide_cap = tiles;
     return PPO_OK;
@@ -1411,41 +1412,39 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
         LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w);
         LAUNCH(c, wide_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a, w);
     }
-    const int ew_grid = (int)std::min<long>((2L * G.Bpad * (H / 8) + 255) / 256, (long)c->sm_count * 16);
     GemmArgs g{};
-    // ---- layer 0: Z1 = X' W0'
+    g.P = a.params; g.img_tower = G.act_tower; g.img_tile = G.act_tile; g.img_piece = G.act_piece; g.cap = G.cap; g.H = H;
+    // ---- layer 0: H1 = tanh(X' W0')  (bias through the ones column of X')
     g.mode = MODE_FWD;
     g.A = w.X; g.a_tower = 0; g.a_tile = G.x_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
     g.B = w.W0; g.b_tower = G.w0_tower; g.b_piece = G.w0_piece; g.b_kb = 0; g.b_g = 4096; g.b_bytes = 4096;
     g.n_tile = 128; g.n_blks = H / 128; g.m_tiles = NT; g.ntasks = 2 * NT * g.n_blks;
-    g.C = w.Z; g.c_tower = G.z_tower; g.ldc = H;
+    g.epi = EPI_ACT; g.bias_off[0] = g.bias_off[1] = -1; g.img_out = w.H1; g.gbuf = w.G1;
     launch_wgemm(c, g);
-    LAUNCH(c, wide_act_kernel, ew_grid, 256, 0, w.Z, a.params, -1, -1, w.H1, G);
-    // ---- layer 1: Z2 = H1 W1 (+ b1 in the activation kernel)
+    // ---- layer 1: H2 = tanh(H1 W1 + b1)
     g.A = w.H1; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
+    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2; g.gbuf = w.G2;
     launch_wgemm(c, g);
-    LAUNCH(c, wide_act_kernel, ew_grid, 256, 0, w.Z, a.params, d.off[T_PI_FC1_B], d.off[T_VF_FC1_B], w.H2, G);
-    // ---- heads: [mu | v] = H2 WH
+    // ---- heads: [mu | v] = H2 WH (fp32 result), then the losses and dY
     g.A = w.H2;
     g.B = w.WH; g.b_tower = G.wh_tower; g.b_piece = G.wh_piece; g.b_kb = BLK8; g.b_g = 0; g.b_bytes = BLK8;
     g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT;
-    g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
+    g.epi = EPI_STORE; g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
     launch_wgemm(c, g);
     LAUNCH(c, (wide_loss_kernel<18>), NT, TM, 0, a, w);
-    // ---- dH2 = dY WH^T, dP2 = dH2 (1 - H2^2)
+    // ---- dP2 = (dY WH^T) (1 - H2^2), column sums -> db1
     g.mode = MODE_BWD;
     g.A = w.dY; g.a_tower = G.dy_tower; g.a_tile = G.dy_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
     g.B = w.WH; g.b_kb = 0; g.b_g = BLK16; g.b_bytes = BLK16;
     g.n_tile = 128; g.n_blks = H / 128; g.ntasks = 2 * NT * g.n_blks;
-    g.C = w.Z; g.c_tower = G.z_tower; g.ldc = H;
+    g.epi = EPI_DACT; g.gbuf = w.G2; g.img_out = w.dP2; g.colsum = w.colb1;
     launch_wgemm(c, g);
-    LAUNCH(c, wide_dact_kernel, dim3(NT, 2), 256, 0, w.Z, w.H2, w.dP2, w.colb1, G);
-    // ---- dH1 = dP2 W1^T, dP1 = dH1 (1 - H1^2)
+    // ---- dP1 = (dP2 W1^T) (1 - H1^2)
     g.A = w.dP2; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = (size_t)nb * BLK8; g.b_g = BLK16; g.b_bytes = BLK16;
+    g.gbuf = w.G1; g.img_out = w.dP1; g.colsum = nullptr;
     launch_wgemm(c, g);
-    LAUNCH(c, wide_dact_kernel, dim3(NT, 2), 256, 0, w.Z, w.H1, w.dP1, (float*)nullptr, G);
     // ---- weight gradients, split over KG groups of samples: dW1 = H1^T dP2, dWhead = H2^T dY, dW0'^T = dP1^T X'
     GemmArgs q{};
     q.mode = MODE_DW;
