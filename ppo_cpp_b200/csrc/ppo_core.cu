@@ -204,6 +204,12 @@ static PeerMailbox make_mailbox(const ppo_core* c, bool grads) {
 }
 // single GPU, or multi-GPU with the peer mailboxes mapped: the persistent / cooperative kernels carry the exchanges
 static inline bool fast_path(const ppo_core* c) { return c->desc.world_size == 1 || c->mbox_ready; }
+// CUDA graphs hold only our own kernels.  With more than one rank that requires every exchange of the captured work
+// to run through the peer mailboxes inside those kernels; the per-step kernels of the other shapes call NCCL.
+static inline bool rollout_graph_ok(const ppo_core* c) { return c->use_graph && c->desc.world_size == 1; }
+static inline bool update_graph_ok(const ppo_core* c) {
+    return c->use_graph && fast_path(c) && (c->desc.world_size == 1 || c->coop || c->persistent_epoch);
+}
 
 #define LAUNCH(core, kernel, grid, block, smem, ...)                               \
     do {                                                                           \
@@ -1239,7 +1245,7 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
         }
         return PPO_OK;
     }
-    if (!c->use_graph || !fast_path(c)) return rollout_synthetic_enqueue(c);
+    if (!rollout_graph_ok(c)) return rollout_synthetic_enqueue(c);
     // every launch argument of the rollout is a fixed device address (the Philox step counter lives on the device),
     // so the whole rollout is captured once and replayed; the training flag is baked into the captured launches
     ppo_core::EpochGraph& g = c->rollout_graph;
@@ -1650,7 +1656,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
             c->rng_on_device = true;
         }
         ppo_core::EpochGraph& ug = c->update_graph;
-        if (!c->use_graph) {
+        if (!update_graph_ok(c)) {
             TRY(enqueue_update_gpu_shuffle(c, lr, cliprange));
         } else {
             if (!ug.exec || ug.lr != lr || ug.cliprange != cliprange || ug.bpow_slot != c->bpow_slot) {
@@ -1702,7 +1708,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         c->rng.random_shuffle(c->perm_host.data(), nb);  // compounded across epochs (ppo2.hpp:288)
         int* pinned = c->perm_pinned + (size_t)e * nb;
         memcpy(pinned, c->perm_host.data(), sizeof(int) * (size_t)nb);
-        if (!c->use_graph || !fast_path(c)) {
+        if (!update_graph_ok(c)) {
             TRY(prepare_epoch(c, pinned));
             if (c->persistent_epoch && fast_path(c)) TRY(train_epoch_device(c, lr, cliprange, e));
             else

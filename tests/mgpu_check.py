@@ -41,7 +41,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for hidden, p2p in (((4, 5), True), ((64, 64), True), ((4, 5), False), ((64, 64), False)):
+    cases = (((4, 5), True), ((64, 64), True), ((4, 5), False), ((64, 64), False), ((256, 256), True))
+    if os.environ.get("MGPU_CASES") == "wide":
+        cases = (((256, 256), True),)
+    for hidden, p2p in cases:
         n_local = 48  # 1.5 tiles of the persistent rollout kernel per rank
         sharded = run(world, rank, local, n_local, hidden, p2p=p2p)
         tag = f"hidden {hidden} {'p2p mailbox' if p2p else 'nccl'}"
