@@ -118,6 +118,11 @@ int ppo_policy_mean(ppo_core *core, const float *obs, int n, float *action, ppo_
 int ppo_vecnorm_reset(ppo_core *core, const float *raw_obs, float *obs_out, ppo_mem mem);
 int ppo_vecnorm_step(ppo_core *core, const float *raw_obs, const float *raw_rew, const float *done, float *obs_out,
                      float *rew_out, ppo_mem mem);
+/* The same as n_steps consecutive ppo_vecnorm_step calls on a recorded trajectory (raw_obs [n_steps][n_envs][O],
+ * raw_rew / done [n_steps][n_envs]; env/env_normalize.hpp:64-92 applied step by step, running statistics and the
+ * discounted return carried on), evaluated as four HBM-bound launches.  rew_out may be NULL.  Single rank only. */
+int ppo_vecnorm_replay(ppo_core *core, const float *raw_obs, const float *raw_rew, const float *done, int n_steps,
+                       float *obs_out, float *rew_out, ppo_mem mem);
 /* obs_rms / ret_rms as serialised by RunningStatistics (common/running_statistics.hpp:57-86) */
 int ppo_vecnorm_get_stats(ppo_core *core, float *obs_mean, float *obs_var, double *obs_count, float *ret_mean,
                           float *ret_var, double *ret_count);

@@ -92,6 +92,7 @@ def load():
         "ppo_policy_mean": ([core, fp, C.c_int, fp, C.c_int], C.c_int),
         "ppo_vecnorm_reset": ([core, fp, fp, C.c_int], C.c_int),
         "ppo_vecnorm_step": ([core, fp, fp, fp, fp, fp, C.c_int], C.c_int),
+        "ppo_vecnorm_replay": ([core, fp, fp, fp, C.c_int, fp, fp, C.c_int], C.c_int),
         "ppo_vecnorm_get_stats": ([core, fp, fp, C.POINTER(C.c_double), fp, fp, C.POINTER(C.c_double)], C.c_int),
         "ppo_vecnorm_set_stats": ([core, fp, fp, C.c_double, fp, fp, C.c_double], C.c_int),
         "ppo_vecnorm_set_training": ([core, C.c_int], C.c_int),

@@ -178,6 +178,15 @@ class PPOCore:
         _check(self.lib, self.lib.ppo_vecnorm_step(self._h, _addr(raw), _addr(rew), _addr(dn), _addr(obs), _addr(r), PPO_HOST))
         return obs, r
 
+    def vecnorm_replay(self, raw_obs, raw_rew, done):
+        """T consecutive vecnorm_step calls on a recorded trajectory [T, n_envs, O] in four launches."""
+        raw = _f32(raw_obs)
+        T = raw.shape[0]
+        rew, dn = _f32(raw_rew).reshape(T, -1), _f32(done).reshape(T, -1)
+        obs, r = np.zeros_like(raw), np.zeros_like(rew)
+        _check(self.lib, self.lib.ppo_vecnorm_replay(self._h, _addr(raw), _addr(rew), _addr(dn), T, _addr(obs), _addr(r), PPO_HOST))
+        return obs, r
+
     def vecnorm_stats(self):
         om, ov = np.zeros(self.O, np.float32), np.zeros(self.O, np.float32)
         rm, rv = np.zeros(1, np.float32), np.zeros(1, np.float32)

@@ -286,6 +286,259 @@ __global__ void norm_apply_kernel(const ApplyArgs a) {
     if (a.step_ctr && blockIdx.x == 0 && threadIdx.x == 0) *a.step_ctr += 1u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// VecNormalize over a recorded trajectory [T][n][D] (ppo_vecnorm_replay): the result of T consecutive
+// EnvNormalize::step calls (env_normalize.hpp:64-92) computed in three HBM-bound passes instead of T latency-bound
+// launch pairs.  The running statistics at step t depend on all rows of steps <= t, but only through per-step batch
+// moments, so: (1) per-env discounted return scan along t (sequential per env, coalesced across envs) -> rt[t][n];
+// (2) per-step column sums of obs and rt around a fixed pivot, all steps in parallel; (3) one warp replays the T Chan
+// merges in order and records the statistics in force at every step; (4) normalise + clip, all steps in parallel.
+struct ReplayArgs {
+    const float *raw_obs, *raw_rew, *done;  // [T][n][D], [T][n], [T][n]
+    float* ret;                             // [n] in/out: discounted return carried across calls
+    float* rt;                              // [T][n] scratch: ret after the step's reward, before the done reset
+    double* partial;                        // [T][NB][2*(D+1)]
+    float* bmom;                            // [T][2*(D+1)]: batch mean[D+1], batch variance[D+1] of every step
+    float* stats;                           // [T][2*D+1]: mean[D], inv_std[D], inv_ret_std
+    int T, n, D, NB;
+    NormStats st;
+    int update_obs, update_ret, norm_obs, norm_reward;
+    float gamma, clip_obs, clip_rew, eps;
+    float *obs_out, *rew_out;
+};
+
+__global__ void replay_ret_kernel(const ReplayArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    float r = a.ret[e];
+    constexpr int RB = 8;
+    for (int t0 = 0; t0 < a.T; t0 += RB) {
+        float rw[RB], dn[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const bool in = t0 + i < a.T;
+            rw[i] = in ? __ldg(a.raw_rew + (size_t)(t0 + i) * a.n + e) : 0.f;
+            dn[i] = in ? __ldg(a.done + (size_t)(t0 + i) * a.n + e) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            if (t0 + i < a.T) {
+                r = __fadd_rn(__fmul_rn(r, a.gamma), rw[i]);  // env_normalize.hpp:71
+                a.rt[(size_t)(t0 + i) * a.n + e] = r;
+                r = __fmul_rn(r, __fsub_rn(1.0f, dn[i]));      // env_normalize.hpp:88
+            }
+        }
+    }
+    a.ret[e] = r;
+}
+
+// grid (NB, T); blockDim = D * k.  Thread stride is a multiple of D, so a thread's column (pair) never changes.
+__global__ void replay_moments_kernel(const ReplayArgs a) {
+    extern __shared__ double sm[];  // [blockDim][4], then [2*32] warp partials of the return column
+    const int D = a.D, tid = threadIdx.x, nth = blockDim.x, t = blockIdx.y;
+    const size_t S = (size_t)gridDim.x * nth, total = (size_t)a.n * D;
+    const float* x0 = a.raw_obs + (size_t)t * total;
+    const bool vec2 = (D & 1) == 0 && nth % (D / 2) == 0 && (total & 1) == 0;  // 8-byte loads: D even keeps rows 8-byte aligned
+    // pivot = the running mean when the replay starts (fixed for all steps)
+    if (vec2) {
+        const int cp = tid % (D / 2);
+        const double p0 = (double)a.st.obs_mean[2 * cp], p1 = (double)a.st.obs_mean[2 * cp + 1];
+        const float2* x2 = reinterpret_cast<const float2*>(x0);
+        double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+        // two-level sums: runs of 4 elements in fp32 (around the pivot, so the terms are O(std)), runs added in double -
+        // the fp64 pipe (conversions included) was the bound of the all-double loop
+        const float f0 = (float)p0, f1 = (float)p1;
+        size_t e = (size_t)blockIdx.x * nth + tid;
+        for (; e + 3 * S < total / 2; e += 4 * S) {
+            const float2 v0 = __ldg(x2 + e), v1 = __ldg(x2 + e + S), v2 = __ldg(x2 + e + 2 * S), v3 = __ldg(x2 + e + 3 * S);
+            const float a0 = v0.x - f0, a1 = v1.x - f0, a2 = v2.x - f0, a3 = v3.x - f0;
+            const float b0 = v0.y - f1, b1 = v1.y - f1, b2 = v2.y - f1, b3 = v3.y - f1;
+            s0 += (double)((a0 + a1) + (a2 + a3));
+            q0 += (double)(fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3));
+            s1 += (double)((b0 + b1) + (b2 + b3));
+            q1 += (double)(fmaf(b0, b0, b1 * b1) + fmaf(b2, b2, b3 * b3));
+        }
+        for (; e < total / 2; e += S) {
+            const float2 v = __ldg(x2 + e);
+            const float a0 = v.x - f0, b0 = v.y - f1;
+            s0 += (double)a0; q0 += (double)(a0 * a0);
+            s1 += (double)b0; q1 += (double)(b0 * b0);
+        }
+        sm[tid * 4] = s0; sm[tid * 4 + 1] = q0; sm[tid * 4 + 2] = s1; sm[tid * 4 + 3] = q1;
+    } else {
+        const int col = (int)(((size_t)blockIdx.x * nth + tid) % D);
+        const double pivot = (double)a.st.obs_mean[col];
+        double s = 0.0, q = 0.0;
+        for (size_t e = (size_t)blockIdx.x * nth + tid; e < total; e += S) {
+            const double x = (double)__ldg(x0 + e) - pivot;
+            s += x;
+            q += x * x;
+        }
+        sm[tid * 4] = s; sm[tid * 4 + 1] = q;
+    }
+    double rs = 0.0, rq = 0.0;
+    for (size_t i = (size_t)blockIdx.x * nth + tid; i < (size_t)a.n; i += S) {
+        const double r = (double)__ldg(a.rt + (size_t)t * a.n + i);
+        rs += r;
+        rq += r * r;
+    }
+    rs = warp_sum(rs);
+    rq = warp_sum(rq);
+    double* wred = sm + 4 * nth;
+    if ((tid & 31) == 0) { wred[(tid >> 5) * 2] = rs; wred[(tid >> 5) * 2 + 1] = rq; }
+    __syncthreads();
+    double* mine = a.partial + ((size_t)t * gridDim.x + blockIdx.x) * 2 * (D + 1);
+    if (tid < D) {
+        double cs = 0.0, cq = 0.0;
+        if (vec2) {
+            const int k = 2 * (tid & 1);
+            for (int j = tid >> 1; j < nth; j += D / 2) { cs += sm[j * 4 + k]; cq += sm[j * 4 + k + 1]; }
+        } else {
+            for (int j = tid; j < nth; j += D) { cs += sm[j * 4]; cq += sm[j * 4 + 1]; }
+        }
+        mine[tid] = cs;
+        mine[D + 1 + tid] = cq;
+    } else if (tid == D) {
+        double cs = 0.0, cq = 0.0;
+        for (int w = 0; w < (nth + 31) / 32; ++w) { cs += wred[w * 2]; cq += wred[w * 2 + 1]; }
+        mine[D] = cs;
+        mine[2 * D + 1] = cq;
+    }
+}
+
+// grid T, 64 threads: per-step column sums over the NB block partials (fixed order) -> batch mean / variance of step t
+// (colwise().mean() and sum((x-mean)^2)/rows of the reference, evaluated in double and rounded once)
+__global__ void replay_reduce_kernel(const ReplayArgs a) {
+    const int D = a.D, W2 = 2 * (D + 1), c = threadIdx.x, t = blockIdx.x;
+    if (c > D) return;
+    const double* p = a.partial + (size_t)t * a.NB * W2;
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+    int b = 0;
+    for (; b + 2 <= a.NB; b += 2) {
+        s0 += p[(size_t)b * W2 + c]; q0 += p[(size_t)b * W2 + D + 1 + c];
+        s1 += p[(size_t)(b + 1) * W2 + c]; q1 += p[(size_t)(b + 1) * W2 + D + 1 + c];
+    }
+    for (; b < a.NB; ++b) { s0 += p[(size_t)b * W2 + c]; q0 += p[(size_t)b * W2 + D + 1 + c]; }
+    const double rows = (double)a.n;
+    const double pivot = c == D ? 0.0 : (double)a.st.obs_mean[c];  // unchanged until replay_merge_kernel runs
+    const double m1 = (s0 + s1) / rows;
+    double var_d = (q0 + q1) / rows - m1 * m1;
+    if (var_d < 0.0) var_d = 0.0;
+    a.bmom[(size_t)t * W2 + c] = (float)(pivot + m1);
+    a.bmom[(size_t)t * W2 + D + 1 + c] = (float)var_d;
+}
+
+// one CTA: the per-step batch moments are staged through shared memory in chunks (all threads), warp 0 replays the
+// Chan merges in order (lane c < D: obs column c, lane D: the return column), all threads turn the recorded variances
+// into 1/sqrt(var + eps) and write the statistics of every step
+constexpr int REPLAY_CH = 128;
+__global__ void __launch_bounds__(256) replay_merge_kernel(const ReplayArgs a) {
+    extern __shared__ float smf[];  // [REPLAY_CH][2*(D+1)] batch moments, then [REPLAY_CH][2*(D+1)] running (mean, var)
+    const int D = a.D, W2 = 2 * (D + 1), SW = 2 * D + 1, c = threadIdx.x;
+    float* run = smf + (size_t)REPLAY_CH * W2;
+    const bool lane_on = c <= D;
+    const bool is_ret = c == D;
+    const bool upd = lane_on && (is_ret ? a.update_ret : a.update_obs);
+    float mean = 0.f, var = 1.f;
+    double count = 0.0;
+    if (lane_on) {
+        mean = is_ret ? *a.st.ret_mean : a.st.obs_mean[c];
+        var = is_ret ? *a.st.ret_var : a.st.obs_var[c];
+        count = is_ret ? *a.st.ret_count : *a.st.obs_count;
+    }
+    const double rows = (double)a.n;
+    for (int t0 = 0; t0 < a.T; t0 += REPLAY_CH) {
+        const int nt = min(REPLAY_CH, a.T - t0);
+        if (a.update_obs || a.update_ret)
+            for (int i = threadIdx.x; i < nt * W2; i += blockDim.x) smf[i] = a.bmom[(size_t)t0 * W2 + i];
+        __syncthreads();
+        if (lane_on) {
+            for (int t = 0; t < nt; ++t) {
+                if (upd) {
+                    chan_merge(mean, var, count, smf[t * W2 + c], smf[t * W2 + D + 1 + c], rows);
+                    count = rows + count;
+                }
+                run[t * W2 + c] = mean;
+                run[t * W2 + D + 1 + c] = var;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * SW; i += blockDim.x) {
+            const int t = i / SW, k = i % SW;
+            float v;
+            if (k < D) v = run[t * W2 + k];
+            else {
+                const int col = k - D;  // D + col < 2D: obs column col; k == 2D: the return column
+                v = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(run[t * W2 + D + 1 + col], a.eps)));
+            }
+            a.stats[(size_t)t0 * SW + i] = v;
+        }
+        __syncthreads();
+    }
+    if (upd) {
+        if (is_ret) { *a.st.ret_mean = mean; *a.st.ret_var = var; *a.st.ret_count = count; }
+        else {
+            a.st.obs_mean[c] = mean; a.st.obs_var[c] = var;
+            if (c == 0) *a.st.obs_count = count;
+        }
+    }
+}
+
+// grid (blocks, T): normalise + clip step t with the statistics in force after its update (env_normalize.hpp:74-86)
+__global__ void replay_apply_kernel(const ReplayArgs a) {
+    extern __shared__ float ss[];  // [2*D+1]
+    const int D = a.D, t = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * D + 1; i += blockDim.x) ss[i] = a.stats[(size_t)t * (2 * D + 1) + i];
+    __syncthreads();
+    const size_t total = (size_t)a.n * D, stride = (size_t)gridDim.x * blockDim.x;
+    const float2* x2 = reinterpret_cast<const float2*>(a.raw_obs + (size_t)t * total);  // D even: rows are 8-byte aligned
+    float2* o2 = reinterpret_cast<float2*>(a.obs_out + (size_t)t * total);
+    if ((total & 3) == 0) {  // 16-byte accesses over the flat step block
+        const float4* x4 = reinterpret_cast<const float4*>(a.raw_obs + (size_t)t * total);
+        float4* o4 = reinterpret_cast<float4*>(a.obs_out + (size_t)t * total);
+#pragma unroll 4
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total / 4; e += stride) {
+            float4 x = __ldg(x4 + e);
+            if (a.norm_obs) {
+                int c = (int)((4 * e) % D);
+                x.x = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+                c = c + 1 == D ? 0 : c + 1;
+                x.y = fminf(fmaxf(__fmul_rn(__fsub_rn(x.y, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+                c = c + 1 == D ? 0 : c + 1;
+                x.z = fminf(fmaxf(__fmul_rn(__fsub_rn(x.z, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+                c = c + 1 == D ? 0 : c + 1;
+                x.w = fminf(fmaxf(__fmul_rn(__fsub_rn(x.w, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+            }
+            o4[e] = x;
+        }
+    } else if ((D & 1) == 0) {
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total / 2; e += stride) {
+            const int c = (int)((2 * e) % D);
+            float2 x = __ldg(x2 + e);
+            if (a.norm_obs) {
+                x.x = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+                x.y = fminf(fmaxf(__fmul_rn(__fsub_rn(x.y, ss[c + 1]), ss[D + c + 1]), -a.clip_obs), a.clip_obs);
+            }
+            o2[e] = x;
+        }
+    } else {
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+            const int c = (int)(e % D);
+            float x = __ldg(a.raw_obs + (size_t)t * total + e);
+            if (a.norm_obs) x = fminf(fmaxf(__fmul_rn(__fsub_rn(x, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
+            a.obs_out[(size_t)t * total + e] = x;
+        }
+    }
+    if (a.rew_out) {
+        const float inv = ss[2 * D];
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.n; i += stride) {
+            float r = __ldg(a.raw_rew + (size_t)t * a.n + i);
+            if (a.norm_reward) r = fminf(fmaxf(__fmul_rn(r, inv), -a.clip_rew), a.clip_rew);  // no mean subtraction (env_normalize.hpp:80)
+            a.rew_out[(size_t)t * a.n + i] = r;
+        }
+    }
+}
+
 __global__ void clamp_kernel(const float* __restrict__ x, size_t n, float lo, float hi, float* __restrict__ out) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = fminf(fmaxf(x[i], lo), hi);

@@ -973,6 +973,59 @@ extern "C" int ppo_vecnorm_step(ppo_core* c, const float* raw_obs, const float* 
     return PPO_OK;
 }
 
+// T consecutive ppo_vecnorm_step calls on a recorded trajectory in four launches (kernels_misc.cuh, Replay*)
+extern "C" int ppo_vecnorm_replay(ppo_core* c, const float* raw_obs, const float* raw_rew, const float* done, int n_steps,
+                                  float* obs_out, float* rew_out, ppo_mem mem) {
+    if (!c || !raw_obs || !raw_rew || !done || !obs_out || n_steps < 1) return fail(PPO_ERR_INVALID, "ppo_vecnorm_replay: bad arguments");
+    if (c->desc.world_size > 1) return fail(PPO_ERR_UNSUPPORTED, "ppo_vecnorm_replay: single rank only (per-step moments are not exchanged)");
+    CU(cudaSetDevice(c->desc.device));
+    const ppo_core_desc& D = c->desc;
+    const int N = D.n_envs, O = c->d.O, T = n_steps;
+    const size_t tn = (size_t)T * N, tno = tn * O;
+    const int threads = O * std::max(1, 256 / O);
+    const int NB = std::max(1, std::min(64, (int)(((size_t)N * O + (size_t)threads * 16 - 1) / ((size_t)threads * 16))));
+    const size_t n_partial = (size_t)T * NB * 2 * (O + 1);  // doubles
+    const size_t n_stats = (size_t)T * (2 * O + 1);
+    const size_t io = mem == PPO_HOST ? 2 * tno + 3 * tn : 0;
+    const size_t n_mom = (size_t)T * 2 * (O + 1);  // floats
+    TRY(ensure_scratch(c, io + tn + 2 * n_partial + n_mom + n_stats + 16));
+    float* p = c->scratch;
+    ReplayArgs a{};
+    if (mem == PPO_HOST) {
+        float* d_obs = p; p += tno;
+        float* d_out = p; p += tno;
+        float* d_rew = p; p += tn;
+        float* d_done = p; p += tn;
+        float* d_rout = p; p += tn;
+        TRY(h2d(c, d_obs, raw_obs, tno)); TRY(h2d(c, d_rew, raw_rew, tn)); TRY(h2d(c, d_done, done, tn));
+        a.raw_obs = d_obs; a.raw_rew = d_rew; a.done = d_done; a.obs_out = d_out; a.rew_out = rew_out ? d_rout : nullptr;
+    } else {
+        a.raw_obs = raw_obs; a.raw_rew = raw_rew; a.done = done; a.obs_out = obs_out; a.rew_out = rew_out;
+    }
+    a.rt = p; p += tn;
+    a.partial = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
+    a.bmom = reinterpret_cast<float*>(a.partial + n_partial);
+    a.stats = a.bmom + n_mom;
+    a.ret = c->ret; a.T = T; a.n = N; a.D = O; a.NB = NB; a.st = c->st;
+    a.update_obs = D.training && D.norm_obs; a.update_ret = D.training && D.norm_reward;
+    a.norm_obs = D.norm_obs; a.norm_reward = D.norm_reward;
+    a.gamma = D.norm_gamma; a.clip_obs = D.clip_obs; a.clip_rew = D.clip_reward; a.eps = D.norm_epsilon;
+    LAUNCH(c, replay_ret_kernel, (N + 127) / 128, 128, 0, a);
+    if (a.update_obs || a.update_ret)
+        LAUNCH(c, replay_moments_kernel, dim3(NB, T), threads, sizeof(double) * (4 * (size_t)threads + 64), a);
+    if (a.update_obs || a.update_ret) LAUNCH(c, replay_reduce_kernel, T, 64, 0, a);
+    LAUNCH(c, replay_merge_kernel, 1, 256, REPLAY_CH * sizeof(float) * 4 * (O + 1), a);
+    const int ab = (int)std::max<size_t>(1, std::min<size_t>(1024, ((size_t)N * O / 4 + 1023) / 1024));  // ~4 float4 per thread
+    LAUNCH(c, replay_apply_kernel, dim3(ab, T), 256, sizeof(float) * (2 * O + 1), a);
+    CU(cudaGetLastError());
+    if (mem == PPO_HOST) {
+        TRY(d2h(c, obs_out, a.obs_out, tno));
+        if (rew_out) TRY(d2h(c, rew_out, a.rew_out, tn));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return PPO_OK;
+}
+
 extern "C" int ppo_vecnorm_get_stats(ppo_core* c, float* obs_mean, float* obs_var, double* obs_count, float* ret_mean,
                                      float* ret_var, double* ret_count) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
@@ -1956,6 +2009,9 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
                 a.norm_obs = 1; a.norm_reward = 1; a.clip_obs = c->desc.clip_obs; a.clip_rew = c->desc.clip_reward; a.eps = c->desc.norm_epsilon;
                 a.obs_out = c->cur_obs;
                 LAUNCH(c, norm_apply_kernel, std::max(1, std::min(c->sm_count * 8, (int)(((size_t)N * c->d.O + 255) / 256))), 256, 0, a);
+            } else if (w == "vecnorm_replay") {  // in place over the rollout buffers (timing only: the statistics keep moving)
+                st = ppo_vecnorm_replay(c, slab(c, B_OBS, 0), slab(c, B_TRUE_REW, 0), slab(c, B_DONES, 0), T, slab(c, B_OBS, 0),
+                                        slab(c, B_UNNORM_REW, 0), PPO_DEVICE);
             } else if (w == "gae") {
                 st = launch_gae(c, slab(c, B_TRUE_REW, 0), slab(c, B_VALUES, 0), slab(c, B_DONES, 0), c->last_values, c->cur_dones, T, N,
                                 c->desc.gamma, c->desc.lam, nullptr, slab(c, B_RETURNS, 0));

@@ -138,6 +138,35 @@ def test_vecnorm_clip_and_constant_input(core_mod):
     c.close()
 
 
+@pytest.mark.parametrize("T,N", [(1, 1), (40, 7), (16, 4096), (300, 33)])
+def test_vecnorm_replay_equals_stepwise(core_mod, T, N):
+    """ppo_vecnorm_replay (a recorded trajectory in four HBM-bound launches: per-env return scan, per-step moments of all
+    steps at once, the T Chan merges replayed by one warp, normalise + clip) against T calls of ppo_vecnorm_step, and the
+    stepwise path is itself checked against the oracle above.  Episodes end inside the trajectory (done resets the
+    discounted return); a second replay continues from the carried state."""
+    rng = np.random.default_rng(T * 1000 + N)
+    raw = (3.0 + 2.0 * rng.standard_normal((2 * T, N, 18))).astype(np.float32)
+    raw[:, :, 5] *= 40.0  # exercises the clip
+    rew = rng.standard_normal((2 * T, N)).astype(np.float32)
+    done = (rng.random((2 * T, N)) < 0.1).astype(np.float32)
+    a = make_core(core_mod, None, n_envs=N, n_steps=8, nminibatches=1)
+    b = make_core(core_mod, None, n_envs=N, n_steps=8, nminibatches=1)
+    a.vecnorm_reset(raw[0])
+    b.vecnorm_reset(raw[0])
+    for half in range(2):
+        sl = slice(half * T, (half + 1) * T)
+        want = [a.vecnorm_step(raw[t], rew[t], done[t]) for t in range(half * T, (half + 1) * T)]
+        obs, r = b.vecnorm_replay(raw[sl], rew[sl], done[sl])
+        assert rel_err(obs, np.stack([w[0] for w in want])) < TOL
+        assert rel_err(r, np.stack([w[1] for w in want])) < TOL
+        sa, sb = a.vecnorm_stats(), b.vecnorm_stats()
+        for k in ("obs_mean", "obs_var", "ret_mean", "ret_var"):
+            assert rel_err(np.atleast_1d(sb[k]), np.atleast_1d(sa[k])) < TOL, k
+        assert sa["obs_count"] == sb["obs_count"] and sa["ret_count"] == sb["ret_count"]
+    a.close()
+    b.close()
+
+
 def test_running_stats_and_clamp_standalone(core_mod):
     rng = np.random.default_rng(12)
     c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)

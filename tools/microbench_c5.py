@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 
 # algorithmic bytes per transition / env step
 # the profiled VecNormalize launches carry observations only: moments read 72 B, apply reads 72 B + writes 72 B per env step
-BYTES = {"gae": 16, "norm_moments": 72, "norm_apply": 144, "policy_step": 152, "train_fwdbwd": 160}
+# vecnorm_replay: the whole VecNormalize of a recorded [T, n_envs] trajectory, 164 B per transition
+BYTES = {"gae": 16, "vecnorm_replay": 164, "norm_moments": 72, "norm_apply": 144, "policy_step": 152, "train_fwdbwd": 160}
 
 
 def measure(n_envs, n_steps, h1, h2, peak, iters):
@@ -30,9 +31,9 @@ def measure(n_envs, n_steps, h1, h2, peak, iters):
     c.rollout_synthetic()  # fills the buffer with real rollout data
     c.sync()
     n_batch = n_envs * n_steps
-    units = {"gae": n_batch, "norm_moments": n_envs, "norm_apply": n_envs, "policy_step": n_envs, "train_fwdbwd": n_batch // 32}
+    units = {"gae": n_batch, "vecnorm_replay": n_batch, "norm_moments": n_envs, "norm_apply": n_envs, "policy_step": n_envs, "train_fwdbwd": n_batch // 32}
     out = []
-    for k in ("gae", "norm_moments", "norm_apply", "policy_step", "train_fwdbwd"):
+    for k in ("gae", "vecnorm_replay", "norm_moments", "norm_apply", "policy_step", "train_fwdbwd"):
         ms = c.profile_kernel(k, iters)
         gbs = units[k] * BYTES[k] / (ms * 1e-3) / 1e9
         out.append({"kernel": k, "family": c.kernel_family("train") if k == "train_fwdbwd" else (c.kernel_family("policy") if k == "policy_step" else None),
