@@ -33,6 +33,7 @@ WORKLOADS = {
     "c1": (1, 2048, 4, 5, 32, 10, "C1 shape: 1 env, MLP [4,5], n_steps 2048 (reference CLI defaults)"),
     "c4": (8192, 64, 256, 256, 32, 10, "C4 shard: 8192 envs/GPU, MLP [256,256], 524288 transitions/update/GPU"),
     "c1x4096": (4096, 64, 4, 5, 32, 10, "reference net [4,5] on 4096 synthetic envs"),
+    "c3x8": (32768, 64, 64, 64, 32, 10, "C3 net on 32768 envs (the global batch of an 8-GPU C3 run, on one GPU)"),
 }
 LR, CLIPRANGE = 3.9e-4, 0.161
 METRIC, UNIT = "ppo_env_steps_per_sec", "env-steps/s"

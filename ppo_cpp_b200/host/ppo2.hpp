@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "tensorboard.hpp"
 #include "env.hpp"
 #include "env_normalize.hpp"
 #include "policies.hpp"
@@ -180,6 +181,8 @@ public:
         _init_num_timesteps();
         Runner runner{env, *act_model, n_steps, gamma, lam};
         std::vector<float> episode_reward(n_envs, 0.f);
+        std::unique_ptr<TensorboardWriter> writer;  // TensorboardWriter writer{tensorboard_log, tb_log_name, new_tb_log} (ppo2.hpp:248)
+        if (!tb_log_name.empty() && !tensorboard_log.empty()) writer = std::make_unique<TensorboardWriter>(tensorboard_log, tb_log_name);
         const int n_updates = total_timesteps / n_batch;
         int save_interval = -1;
         if (num_saves > 0) save_interval = static_cast<int>(std::ceil(static_cast<float>(n_updates) / static_cast<float>(num_saves)));
@@ -199,7 +202,7 @@ public:
                 last_losses[i] = loss_vals[i];
             }
             std::cout << std::endl;
-            if (!tb_log_name.empty() && !tensorboard_log.empty()) log_episode_rewards(runner, episode_reward, num_timesteps - n_batch);
+            if (writer) log_episode_rewards(runner, episode_reward, *writer, num_timesteps - n_batch);
             if (save_interval > 0 && num_saves > 0 && update % save_interval == 0) {
                 assert(!save_path.empty());
                 save(save_path, update / save_interval - 1);
@@ -217,15 +220,17 @@ public:
     float last_losses[5] = {0, 0, 0, 0, 0};
 
 private:
-    // Utils::total_episode_reward_logger (ppo2/utils.hpp:75-114) writing "step,episode_reward" CSV lines
-    // instead of TensorBoard events (event files are out of scope)
-    void log_episode_rewards(Runner& runner, std::vector<float>& acc, int total_steps) {
+    // Utils::total_episode_reward_logger (ppo2/utils.hpp:75-114): the reward summed over each finished episode as the
+    // TensorBoard scalar "episode_reward" at global step total_steps + t (ppo2.hpp:358); the same pairs also go to
+    // <tensorboard_log>/episode_reward.csv ("step,episode_reward")
+    void log_episode_rewards(Runner& runner, std::vector<float>& acc, TensorboardWriter& writer, int total_steps) {
         auto rew = runner.fetch("unnormalized_rewards", 1);
         auto dn = runner.fetch("dones", 1);
         std::ofstream out(tensorboard_log + "/episode_reward.csv", std::ios::app);
         for (int e = 0; e < n_envs; ++e) {
             for (int t = 0; t < n_steps; ++t) {
                 if ((*dn)(e * n_steps + t, 0) > .5f) {
+                    writer.write_scalar(total_steps + t, "episode_reward", acc[e]);
                     out << (total_steps + t) << "," << acc[e] << "\n";
                     acc[e] = 0.f;
                 }

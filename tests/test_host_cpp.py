@@ -25,6 +25,28 @@ def test_vecenv_reference_unit_test():
     assert "vecenv_test OK" in r.stdout
 
 
+def test_tensorboard_event_file(tmp_path):
+    """host/tensorboard.hpp (the reference's TensorboardWriter interface, ppo2/tensorboard.hpp:13-52, without TensorFlow):
+    CRC-32C known answers, then an event file read back by TensorBoard's own reader, which checks the masked CRC of every
+    record header and payload."""
+    _build()
+    r = subprocess.run([os.path.join(BIN, "tensorboard_test"), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "tensorboard_test OK" in r.stdout, r.stdout + r.stderr
+    files = [f for f in os.listdir(tmp_path) if f.startswith("PPO2.out.tfevents.")]
+    assert len(files) == 1
+    ea = pytest.importorskip("tensorboard.backend.event_processing.event_accumulator")
+    acc = ea.EventAccumulator(str(tmp_path / files[0]))
+    acc.Reload()
+    assert sorted(acc.Tags()["scalars"]) == ["episode_reward", "other/scalar"]
+    ev = acc.Scalars("episode_reward")
+    assert len(ev) == 150
+    assert [e.step for e in ev] == [20 * i for i in range(150)]
+    assert np.allclose([e.value for e in ev], [np.float32(150.0) / np.float32(i + 1) for i in range(150)], rtol=1e-6)
+    assert [e.wall_time for e in ev] == [1000.0 + i for i in range(150)]
+    o = acc.Scalars("other/scalar")
+    assert len(o) == 1 and o[0].step == 7 and o[0].value == -2.5
+
+
 def _write_graph(tmp_path):
     from ppo_cpp_b200.meta_graph import write_meta_txt
     tensors, _ = load_weights("graph_4_5_init.npz")
@@ -59,6 +81,8 @@ def test_cli_flags_and_csv_line(tmp_path):
     names = sorted(os.listdir(ck))
     assert "t0.pkl.0.json" in names and "t0.pkl.1.json" in names and "t0.pkl.0.data-00000-of-00001" in names
     assert os.path.getsize(ck / "t0.pkl.0.data-00000-of-00001") == 1768  # 442 fp32, as the reference's checkpoint
+    tb = tmp_path / "exp" / "tensorboard" / "t0"
+    assert any(f.startswith("PPO2.out.tfevents.") for f in os.listdir(tb)), os.listdir(tb)  # TensorboardWriter (ppo2.hpp:248)
     # playback of the saved checkpoint (-p): restores weights + normaliser statistics, no training
     r2 = subprocess.run([os.path.join(BIN, "ppo_cpp"), "-g", graph, "-p", str(ck / "t0.pkl.1"), "--duration", "1.5", "--seed", "5"],
                         capture_output=True, text=True, timeout=120)
