@@ -170,8 +170,10 @@ struct ppo_core {
     EpochGraph update_graph;               // GPU-shuffle path: the whole update (permutations + all epochs) as one graph
     std::vector<int> perm_host;
     int* perm_pinned = nullptr;  // [noptepochs][n_batch_global]
-    float* stage = nullptr;      // pinned staging
+    float* stage = nullptr;      // pinned staging for pageable host buffers of the host-env protocol: two slots (step parity)
     size_t stage_floats = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};  // the H2D copies out of a slot have finished
+    unsigned stage_ctr = 0;
     float* scratch = nullptr;    // device scratch for host-pointer calls
     size_t scratch_floats = 0;
 
@@ -252,6 +254,66 @@ static int d2h(ppo_core* c, float* dst, const float* src, size_t n) {
     return PPO_OK;
 }
 
+// Host buffers of the per-step host-env protocol (Runner::run with host physics, runner.hpp:56-157).  Pinned memory is
+// DMA'd in place.  Pageable memory is staged through the core's own pinned double buffer: the caller's memcpy into slot
+// (step & 1) overlaps the DMA still reading slot (step - 1) & 1, and the call returns without waiting for the copy
+// (cudaMemcpyAsync from pageable memory would block until the driver has staged it).
+static bool host_ptr_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+struct StageCopy { float* dst; const float* src; size_t n; };
+static int h2d_staged(ppo_core* c, const StageCopy* cp, int ncp) {
+    bool all_pinned = true;
+    size_t total = 0;
+    for (int i = 0; i < ncp; ++i) {
+        all_pinned = all_pinned && host_ptr_pinned(cp[i].src);
+        total += cp[i].n;
+    }
+    if (all_pinned) {
+        for (int i = 0; i < ncp; ++i) TRY(h2d(c, cp[i].dst, cp[i].src, cp[i].n));
+        return PPO_OK;
+    }
+    if (2 * total > c->stage_floats) {
+        TRY(ensure_stage(c, 2 * total));
+        for (int k = 0; k < 2; ++k)
+            if (!c->stage_ev[k]) CU(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    }
+    const unsigned slot = c->stage_ctr++ & 1u;
+    CU(cudaEventSynchronize(c->stage_ev[slot]));  // copies issued from this slot two steps ago (a fresh event is complete)
+    float* p = c->stage + (size_t)slot * (c->stage_floats / 2);
+    for (int i = 0; i < ncp; ++i) {
+        memcpy(p, cp[i].src, cp[i].n * sizeof(float));
+        TRY(h2d(c, cp[i].dst, p, cp[i].n));
+        p += cp[i].n;
+    }
+    CU(cudaEventRecord(c->stage_ev[slot], c->stream));
+    return PPO_OK;
+}
+// device -> host buffer, complete on return
+static int d2h_staged_sync(ppo_core* c, float* dst, const float* src, size_t n) {
+    if (host_ptr_pinned(dst)) {
+        TRY(d2h(c, dst, src, n));
+        CU(cudaStreamSynchronize(c->stream));
+        return PPO_OK;
+    }
+    if (2 * n > c->stage_floats) {
+        TRY(ensure_stage(c, 2 * n));
+        for (int k = 0; k < 2; ++k)
+            if (!c->stage_ev[k]) CU(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    }
+    // the stream is synchronised below, so every earlier copy out of the staging slots has finished when we reuse one
+    CU(cudaStreamSynchronize(c->stream));
+    TRY(d2h(c, c->stage, src, n));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(dst, c->stage, n * sizeof(float));
+    return PPO_OK;
+}
+
 extern "C" int ppo_core_desc_default(ppo_core_desc* d) {
     if (!d) return fail(PPO_ERR_INVALID, "desc is NULL");
     memset(d, 0, sizeof(*d));
@@ -326,6 +388,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
         if (c->buf[i] && !(c->mbox_mem && is_global_buf(i))) cudaFree(c->buf[i]);
     if (c->perm_pinned) cudaFreeHost(c->perm_pinned);
     if (c->stage) cudaFreeHost(c->stage);
+    for (int k = 0; k < 2; ++k)
+        if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1204,8 +1268,7 @@ extern "C" int ppo_runner_act(ppo_core* c, int t, float* actions_out, ppo_mem me
     if (actions_out) {
         const size_t na = (size_t)c->desc.n_envs * c->d.A;
         if (mem == PPO_HOST) {
-            TRY(d2h(c, actions_out, c->cur_actions, na));
-            CU(cudaStreamSynchronize(c->stream));
+            TRY(d2h_staged_sync(c, actions_out, c->cur_actions, na));
         } else {
             CU(cudaMemcpyAsync(actions_out, c->cur_actions, na * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
         }
@@ -1219,9 +1282,8 @@ extern "C" int ppo_runner_observe(ppo_core* c, int t, const float* raw_obs, cons
     const int N = c->desc.n_envs;
     const float *d_o = raw_obs, *d_r = raw_rew, *d_d = done;
     if (mem == PPO_HOST) {
-        TRY(h2d(c, c->raw_obs, raw_obs, (size_t)N * c->d.O));
-        TRY(h2d(c, c->raw_rew, raw_rew, N));
-        TRY(h2d(c, c->raw_done, done, N));
+        const StageCopy cp[3] = {{c->raw_obs, raw_obs, (size_t)N * c->d.O}, {c->raw_rew, raw_rew, (size_t)N}, {c->raw_done, done, (size_t)N}};
+        TRY(h2d_staged(c, cp, 3));
         d_o = c->raw_obs; d_r = c->raw_rew; d_d = c->raw_done;
     }
     return vecnorm_device(c, d_o, d_r, d_d, c->cur_obs, c->nrew, c->cur_dones, slab(c, B_TRUE_REW, t), slab(c, B_UNNORM_REW, t), true);
