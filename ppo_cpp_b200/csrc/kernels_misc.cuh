@@ -631,10 +631,25 @@ __global__ void advnorm_stats_kernel(const float* __restrict__ ret, const float*
     if (gather) gather += (size_t)blockIdx.y * gather_stride;
     stats += (size_t)blockIdx.y * stats_stride;
     const int* g = gather ? gather + (size_t)k * B : nullptr;
+    // the gathered rows are random 4-byte reads: 8 independent (index -> row) chains in flight per thread
+    constexpr int U = 8;
     double s = 0.0;
-    for (int i = tid; i < B; i += blockDim.x) {
-        const int row = g ? g[i] : (k * B + i);
-        s += (double)__fsub_rn(ret[row], val[row]);
+    {
+        int i = tid;
+        for (; i + (U - 1) * (int)blockDim.x < B; i += U * blockDim.x) {
+            int row[U];
+            float d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) row[u] = g ? __ldg(g + i + u * blockDim.x) : (k * B + i + u * (int)blockDim.x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) d[u] = __fsub_rn(__ldg(ret + row[u]), __ldg(val + row[u]));
+#pragma unroll
+            for (int u = 0; u < U; ++u) s += (double)d[u];
+        }
+        for (; i < B; i += blockDim.x) {
+            const int row = g ? g[i] : (k * B + i);
+            s += (double)__fsub_rn(ret[row], val[row]);
+        }
     }
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
@@ -647,10 +662,23 @@ __global__ void advnorm_stats_kernel(const float* __restrict__ ret, const float*
     __syncthreads();
     const float mean = s_mean;
     double q = 0.0;
-    for (int i = tid; i < B; i += blockDim.x) {
-        const int row = g ? g[i] : (k * B + i);
-        const float d = __fsub_rn(__fsub_rn(ret[row], val[row]), mean);
-        q += (double)__fmul_rn(d, d);
+    {
+        int i = tid;
+        for (; i + (U - 1) * (int)blockDim.x < B; i += U * blockDim.x) {
+            int row[U];
+            float d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) row[u] = g ? __ldg(g + i + u * blockDim.x) : (k * B + i + u * (int)blockDim.x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) d[u] = __fsub_rn(__fsub_rn(__ldg(ret + row[u]), __ldg(val + row[u])), mean);
+#pragma unroll
+            for (int u = 0; u < U; ++u) q += (double)__fmul_rn(d[u], d[u]);
+        }
+        for (; i < B; i += blockDim.x) {
+            const int row = g ? g[i] : (k * B + i);
+            const float d = __fsub_rn(__fsub_rn(ret[row], val[row]), mean);
+            q += (double)__fmul_rn(d, d);
+        }
     }
     q = warp_sum(q);
     __syncthreads();

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) {
                         v[i] = tanhf(ob >= 0 ? v[i] + __ldg(g.P + ob + col0 + i) : v[i]);
-                        gp[(size_t)i * TM] = 1.f - v[i] * v[i];
+                        if (g.gbuf) gp[(size_t)i * TM] = 1.f - v[i] * v[i];  // kept for the backward pass (training only)
                     }
                 } else {  // TanhGrad (GRAPH:20925-23699)
 #pragma unroll
@@ -534,6 +534,78 @@ __global__ void wide_gather_kernel(const TrainArgs a, const WideBufs w) {
         }
         umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
     }
+}
+
+// ---- policy step on the W family (MlpPolicy::step/value/get_deterministic_action, policies.hpp:33-77): the three
+// forward GEMMs above, then one thread per env: Gaussian sample (Philox or given noise), neglogp, value, rollout stores
+__global__ void wide_policy_gather_kernel(const float* __restrict__ obs, int n, float* __restrict__ obs_store, int O, const WideBufs w) {
+    const Geom& G = w.G;
+    const int nj = O / 8 + 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < G.Bpad * nj; e += gridDim.x * blockDim.x) {
+        const int row = e / nj, j = e % nj;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = 8 * j + i;
+            x[i] = 0.f;
+            if (row < n) {
+                if (c < O) {
+                    x[i] = __ldg(obs + (size_t)row * O + c);
+                    if (obs_store) obs_store[(size_t)row * O + c] = x[i];
+                } else if (c == O) x[i] = 1.f;
+            }
+        }
+        umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
+    }
+}
+
+__global__ void wide_policy_head_kernel(const PolicyArgs a, const WideBufs w) {
+    const NetDims& d = a.d;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.n) return;
+    const float* p = a.params;
+    if (a.mode != 2) {
+        const float v = w.MU[w.G.mu_tower + (size_t)row * 64] + __ldg(p + d.off[T_VF_B]);
+        if (a.value) a.value[row] = v;
+        if (a.val_store) a.val_store[row] = v;
+    }
+    const float* mu = w.MU + (size_t)row * 64;
+    if (a.mode == 0) {
+        const float* logstd = p + d.off[T_LOGSTD];
+        const uint32_t step = a.eps ? 0u : *a.step_ctr;
+        float ss = 0.f, sl = 0.f;
+        for (int j0 = 0; j0 < d.A; j0 += 4) {
+            float e4[4];
+            if (!a.eps) normal4(a.seed, a.env_id0 + (uint32_t)row, step, (uint32_t)(j0 >> 2), PPO_TAG_ACTION, e4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + q;
+                if (j < d.A) {
+                    const float ls = __ldg(logstd + j);
+                    const float sd = expf(ls);
+                    const float e = a.eps ? a.eps[(size_t)row * d.A + j] : e4[q];
+                    const float m = mu[j] + __ldg(p + d.off[T_PI_B] + j);
+                    const float act = __fadd_rn(m, __fmul_rn(sd, e));  // GRAPH:5992-6019
+                    const float z = __fdiv_rn(__fsub_rn(act, m), sd);
+                    ss = __fadd_rn(ss, __fmul_rn(z, z));
+                    sl = __fadd_rn(sl, ls);
+                    if (a.action) a.action[(size_t)row * d.A + j] = act;
+                    if (a.act_store) a.act_store[(size_t)row * d.A + j] = act;
+                }
+            }
+        }
+        // 0.5*sum(z^2) + 0.5*log(2pi)*float(A) + sum(logstd)   (GRAPH:6103-6672)
+        const float nl = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, ss), __fmul_rn(PPO_HALF_LOG_2PI, (float)d.A)), sl);
+        if (a.neglogp) a.neglogp[row] = nl;
+        if (a.nlp_store) a.nlp_store[row] = nl;
+    } else if (a.mode == 2) {
+        for (int j = 0; j < d.A; ++j) {
+            const float m = mu[j] + __ldg(p + d.off[T_PI_B] + j);  // mean + 0.0 (GRAPH:6046-6076)
+            if (a.action) a.action[(size_t)row * d.A + j] = m;
+            if (a.act_store) a.act_store[(size_t)row * d.A + j] = m;
+        }
+    }
+    if (a.dones_store) a.dones_store[row] = a.dones_in[row];
 }
 
 // Losses and head gradients per sample (GRAPH:9428-11446, 10213-10400), one thread per sample, one CTA per tile.

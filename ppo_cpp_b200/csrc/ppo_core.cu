@@ -566,7 +566,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
         st = core_alloc(c);
         if (st != PPO_OK) break;
         if (c->wide) {
-            st = ensure_wide(c, (int)((nbg / desc->nminibatches / desc->world_size + wide::TM - 1) / wide::TM));
+            const long per_rank_mb = nbg / desc->nminibatches / desc->world_size;
+            st = ensure_wide(c, (int)((std::max<long>(per_rank_mb, desc->n_envs) + wide::TM - 1) / wide::TM));
             if (st != PPO_OK) break;
         }
         if (c->umma && getenv("PPO_UMMA_PROF")) {
@@ -832,12 +833,15 @@ extern "C" int ppo_core_save_checkpoint_data(ppo_core* c, const char* prefix) {
 }
 
 // ------------------------------------------------------------------------------------------------ policy
+static int launch_wide_policy(ppo_core* c, const PolicyArgs& a);
+constexpr int WIDE_POLICY_MIN = 1024;  // below this the single launch of the tile kernel wins over five launches
 static int launch_policy(ppo_core* c, PolicyArgs& a) {
     a.d = c->d;
     a.params = c->params;
     a.seed = c->desc.seed;
     a.env_id0 = (uint32_t)c->desc.env_offset;
     a.step_ctr = c->step_ctr;
+    if (c->wide && a.n >= WIDE_POLICY_MIN) return launch_wide_policy(c, a);
     if (c->fused) {
         const int ntiles = (a.n + F_TM_POLICY - 1) / F_TM_POLICY;
         const int grid = std::max(1, std::min(ntiles, c->sm_count * 2));
@@ -1518,6 +1522,41 @@ static void launch_wgemm(ppo_core* c, const wide::GemmArgs& g) {
     LAUNCH(c, wide::wgemm_kernel, grid, wide::GEMM_NTH, wide::GEMM_SMEM, g);
 }
 
+// policy step / value / mean for n envs on the W family: weight images, X' image, three forward GEMMs, per-env tail
+static int launch_wide_policy(ppo_core* c, const PolicyArgs& a) {
+    using namespace wide;
+    const int NT = (a.n + TM - 1) / TM;
+    TRY(ensure_wide(c, NT));
+    WideBufs w = c->wb;
+    Geom& G = w.G;
+    G.init(c->d.H1, NT, c->wide_cap);
+    const int H = G.H, nb = G.nb;
+    const NetDims& d = c->d;
+    const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
+    LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w);
+    LAUNCH(c, wide_policy_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a.obs, a.n, a.obs_store, d.O, w);
+    GemmArgs g{};
+    g.P = a.params; g.img_tower = G.act_tower; g.img_tile = G.act_tile; g.img_piece = G.act_piece; g.cap = G.cap; g.H = H;
+    g.mode = MODE_FWD;
+    g.A = w.X; g.a_tower = 0; g.a_tile = G.x_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
+    g.B = w.W0; g.b_tower = G.w0_tower; g.b_piece = G.w0_piece; g.b_kb = 0; g.b_g = 4096; g.b_bytes = 4096;
+    g.n_tile = 128; g.n_blks = H / 128; g.m_tiles = NT; g.ntasks = 2 * NT * g.n_blks;
+    g.epi = EPI_ACT; g.bias_off[0] = g.bias_off[1] = -1; g.img_out = w.H1; g.gbuf = nullptr;
+    launch_wgemm(c, g);
+    g.A = w.H1; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
+    g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
+    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2;
+    launch_wgemm(c, g);
+    g.A = w.H2;
+    g.B = w.WH; g.b_tower = G.wh_tower; g.b_piece = G.wh_piece; g.b_kb = BLK8; g.b_g = 0; g.b_bytes = BLK8;
+    g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT;
+    g.epi = EPI_STORE; g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
+    launch_wgemm(c, g);
+    LAUNCH(c, wide_policy_head_kernel, (a.n + 127) / 128, 128, 0, a, w);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+
 // loss forward + backward of one minibatch shard -> KG gradient slabs (split-K groups of the weight-gradient GEMMs)
 static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     using namespace wide;
@@ -2004,6 +2043,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     }
     if (w == "rollout") return (c->persistent_rollout && fast_path(c)) ? "rollout_persistent_kernel (one cooperative launch per rollout)" : "per-step kernels";
     if (w == "policy") {
+        if (c->wide && c->desc.n_envs >= WIDE_POLICY_MIN) return "wgemm_kernel forward (tcgen05, split-bf16 operand images) + wide_policy_head_kernel";
         if (c->fused) return "policy_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "policy_tile_kernel (fp32 FFMA, generic hidden sizes)";
     }

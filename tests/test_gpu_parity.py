@@ -51,7 +51,8 @@ def test_policy_step_golden(core_mod, wname, forward_kat, init_weights, ckpt_wei
     c.close()
 
 
-@pytest.mark.parametrize("h1,h2,n", [(4, 5, 1), (4, 5, 1000), (8, 8, 129), (64, 64, 4096), (64, 32, 77), (256, 256, 300), (5, 3, 65)])
+@pytest.mark.parametrize("h1,h2,n", [(4, 5, 1), (4, 5, 1000), (8, 8, 129), (64, 64, 4096), (64, 32, 77), (256, 256, 300), (5, 3, 65),
+                                     (256, 256, 3000), (128, 128, 1024)])  # the last two: W-family forward (tcgen05 GEMMs)
 def test_policy_step_vs_oracle(core_mod, h1, h2, n):
     rng = np.random.default_rng(h1 * 1000 + h2 + n)
     p = rand_params(rng, h1, h2)
