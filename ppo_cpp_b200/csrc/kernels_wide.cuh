@@ -14,7 +14,7 @@
 // The same block serves as K-major operand (forward: act x W, backward: dY x W^T) and as MN-major operand
 // (weight gradients: act^T x dY reduced over the samples).
 //
-// Kernels (one minibatch = 11 launches + reduce + Adam, all captured in the update's CUDA graph):
+// Kernels (one minibatch = 9 launches + reduce + Adam, all captured in the update's CUDA graph):
 //   wide_prep_weights_kernel   fp32 parameters -> weight images (W0' with the bias as an extra input row, W1, heads)
 //   wide_gather_kernel         minibatch rows of the rollout buffer -> X' image (obs | 1)
 //   wgemm_kernel               persistent, warp-specialised (bulk-copy producer / MMA issuer / 8 epilogue warps),
@@ -23,7 +23,7 @@
 //       mode BWD   C = A(K-major image) x W^T(K-major view)     dH2, dH1
 //       mode DW    slab[kgroup] = A^T(MN-major) x B(MN-major) over a range of samples (split-K): dW1, dWhead, dW0'
 //       epilogues: fp32 result | H = tanh(acc + b) -> image | dP = acc * (1 - H^2) -> image + column sums (bias gradient)
-//   wide_loss_kernel           policy / value losses per sample, dL/dmu, dL/dlogstd terms, dL/dv -> dY image
+//                  | heads -> policy / value losses per sample, dL/dmu, dL/dlogstd terms, dL/dv -> dY image + per-warp sums
 //   wide_fold_kernel           per-tile column / loss sums -> slab 0 (zeros in the other slabs)
 // The slabs then go through the same reduce (+ cross-GPU exchange) + global-norm clip + Adam kernel as every family.
 #pragma once
@@ -74,7 +74,7 @@ struct Geom {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_DW = 2 };
 enum { DW_W1 = 0, DW_HEAD = 1, DW_W0 = 2 };
-enum { EPI_STORE = 0, EPI_ACT = 1, EPI_DACT = 2 };  // fp32 result | tanh(acc + b) -> image | acc * (1 - H^2) -> image (+ column sums)
+enum { EPI_STORE = 0, EPI_ACT = 1, EPI_DACT = 2, EPI_LOSS = 3 };  // fp32 result | tanh(acc + b) -> image | acc * (1 - H^2) -> image (+ column sums) | heads -> losses -> dY image
 
 struct DwProb {
     const uint8_t* A; size_t a_tower, a_tile, a_piece;  // M side: image whose features become the rows of the result
@@ -98,6 +98,9 @@ struct GemmArgs {
     size_t img_tower, img_tile, img_piece;
     float* colsum; int cap;                   // EPI_DACT: [tower][tile * 4 + lane quarter][H] partial column sums, or NULL
     float* gbuf;                              // 1 - H^2 as fp32, [tower][tile][column][128 rows]: written by EPI_ACT, read by EPI_DACT
+    TrainArgs ta;                             // EPI_LOSS: the minibatch (gather list, rollout buffers, advantage statistics)
+    uint8_t* dY; size_t dy_tower, dy_tile;    // EPI_LOSS: head gradients image [tower][tile][piece][16 KB]
+    float* colloss;                           // EPI_LOSS: [tile * 4 + lane quarter][COLPART] per-warp sums
     // DW
     DwProb dw[3];
     int n_dw, KG, HT;     // split-K groups, half tiles (64 samples) in the minibatch
@@ -323,7 +326,117 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
             const Task k = decode_task(g, t);
             const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
             float v[64];
+            if (!dwm && g.epi == EPI_LOSS && half == 1) {  // the heads fit in the first 32 columns: these warps only release the buffer
+                mbar_wait_b(BAR_ACCFULL(ab), aph);
+                umma::tc_fence_after();
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_ACCEMPTY(ab));
+                continue;
+            }
             if (!dwm && g.epi != EPI_STORE) {
+                uint8_t* out_base;
+                size_t out_piece;
+                if (g.epi == EPI_LOSS) {
+                    // ---- losses and head gradients of this warp's 32 samples (GRAPH:9428-11446, 10213-10400): the accumulator
+                    // holds mu - b (pi tower, columns 0..A-1) or v - b (V tower, column 0); the sample's inputs are requested
+                    // before the accumulator is waited for
+                    constexpr int A = 18;
+                    const TrainArgs& a = g.ta;
+                    const NetDims& d = a.d;
+                    const float* P = a.params;
+                    const int grow = k.m * TM + row;
+                    const bool valid = grow < a.count;
+                    float ret = 0.f, oldv = 0.f, oldn = 0.f, adv = 0.f, act[A];
+#pragma unroll
+                    for (int j = 0; j < A; ++j) act[j] = 0.f;
+                    if (valid) {
+                        const long src = a.gather ? (long)__ldg(a.gather + a.slot0 + grow) : (long)(a.slot0 + grow);
+                        ret = __ldg(a.ret + src);
+                        oldv = __ldg(a.val + src);
+                        if (k.tower == 0) {
+                            oldn = __ldg(a.nlp + src);
+#pragma unroll
+                            for (int j = 0; j < A; ++j) act[j] = __ldg(a.act + src * A + j);
+                            if (a.adv_direct) adv = __ldg(a.adv_direct + a.slot0 + grow);
+                            else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
+                                const float2 st = __ldg(a.mbstats);
+                                adv = __fdiv_rn(__fsub_rn(__fsub_rn(ret, oldv), st.x), st.y);
+                            }
+                        }
+                    }
+                    mbar_wait_b(BAR_ACCFULL(ab), aph);
+                    umma::tc_fence_after();
+                    float mu[32];
+                    umma::tmem_ld32_sum(tlane + ab * 256u, tlane + ab * 256u + 128u, mu);
+                    umma::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR_ACCEMPTY(ab));
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+                    float* cl = g.colloss + ((size_t)k.m * 4 + q) * COLPART;
+                    if (k.tower == 0) {
+                        float l_pg = 0.f, l_kl = 0.f, l_cf = 0.f;
+                        if (valid) {
+                            const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+                            float z[A], isd[A];
+                            float ss = 0.f, sl = 0.f;
+#pragma unroll
+                            for (int j = 0; j < A; ++j) {
+                                const float ls = __ldg(P + d.off[T_LOGSTD] + j);
+                                isd[j] = 1.f / expf(ls);
+                                z[j] = (act[j] - (mu[j] + __ldg(P + d.off[T_PI_B] + j))) * isd[j];
+                                ss += z[j] * z[j];
+                                sl += ls;
+                            }
+                            const float nlp = (0.5f * ss + PPO_HALF_LOG_2PI * (float)A) + sl;
+                            const float ratio = expf(oldn - nlp);
+                            const float pg1 = -adv * ratio;
+                            const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);  // clip_by_value = max(min(x,hi),lo)
+                            const bool take1 = pg1 >= pg2;                          // ties -> unclipped branch
+                            l_pg = take1 ? pg1 : pg2;
+                            const float dn = nlp - oldn;
+                            l_kl = dn * dn;
+                            l_cf = (fabsf(ratio - 1.f) > a.cliprange) ? 1.f : 0.f;
+                            const float g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
+#pragma unroll
+                            for (int j = 0; j < A; ++j) {
+                                v[j] = g_nlp * (-z[j] * isd[j]);        // dL/dmu_j
+                                v[32 + j] = g_nlp * (1.f - z[j] * z[j]);  // dL/dlogstd_j term
+                            }
+                        }
+                        float w32[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) w32[i] = v[i];
+                        const float s0 = colsum32(w32, lane);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) w32[i] = v[32 + i];
+                        const float s1 = colsum32(w32, lane);
+                        if (lane < A) {
+                            cl[CP_DBPI + lane] = s0;
+                            cl[CP_DLS + lane] = s1;
+                        }
+                        const float t1 = warp_sum(l_pg), t3 = warp_sum(l_kl), t4 = warp_sum(l_cf);
+                        if (lane == 0) { cl[CP_PG] = t1; cl[CP_KL] = t3; cl[CP_CLIP] = t4; }
+                    } else {
+                        float dv = 0.f, l_vf = 0.f;
+                        if (valid) {
+                            const float vv = mu[0] + __ldg(P + d.off[T_VF_B]);
+                            const float dvo = vv - oldv;
+                            const float vc = oldv + fmaxf(fminf(dvo, a.cliprange), -a.cliprange);
+                            const float l1 = (vv - ret) * (vv - ret), l2 = (vc - ret) * (vc - ret);
+                            const bool tk = l1 >= l2;  // ties -> unclipped branch
+                            l_vf = tk ? l1 : l2;
+                            const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
+                            dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (vv - ret) : (inr ? 2.f * (vc - ret) : 0.f));
+                        }
+                        v[0] = dv;
+                        const float t0 = warp_sum(dv), t2 = warp_sum(l_vf);
+                        if (lane == 0) { cl[CP_DBV] = t0; cl[CP_VF] = t2; }
+                    }
+                    out_base = g.dY + k.tower * g.dy_tower + (size_t)k.m * g.dy_tile + (size_t)q * EPI_STAGE;
+                    out_piece = BLK16;
+                } else {
                 // ---- H = tanh(acc + b) or dP = acc * (1 - H^2), 64 columns = column block cb of the layer
                 const int col0 = k.n * g.n_tile + 64 * half;
                 const size_t boff = k.tower * g.img_tower + (size_t)k.m * g.img_tile + (size_t)(col0 >> 6) * BLK16 + (size_t)q * EPI_STAGE;
@@ -362,6 +475,9 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
                         }
                     }
                 }
+                out_base = g.img_out + boff;
+                out_piece = g.img_piece;
+                }
                 // three bf16 pieces, one after the other through the staging slice: piece p = bf16(x), x -= piece
 #pragma unroll 1
                 for (int p = 0; p < 3; ++p) {
@@ -386,7 +502,7 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
                     umma::fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.img_out + boff + (size_t)p * g.img_piece),
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_base + (size_t)p * out_piece),
                                      "r"(stg_u32), "r"(EPI_STAGE)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -460,7 +576,7 @@ struct WideBufs {
     uint8_t *X, *H1, *H2, *dP2, *dP1, *dY;  // images
     uint8_t *W0, *W1, *WH;                  // weight images
     float *G1, *G2, *MU;                    // G: 1 - H^2 per layer, fp32 [2][cap][H][128]; MU: fp32 head results [2][cap * 128 x 64]
-    float *colloss;                         // [NT][COLPART]
+    float *colloss;                         // [cap * 4][COLPART]: per (tile, lane quarter) sums of the loss stage
     float *colb1;                           // [2][cap * 4][H]: per (tile, lane quarter) column sums of dP2
 };
 
@@ -608,98 +724,6 @@ __global__ void wide_policy_head_kernel(const PolicyArgs a, const WideBufs w) {
     if (a.dones_store) a.dones_store[row] = a.dones_in[row];
 }
 
-// Losses and head gradients per sample (GRAPH:9428-11446, 10213-10400), one thread per sample, one CTA per tile.
-// MU buffer: pi rows hold mu - b (columns 0..A-1), V rows hold v - b (column 0).
-template <int A>
-__global__ void __launch_bounds__(TM) wide_loss_kernel(const TrainArgs a, const WideBufs w) {
-    __shared__ float s_red[4][COLPART];
-    const Geom& G = w.G;
-    const NetDims& d = a.d;
-    const int tile = blockIdx.x, r = threadIdx.x, row = tile * TM + r, lane = r & 31, wp = r >> 5;
-    const bool valid = row < a.count;
-    const float* P = a.params;
-    float dmu[32], dls[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) dmu[j] = dls[j] = 0.f;
-    float l_pg = 0.f, l_vf = 0.f, l_kl = 0.f, l_cf = 0.f, dv = 0.f;
-    if (valid) {
-        const long src = a.gather ? (long)__ldg(a.gather + a.slot0 + row) : (long)(a.slot0 + row);
-        const float ret = __ldg(a.ret + src), oldv = __ldg(a.val + src), oldn = __ldg(a.nlp + src);
-        float adv;
-        if (a.adv_direct) adv = __ldg(a.adv_direct + a.slot0 + row);
-        else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
-            const float2 st = __ldg(a.mbstats);
-            adv = __fdiv_rn(__fsub_rn(__fsub_rn(ret, oldv), st.x), st.y);
-        }
-        const float* mu = w.MU + (size_t)row * 64;
-        const float* act = a.act + src * A;
-        const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
-        float z[A], isd[A];
-        float ss = 0.f, sl = 0.f;
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            const float ls = __ldg(P + d.off[T_LOGSTD] + j);
-            isd[j] = 1.f / expf(ls);
-            z[j] = (__ldg(act + j) - (mu[j] + __ldg(P + d.off[T_PI_B] + j))) * isd[j];
-            ss += z[j] * z[j];
-            sl += ls;
-        }
-        const float nlp = (0.5f * ss + PPO_HALF_LOG_2PI * (float)A) + sl;
-        const float ratio = expf(oldn - nlp);
-        const float pg1 = -adv * ratio;
-        const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);  // clip_by_value = max(min(x,hi),lo)
-        const bool take1 = pg1 >= pg2;                          // ties -> unclipped branch
-        l_pg = take1 ? pg1 : pg2;
-        const float dn = nlp - oldn;
-        l_kl = dn * dn;
-        l_cf = (fabsf(ratio - 1.f) > a.cliprange) ? 1.f : 0.f;
-        const float g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            dmu[j] = g_nlp * (-z[j] * isd[j]);
-            dls[j] = g_nlp * (1.f - z[j] * z[j]);
-        }
-        // value head
-        const float v = w.MU[G.mu_tower + (size_t)row * 64] + __ldg(P + d.off[T_VF_B]);
-        const float dvo = v - oldv;
-        const float vc = oldv + fmaxf(fminf(dvo, a.cliprange), -a.cliprange);
-        const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
-        const bool tk = l1 >= l2;  // ties -> unclipped branch
-        l_vf = tk ? l1 : l2;
-        const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
-        dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (v - ret) : (inr ? 2.f * (vc - ret) : 0.f));
-    }
-    // dY images: pi = [dMU (32 columns) | dLS (32 columns)], V = [dv | 0 ...]
-    uint8_t* ypi = w.dY + (size_t)tile * G.dy_tile;
-    uint8_t* yv = w.dY + G.dy_tower + (size_t)tile * G.dy_tile;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        umma::store_chunk(ypi, BLK16, chunk_off(r, j), dmu + 8 * j);
-        umma::store_chunk(ypi, BLK16, chunk_off(r, 4 + j), dls + 8 * j);
-    }
-    {
-        float x[8] = {dv, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        umma::store_chunk(yv, BLK16, chunk_off(r, 0), x);
-    }
-    // per-tile sums: bias / logstd gradients and the loss terms
-#pragma unroll
-    for (int j = 0; j < A; ++j) {
-        const float s0 = warp_sum(dmu[j]), s1 = warp_sum(dls[j]);
-        if (lane == 0) {
-            s_red[wp][CP_DBPI + j] = s0;
-            s_red[wp][CP_DLS + j] = s1;
-        }
-    }
-    {
-        const float t0 = warp_sum(dv), t1 = warp_sum(l_pg), t2 = warp_sum(l_vf), t3 = warp_sum(l_kl), t4 = warp_sum(l_cf);
-        if (lane == 0) {
-            s_red[wp][CP_DBV] = t0; s_red[wp][CP_PG] = t1; s_red[wp][CP_VF] = t2; s_red[wp][CP_KL] = t3; s_red[wp][CP_CLIP] = t4;
-        }
-    }
-    __syncthreads();
-    if (r <= CP_CLIP) w.colloss[(size_t)tile * COLPART + r] = ((s_red[0][r] + s_red[1][r]) + s_red[2][r]) + s_red[3][r];
-}
-
 // per-tile sums -> slab 0; the same columns of the other slabs are zero (the GEMMs own every weight column of every slab).
 // One warp per output column: lanes stride over the tiles, fixed-order butterfly in double.
 __global__ void wide_fold_kernel(const TrainArgs a, const WideBufs w, int nslabs) {
@@ -726,7 +750,7 @@ __global__ void wide_fold_kernel(const TrainArgs a, const WideBufs w, int nslabs
             const int sc = l == L_PG ? CP_PG : l == L_VF ? CP_VF : l == L_KL ? CP_KL : l == L_CLIP ? CP_CLIP : -1;
             if (sc >= 0) { src = w.colloss + sc; stride = COLPART; }
         }
-        const int nsrc = e < 2 * H ? 4 * G.NT : G.NT;
+        const int nsrc = 4 * G.NT;  // one entry per (tile, TMEM lane quarter = epilogue warp)
         if (src)
             for (int i = lane; i < nsrc; i += 32) t += (double)src[(size_t)i * stride];
         t = warp_sum(t);

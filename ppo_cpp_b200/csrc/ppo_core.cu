@@ -1498,7 +1498,7 @@ static int ensure_wide(ppo_core* c, int tiles) {
     const size_t R = (size_t)tiles * wide::TM, H = (size_t)G.H;
     const size_t sizes[] = {(size_t)tiles * G.x_tile, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.dy_tower,
                             2 * G.w0_tower, 2 * G.w1_tower, 2 * G.wh_tower, 2 * R * H * sizeof(float), 2 * R * 64 * sizeof(float),
-                            (size_t)tiles * wide::COLPART * sizeof(float), 2 * 4 * (size_t)tiles * H * sizeof(float), 2 * R * H * sizeof(float)};
+                            4 * (size_t)tiles * wide::COLPART * sizeof(float), 2 * 4 * (size_t)tiles * H * sizeof(float), 2 * R * H * sizeof(float)};
     size_t off[14], total = 0;
     for (int i = 0; i < 14; ++i) {
         off[i] = total;
@@ -1586,13 +1586,12 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
     g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2; g.gbuf = w.G2;
     launch_wgemm(c, g);
-    // ---- heads: [mu | v] = H2 WH (fp32 result), then the losses and dY
+    // ---- heads: [mu | v] = H2 WH, losses and head gradients (dY image) in the epilogue
     g.A = w.H2;
     g.B = w.WH; g.b_tower = G.wh_tower; g.b_piece = G.wh_piece; g.b_kb = BLK8; g.b_g = 0; g.b_bytes = BLK8;
     g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT;
-    g.epi = EPI_STORE; g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
+    g.epi = EPI_LOSS; g.ta = a; g.dY = w.dY; g.dy_tower = G.dy_tower; g.dy_tile = G.dy_tile; g.colloss = w.colloss;
     launch_wgemm(c, g);
-    LAUNCH(c, (wide_loss_kernel<18>), NT, TM, 0, a, w);
     // ---- dP2 = (dY WH^T) (1 - H2^2), column sums -> db1
     g.mode = MODE_BWD;
     g.A = w.dY; g.a_tower = G.dy_tower; g.a_tile = G.dy_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
