@@ -615,7 +615,8 @@ def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps
     assert np.array_equal(a["b1"], b["b1"]) and np.array_equal(a["b2"], b["b2"])
 
 
-@pytest.mark.parametrize("n_envs,n_steps,epochs,seed", [(1, 2, 1, 1), (3, 7, 4, 42), (16, 64, 3, 7), (257, 33, 2, 123456), (4096, 64, 10, 42)])
+@pytest.mark.parametrize("n_envs,n_steps,epochs,seed", [(1, 2, 1, 1), (3, 7, 4, 42), (16, 64, 3, 7), (257, 33, 2, 123456), (4096, 64, 10, 42),
+                                                         (16384, 64, 4, 9)])  # the last one: 4 x 1 M entries (the global batch of a multi-GPU run)
 def test_device_random_shuffle_bit_exact(core_mod, n_envs, n_steps, epochs, seed):
     """The permutations built on the device (parallel glibc rand() stream by polynomial jump-ahead + parallel resolution
     of the swap chain, kernels_shuffle.cuh) must equal std::srand(seed) + std::random_shuffle bit for bit: every epoch of
