@@ -308,17 +308,16 @@ def run_ours(args):
     if args.e2e:
         rng = np.random.default_rng(rank)
         pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
-        raw_obs, raw_rew, raw_done, act = pin((n_steps, n_envs, 18)), pin((n_steps, n_envs)), pin((n_steps, n_envs)), pin((n_envs, 18))
+        raw_obs, raw_rew, raw_done, act = pin((n_steps, n_envs, 18)), pin((n_steps, n_envs)), pin((n_steps, n_envs)), pin((n_steps, n_envs, 18))
         raw_obs[:] = rng.standard_normal(raw_obs.shape)
         raw_rew[:] = rng.standard_normal(raw_rew.shape)
         raw_done[:] = rng.random(raw_done.shape) < 1 / 334
         losses = np.zeros(5, np.float32)
 
         def host_update():
-            for t_ in range(n_steps):
-                c.runner_act(t_, act)                                    # D2H: actions for the host env
-                c.runner_observe(t_, raw_obs[t_], raw_rew[t_], raw_done[t_])  # H2D: what the host env returned
-            c.runner_finish()
+            # the loop of Runner::run in C (ppo_runner_rollout_replay): per env step D2H of the actions for the host env,
+            # H2D of what the host env returned (here: the next rows of the recorded arrays), then bootstrap + GAE
+            c.runner_rollout_replay(raw_obs, raw_rew, raw_done, act)
             return c.train_update(LR, CLIPRANGE, want_losses=True)      # D2H: the update's mean losses
 
         c.runner_reset(raw_obs[0])
@@ -337,7 +336,7 @@ def run_ours(args):
         ce = c.counters()
         e2e = {"value": n_batch_global * k_e2e / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": ce["h2d_bytes"] // k_e2e,
                "d2h_bytes_per_step": ce["d2h_bytes"] // k_e2e, "steps": k_e2e, "ms_per_step": float(tt[0]) / k_e2e * 1e3,
-               "path": "ppo_runner_act/observe/finish + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
+               "path": "ppo_runner_rollout_replay (per env step: act -> D2H actions, H2D obs/rew/done -> observe) + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
                "final_losses": [float(x) for x in losses]}
 
     cpu_baseline = None

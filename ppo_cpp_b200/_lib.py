@@ -103,6 +103,8 @@ def load():
         "ppo_runner_act": ([core, C.c_int, fp, C.c_int], C.c_int),
         "ppo_runner_observe": ([core, C.c_int, fp, fp, fp, C.c_int], C.c_int),
         "ppo_runner_finish": ([core], C.c_int),
+        "ppo_runner_rollout_host": ([core, C.c_void_p, C.c_void_p, fp], C.c_int),
+        "ppo_runner_rollout_replay": ([core, fp, fp, fp, fp], C.c_int),
         "ppo_synth_env_reset": ([core], C.c_int),
         "ppo_rollout_synthetic": ([core], C.c_int),
         "ppo_rollout_get": ([core, C.c_char_p, fp, C.c_size_t], C.c_int),

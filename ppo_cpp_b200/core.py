@@ -245,6 +245,12 @@ class PPOCore:
     def runner_finish(self):
         _check(self.lib, self.lib.ppo_runner_finish(self._h))
 
+    def runner_rollout_replay(self, raw_obs, raw_rew, done, actions_out: Optional[np.ndarray] = None):
+        """The act/observe loop of a whole rollout in one C call, the host env being a recorded trajectory."""
+        raw, rew, dn = _f32(raw_obs), _f32(raw_rew), _f32(done)
+        _check(self.lib, self.lib.ppo_runner_rollout_replay(self._h, _addr(raw), _addr(rew), _addr(dn),
+                                                            _addr(actions_out) if actions_out is not None else None))
+
     def synth_env_reset(self):
         _check(self.lib, self.lib.ppo_synth_env_reset(self._h))
 

@@ -1303,6 +1303,49 @@ extern "C" int ppo_runner_finish(ppo_core* c) {
                       c->desc.n_steps, c->desc.n_envs, c->desc.gamma, c->desc.lam, nullptr, slab(c, B_RETURNS, 0));
 }
 
+extern "C" int ppo_runner_rollout_host(ppo_core* c, ppo_env_step_fn step, void* user, float* actions) {
+    if (!c || !step || !actions) return fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: NULL argument");
+    for (int t = 0; t < c->desc.n_steps; ++t) {
+        TRY(ppo_runner_act(c, t, actions, PPO_HOST));
+        const float *o = nullptr, *r = nullptr, *d = nullptr;
+        if (step(user, t, actions, &o, &r, &d) != 0) return fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: the env aborted at step %d", t);
+        TRY(ppo_runner_observe(c, t, o, r, d, PPO_HOST));
+    }
+    return ppo_runner_finish(c);
+}
+
+namespace {
+struct ReplayEnv {
+    const float *obs, *rew, *done;
+    float* actions_out;
+    size_t no, n, na;
+};
+int replay_env_step(void* user, int t, const float* actions, const float** raw_obs, const float** raw_rew, const float** done) {
+    ReplayEnv* e = static_cast<ReplayEnv*>(user);
+    if (e->actions_out && actions != e->actions_out + (size_t)t * e->na) memcpy(e->actions_out + (size_t)t * e->na, actions, e->na * sizeof(float));
+    *raw_obs = e->obs + (size_t)t * e->no;
+    *raw_rew = e->rew + (size_t)t * e->n;
+    *done = e->done + (size_t)t * e->n;
+    return 0;
+}
+}  // namespace
+
+extern "C" int ppo_runner_rollout_replay(ppo_core* c, const float* raw_obs, const float* raw_rew, const float* done, float* actions_out) {
+    if (!c || !raw_obs || !raw_rew || !done) return fail(PPO_ERR_INVALID, "ppo_runner_rollout_replay: NULL argument");
+    const size_t N = (size_t)c->desc.n_envs;
+    ReplayEnv env{raw_obs, raw_rew, done, actions_out, N * c->d.O, N, N * c->d.A};
+    if (actions_out) {  // every step's actions land directly in their row of actions_out
+        for (int t = 0; t < c->desc.n_steps; ++t) {
+            float* a = actions_out + (size_t)t * env.na;
+            TRY(ppo_runner_act(c, t, a, PPO_HOST));
+            TRY(ppo_runner_observe(c, t, raw_obs + (size_t)t * env.no, raw_rew + (size_t)t * N, done + (size_t)t * N, PPO_HOST));
+        }
+        return ppo_runner_finish(c);
+    }
+    std::vector<float> scratch(env.na);
+    return ppo_runner_rollout_host(c, replay_env_step, &env, scratch.data());
+}
+
 extern "C" int ppo_synth_env_reset(ppo_core* c) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     CU(cudaSetDevice(c->desc.device));

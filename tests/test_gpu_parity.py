@@ -693,6 +693,40 @@ def test_runner_host_env_protocol_equals_device_env(core_mod, ckpt_weights):
     c2.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_runner_rollout_replay_equals_stepwise_protocol(core_mod, ckpt_weights, pinned):
+    """ppo_runner_rollout_replay (the act/observe loop of Runner::run as one C call, host env = a recorded trajectory)
+    against the same trajectory fed step by step; pageable buffers go through the core's pinned double buffer, pinned
+    buffers are DMA'd in place.  Same kernels in the same order: bit-identical rollout buffers and actions."""
+    _, flat = ckpt_weights
+    n_envs, n_steps, seed = 33, 20, 5
+    rng = np.random.default_rng(3)
+    shape = [(n_steps, n_envs, 18), (n_steps, n_envs), (n_steps, n_envs), (n_steps, n_envs, 18)]
+    if pinned:
+        import torch
+        raw, rew, done, acts = (torch.empty(s_, dtype=torch.float32, pin_memory=True).numpy() for s_ in shape)
+    else:
+        raw, rew, done, acts = (np.empty(s_, np.float32) for s_ in shape)
+    raw[:] = 2.0 + rng.standard_normal(shape[0])
+    rew[:] = rng.standard_normal(shape[1])
+    done[:] = rng.random(shape[2]) < 0.1
+    a = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=seed)
+    b = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=seed)
+    a.runner_reset(raw[0])
+    b.runner_reset(raw[0])
+    want_acts = []
+    for t in range(n_steps):
+        want_acts.append(a.runner_act(t).copy())
+        a.runner_observe(t, raw[t], rew[t], done[t])
+    a.runner_finish()
+    b.runner_rollout_replay(raw, rew, done, acts)
+    assert np.array_equal(acts, np.stack(want_acts))
+    for n in ("obs", "actions", "values", "neglogpacs", "returns", "dones", "true_rewards", "unnormalized_rewards"):
+        assert np.array_equal(a.rollout_get(n), b.rollout_get(n)), n
+    a.close()
+    b.close()
+
+
 def test_rollout_mock_env_c1(core_mod, init_weights, kat):
     """Config C1: EnvMock (constant obs/reward 1, done every 300th step) driven through the host protocol.
     Rewards, dones and the done-lag of Runner::run are exact; the normalised observation is cancellation noise
