@@ -167,7 +167,13 @@ struct ppo_core {
     uint32_t* win_pinned = nullptr;
     const int* cur_gather = nullptr;       // gather list / advantage statistics of the epoch being trained
     const float2* cur_mbstats = nullptr;
-    EpochGraph update_graph;               // GPU-shuffle path: the whole update (permutations + all epochs) as one graph
+    EpochGraph update_graph;               // GPU-shuffle path: advantage statistics + all epochs of an update as one graph
+    EpochGraph shuffle_graph;              // ... and the permutations of all its epochs as another: they do not depend on the
+                                           // rollout, so the next update's are built on stream2 while the rollout runs
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_shuf = nullptr;
+    bool shuffle_prefetched = false;       // sh_perm / sh_gather already hold the NEXT update's permutations (ev_shuf)
+    uint32_t* rng_win_saved = nullptr;     // generator window before the prefetched draws (to undo an unused prefetch)
     std::vector<int> perm_host;
     int* perm_pinned = nullptr;  // [noptepochs][n_batch_global]
     float* stage = nullptr;      // pinned staging for pageable host buffers of the host-env protocol: two slots (step parity)
@@ -374,6 +380,12 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->rollout_graph.exec) cudaGraphExecDestroy(c->rollout_graph.exec);
     if (c->update_graph.exec) cudaGraphExecDestroy(c->update_graph.exec);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->shuffle_graph.exec) cudaGraphExecDestroy(c->shuffle_graph.exec);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_shuf) cudaEventDestroy(c->ev_shuf);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->rng_win_saved) cudaFree(c->rng_win_saved);
     if (c->win_pinned) cudaFreeHost(c->win_pinned);
     void* dev_ptrs[] = {c->params, c->adam_m, c->adam_v, c->bpow, c->st.obs_mean, c->st.obs_var, c->st.obs_count,
                         c->st.ret_mean, c->st.ret_var, c->st.ret_count, c->ret, c->mom_partial, c->moments, c->ticket,
@@ -395,6 +407,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
 }
 
 static int ensure_wide(ppo_core* c, int tiles);
+static int prefetch_shuffle(ppo_core* c);
 static int core_alloc(ppo_core* c) {
     const ppo_core_desc& D = c->desc;
     const NetDims& d = c->d;
@@ -1268,6 +1281,7 @@ static int runner_act_device(ppo_core* c, int t) {
 extern "C" int ppo_runner_act(ppo_core* c, int t, float* actions_out, ppo_mem mem) {
     if (!c || t < 0 || t >= c->desc.n_steps) return fail(PPO_ERR_INVALID, "ppo_runner_act: step %d out of range", t);
     CU(cudaSetDevice(c->desc.device));
+    if (t == 0) TRY(prefetch_shuffle(c));
     TRY(runner_act_device(c, t));
     if (actions_out) {
         const size_t na = (size_t)c->desc.n_envs * c->d.A;
@@ -1368,6 +1382,7 @@ static int rollout_synthetic_enqueue(ppo_core* c) {
 extern "C" int ppo_rollout_synthetic(ppo_core* c) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     CU(cudaSetDevice(c->desc.device));
+    TRY(prefetch_shuffle(c));  // the next update's permutations, on stream2, while this rollout runs
     if (c->persistent_rollout && fast_path(c)) {
         const ppo_core_desc& D = c->desc;
         RolloutArgs r{};
@@ -1479,6 +1494,11 @@ extern "C" int ppo_rollout_set(ppo_core* c, const char* name, const float* in, s
 // ------------------------------------------------------------------------------------------------ update
 extern "C" int ppo_shuffle_seed(ppo_core* c, unsigned seed) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    if (c->shuffle_prefetched) {  // permutations drawn from the old stream: discard (the new window is uploaded by the next update)
+        cudaSetDevice(c->desc.device);
+        cudaStreamSynchronize(c->stream2);
+        c->shuffle_prefetched = false;
+    }
     c->rng.srand(seed);
     c->rng_on_device = false;  // the host object is authoritative again; the next device shuffle uploads its window
     return PPO_OK;
@@ -1760,8 +1780,8 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
 // (kernels_shuffle.cuh), then the epochs back to back.  Nothing here waits for the host.
 static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int loss_row);
 static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e);
-static int enqueue_update_gpu_shuffle(ppo_core* c, float lr, float cliprange) {
-    const int n = c->n_batch_global, E = c->desc.noptepochs, M = c->desc.nminibatches;
+static int enqueue_shuffle(ppo_core* c) {
+    const int n = c->n_batch_global, E = c->desc.noptepochs;
     const long long total = (long long)E * (n - 1);
     CU(cudaMemsetAsync(c->sh_cnt, 0, sizeof(int) * (size_t)E * (n + 1), c->stream));
     const int draw_threads = (int)((total + shuf::L - 1) / shuf::L);
@@ -1779,6 +1799,11 @@ static int enqueue_update_gpu_shuffle(ppo_core* c, float lr, float cliprange) {
     for (int e = 0; e < E; ++e)
         LAUNCH(c, shuf::shuffle_compose_kernel, (n + 255) / 256, 256, 0, e ? c->sh_perm + (size_t)(e - 1) * n : (const int*)nullptr,
                c->sh_sigma + (size_t)e * n, n, c->desc.n_steps, c->desc.n_envs, c->sh_perm + (size_t)e * n, c->sh_gather + (size_t)e * n);
+    CU(cudaGetLastError());
+    return PPO_OK;
+}
+static int enqueue_epochs(ppo_core* c, float lr, float cliprange) {
+    const int n = c->n_batch_global, E = c->desc.noptepochs, M = c->desc.nminibatches;
     LAUNCH(c, advnorm_stats_kernel, dim3(M, E), 512, 0, c->buf[B_RETURNS], c->buf[B_VALUES], c->sh_gather, c->B_global, c->sh_mbstats, (size_t)n, M);
     CU(cudaGetLastError());
     for (int e = 0; e < E; ++e) {
@@ -1789,6 +1814,72 @@ static int enqueue_update_gpu_shuffle(ppo_core* c, float lr, float cliprange) {
             for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
     }
     c->perm_set = true;  // cur_gather / cur_mbstats describe the last epoch
+    return PPO_OK;
+}
+
+// capture `enqueue` (launches on c->stream) once and replay it on `on`; lr / cliprange / beta-power slot are baked in
+template <class F>
+static int replay_graph(ppo_core* c, ppo_core::EpochGraph& g, cudaStream_t on, float lr, float cliprange, F enqueue) {
+    if (!g.exec || g.lr != lr || g.cliprange != cliprange || g.bpow_slot != c->bpow_slot) {
+        if (g.exec) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        const int slot0 = c->bpow_slot;
+        const uint64_t k0 = c->ctr.kernel_launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int st = enqueue();
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        g.kernels = c->ctr.kernel_launches - k0;
+        c->ctr.kernel_launches = k0;  // nothing ran yet; the replay accounts for them
+        g.flip = c->bpow_slot ^ slot0;
+        c->bpow_slot = slot0;
+        if (st != PPO_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return st;
+        }
+        if (ce != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        g.lr = lr; g.cliprange = cliprange; g.bpow_slot = slot0;
+    }
+    CU(cudaGraphLaunch(g.exec, on));
+    c->ctr.graph_launches++;
+    c->ctr.kernel_launches += g.kernels;
+    c->bpow_slot ^= g.flip;
+    return PPO_OK;
+}
+
+// The permutations of an update depend only on the rand() stream, not on the rollout: build the next update's on a
+// second stream while the rollout runs (called when a rollout starts).  Undone by drop_shuffle_prefetch.
+static int prefetch_shuffle(ppo_core* c) {
+    if (getenv("PPO_DISABLE_SHUFFLE_PREFETCH") != nullptr || c->shuffle_prefetched || !c->rng_on_device || !(c->gpu_shuffle && fast_path(c)) || !update_graph_ok(c) || c->desc.noptepochs < 1)
+        return PPO_OK;
+    if (!c->stream2) {
+        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_shuf, cudaEventDisableTiming));
+        CU(cudaMalloc(&c->rng_win_saved, 31 * sizeof(uint32_t)));
+    }
+    CU(cudaEventRecord(c->ev_main, c->stream));        // the previous update (it reads sh_gather) has been enqueued before this point
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_main, 0));
+    CU(cudaMemcpyAsync(c->rng_win_saved, c->rng_win, 31 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream2));
+    TRY(replay_graph(c, c->shuffle_graph, c->stream2, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }));
+    CU(cudaEventRecord(c->ev_shuf, c->stream2));
+    c->shuffle_prefetched = true;
+    return PPO_OK;
+}
+// the prefetched permutations will not be used (re-seed, switch to the host shuffle): put the generator back
+static int drop_shuffle_prefetch(ppo_core* c, bool restore_window) {
+    if (!c->shuffle_prefetched) return PPO_OK;
+    CU(cudaStreamSynchronize(c->stream2));
+    if (restore_window) {
+        CU(cudaMemcpyAsync(c->rng_win, c->rng_win_saved, 31 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->shuffle_prefetched = false;
     return PPO_OK;
 }
 
@@ -1852,39 +1943,17 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
             CU(cudaStreamSynchronize(c->stream));
             c->rng_on_device = true;
         }
-        ppo_core::EpochGraph& ug = c->update_graph;
         if (!update_graph_ok(c)) {
-            TRY(enqueue_update_gpu_shuffle(c, lr, cliprange));
+            TRY(enqueue_shuffle(c));
+            TRY(enqueue_epochs(c, lr, cliprange));
         } else {
-            if (!ug.exec || ug.lr != lr || ug.cliprange != cliprange || ug.bpow_slot != c->bpow_slot) {
-                if (ug.exec) {
-                    cudaGraphExecDestroy(ug.exec);
-                    ug.exec = nullptr;
-                }
-                const int slot0 = c->bpow_slot;
-                const uint64_t k0 = c->ctr.kernel_launches;
-                cudaGraph_t graph = nullptr;
-                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                const int st = enqueue_update_gpu_shuffle(c, lr, cliprange);
-                const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-                ug.kernels = c->ctr.kernel_launches - k0;
-                c->ctr.kernel_launches = k0;
-                ug.flip = c->bpow_slot ^ slot0;
-                c->bpow_slot = slot0;
-                if (st != PPO_OK) {
-                    if (graph) cudaGraphDestroy(graph);
-                    return st;
-                }
-                if (ce != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaStreamEndCapture(update) failed: %s", cudaGetErrorString(ce));
-                const cudaError_t ie = cudaGraphInstantiate(&ug.exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ie != cudaSuccess) return fail(PPO_ERR_CUDA, "cudaGraphInstantiate(update) failed: %s", cudaGetErrorString(ie));
-                ug.lr = lr; ug.cliprange = cliprange; ug.bpow_slot = slot0;
+            if (c->shuffle_prefetched) {  // built on stream2 while the rollout ran
+                CU(cudaStreamWaitEvent(c->stream, c->ev_shuf, 0));
+                c->shuffle_prefetched = false;
+            } else {
+                TRY(replay_graph(c, c->shuffle_graph, c->stream, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }));
             }
-            CU(cudaGraphLaunch(ug.exec, c->stream));
-            c->ctr.graph_launches++;
-            c->ctr.kernel_launches += ug.kernels;
-            c->bpow_slot ^= ug.flip;
+            TRY(replay_graph(c, c->update_graph, c->stream, lr, cliprange, [&]() { return enqueue_epochs(c, lr, cliprange); }));
         }
         if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
         CU(cudaGetLastError());
@@ -1894,6 +1963,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         }
         return PPO_OK;
     }
+    TRY(drop_shuffle_prefetch(c, true));
     if (c->rng_on_device) {  // host path after a device shuffle: bring the generator state back
         CU(cudaMemcpyAsync(c->win_pinned, c->rng_win, 31 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -1979,6 +2049,8 @@ extern "C" int ppo_train_get_permutation(ppo_core* c, int epoch, int* out, int n
     if (epoch < 0 || epoch >= c->desc.noptepochs) return fail(PPO_ERR_INVALID, "epoch %d out of range", epoch);
     CU(cudaSetDevice(c->desc.device));
     if (c->gpu_shuffle && fast_path(c)) {
+        if (c->shuffle_prefetched)
+            return fail(PPO_ERR_INVALID, "the permutations of the last update are gone: the next rollout has started (they are rebuilt then)");
         CU(cudaMemcpyAsync(out, c->sh_perm + (size_t)epoch * n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     } else {

@@ -647,6 +647,42 @@ def test_device_random_shuffle_bit_exact(core_mod, n_envs, n_steps, epochs, seed
     c.close()
 
 
+def test_shuffle_prefetch_equals_inline(core_mod, monkeypatch):
+    """From the second update on, the permutations are built on a second stream while the rollout runs (they depend on the
+    rand() stream only).  Same kernels, same generator state: training and permutations are bit-identical to the inline
+    order, and a re-seed after the prefetch has started discards it."""
+    rng = np.random.default_rng(4)
+    p = rand_params(rng, 64, 64)
+    n_envs, n_steps, E = 256, 16, 3
+    res = []
+    for env in (None, "PPO_DISABLE_SHUFFLE_PREFETCH"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        c = make_core(core_mod, p, hidden1=64, hidden2=64, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=E, seed=21)
+        c.shuffle_seed(7)
+        c.synth_env_reset()
+        losses = [c.learn_update_synthetic(3e-4, 0.2) for _ in range(3)]
+        perms = [c.train_get_permutation(e) for e in range(E)]
+        # a rollout starts (prefetch of the 4th update's permutations), then the generator is re-seeded
+        c.rollout_synthetic()
+        c.shuffle_seed(77)
+        c.train_update(3e-4, 0.2)
+        reseeded = [c.train_get_permutation(e) for e in range(E)]
+        res.append(dict(losses=np.stack(losses), params=c.get_tensor("params"), perms=perms, reseeded=reseeded))
+        c.close()
+        if env:
+            monkeypatch.delenv(env)
+    a, b = res
+    assert np.array_equal(a["params"], b["params"]) and np.array_equal(a["losses"], b["losses"])
+    n = n_envs * n_steps
+    want = core_mod.host_random_shuffle(7, n, 3 * E)  # three updates: identity again at each, the stream goes on
+    stream3 = core_mod.host_random_shuffle(77, n, E)
+    for e in range(E):
+        assert np.array_equal(a["perms"][e], b["perms"][e])
+        assert np.array_equal(a["reseeded"][e], stream3[e]) and np.array_equal(b["reseeded"][e], stream3[e])
+    del want
+
+
 def test_device_shuffle_equals_host_shuffle_training(core_mod, monkeypatch):
     """Same training run with the permutations from the device kernels and from the host restatement."""
     rng = np.random.default_rng(4)
