@@ -1671,7 +1671,8 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     GemmArgs q{};
     q.mode = MODE_DW;
     q.HT = 2 * NT;
-    q.KG = std::min(16, q.HT);
+    static const int kg_env = getenv("PPO_WIDE_KG") ? atoi(getenv("PPO_WIDE_KG")) : 0;  // split-K groups (measurements)
+    q.KG = std::min(kg_env > 0 ? kg_env : 16, std::min(q.HT, c->max_train_grid));
     q.partial = a.partial; q.PS = a.PS; q.H = H; q.O = d.O; q.A_dim = d.A;
     q.off_w1[0] = d.off[T_PI_FC1_W]; q.off_w1[1] = d.off[T_VF_FC1_W];
     q.off_w0[0] = d.off[T_PI_FC0_W]; q.off_w0[1] = d.off[T_VF_FC0_W];
