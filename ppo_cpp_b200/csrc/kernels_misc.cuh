@@ -498,7 +498,7 @@ __global__ void replay_apply_kernel(const ReplayArgs a) {
         float4* o4 = reinterpret_cast<float4*>(a.obs_out + (size_t)t * total);
 #pragma unroll 4
         for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total / 4; e += stride) {
-            float4 x = __ldg(x4 + e);
+            float4 x = __ldcs(x4 + e);  // streamed once: evict first
             if (a.norm_obs) {
                 int c = (int)((4 * e) % D);
                 x.x = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
@@ -509,7 +509,7 @@ __global__ void replay_apply_kernel(const ReplayArgs a) {
                 c = c + 1 == D ? 0 : c + 1;
                 x.w = fminf(fmaxf(__fmul_rn(__fsub_rn(x.w, ss[c]), ss[D + c]), -a.clip_obs), a.clip_obs);
             }
-            o4[e] = x;
+            __stcs(o4 + e, x);
         }
     } else if ((D & 1) == 0) {
         for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total / 2; e += stride) {
