@@ -1821,8 +1821,8 @@ static int enqueue_epochs(ppo_core* c, float lr, float cliprange) {
 
 // capture `enqueue` (launches on c->stream) once and replay it on `on`; lr / cliprange / beta-power slot are baked in
 template <class F>
-static int replay_graph(ppo_core* c, ppo_core::EpochGraph& g, cudaStream_t on, float lr, float cliprange, F enqueue) {
-    if (!g.exec || g.lr != lr || g.cliprange != cliprange || g.bpow_slot != c->bpow_slot) {
+static int replay_graph(ppo_core* c, ppo_core::EpochGraph& g, cudaStream_t on, float lr, float cliprange, F enqueue, bool uses_adam = true) {
+    if (!g.exec || g.lr != lr || g.cliprange != cliprange || (uses_adam && g.bpow_slot != c->bpow_slot)) {
         if (g.exec) {
             cudaGraphExecDestroy(g.exec);
             g.exec = nullptr;
@@ -1868,7 +1868,7 @@ static int prefetch_shuffle(ppo_core* c) {
     CU(cudaEventRecord(c->ev_main, c->stream));        // the previous update (it reads sh_gather) has been enqueued before this point
     CU(cudaStreamWaitEvent(c->stream2, c->ev_main, 0));
     CU(cudaMemcpyAsync(c->rng_win_saved, c->rng_win, 31 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream2));
-    TRY(replay_graph(c, c->shuffle_graph, c->stream2, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }));
+    TRY(replay_graph(c, c->shuffle_graph, c->stream2, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }, false));
     CU(cudaEventRecord(c->ev_shuf, c->stream2));
     c->shuffle_prefetched = true;
     return PPO_OK;
@@ -1953,7 +1953,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
                 CU(cudaStreamWaitEvent(c->stream, c->ev_shuf, 0));
                 c->shuffle_prefetched = false;
             } else {
-                TRY(replay_graph(c, c->shuffle_graph, c->stream, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }));
+                TRY(replay_graph(c, c->shuffle_graph, c->stream, 0.f, 0.f, [&]() { return enqueue_shuffle(c); }, false));
             }
             TRY(replay_graph(c, c->update_graph, c->stream, lr, cliprange, [&]() { return enqueue_epochs(c, lr, cliprange); }));
         }
