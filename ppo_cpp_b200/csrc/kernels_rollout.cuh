@@ -293,16 +293,22 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
         if (merge) {
             // -- RunningStatistics::update over ALL envs: partials -> grid barrier -> fixed-order total in every CTA
             // partial layout [parity][column][cta]: the totals below read 32 consecutive CTAs per load instruction
+            const bool solo = gridDim.x == 1 && world == 1;  // one CTA holds every env (C1 / C2 shapes): its partials ARE the totals
             double* mine = a.partial + (size_t)(t & 1) * 2 * (D + 1) * gridDim.x + blockIdx.x;
-            if (tid <= D) {
+            if (solo) {
+                if (tid <= D) {
+                    csum[tid] = ps;
+                    csum[D + 1 + tid] = pq;
+                }
+            } else if (tid <= D) {
                 mine[(size_t)tid * gridDim.x] = ps;
                 mine[(size_t)(D + 1 + tid) * gridDim.x] = pq;
             }
             R_PROF();  // partial moments written
-            bar.sync();
+            if (!solo) bar.sync();
             R_PROF();  // grid barrier passed
             const double* all = a.partial + (size_t)(t & 1) * 2 * (D + 1) * gridDim.x;
-            if (world == 1 || blockIdx.x == 0) {
+            if (!solo && (world == 1 || blockIdx.x == 0)) {
                 // warp w sums columns w, w+8, ...: lane partials over the CTAs (independent loads, 5 columns x 4 in flight),
                 // then a butterfly — the same order in every CTA, so every CTA gets the same bits
                 constexpr int CPW = 5;  // columns per warp: 8 warps x 5 >= 2*(D+1) for D <= 19
