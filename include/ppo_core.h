@@ -182,7 +182,9 @@ int ppo_train_update(ppo_core *core, float lr, float cliprange, float *mean_loss
  * losses[5] of that step; grads (may be NULL) = the unclipped gradient, n_params_trainable floats */
 int ppo_train_set_permutation(ppo_core *core, const int *perm, int n);
 /* perm.indices of epoch `epoch` of the LAST ppo_train_update (n_batch ints, compounded over the epochs as in
- * ppo2.hpp:274-288) — lets a test compare the device-built permutations with std::random_shuffle bit for bit */
+ * ppo2.hpp:274-288) — lets a test compare the device-built permutations with std::random_shuffle bit for bit.
+ * Valid until the next rollout starts: the permutations of the NEXT update are then built beside the rollout
+ * (they depend on the rand() stream only) and this call returns PPO_ERR_INVALID. */
 int ppo_train_get_permutation(ppo_core *core, int epoch, int *out, int n);
 int ppo_train_minibatch(ppo_core *core, int k, float lr, float cliprange, float *losses, float *grads);
 /* standalone pieces on caller data (host pointers): advantage normalisation (ppo2.hpp:401-406) and loss+grad */
