@@ -174,6 +174,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): whatever libraries print on the way (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
@@ -364,7 +368,10 @@ def run_ours(args):
             "gpu_launches": int(ctr["kernel_launches"]), "clocks": clocks, "roofline": roofline, "kernel_ms": kernels,
             "cpu_baseline": cpu_baseline, "e2e": e2e,
         }
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     c.close()
     if world > 1:
         dist.destroy_process_group()
