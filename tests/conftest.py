@@ -42,6 +42,30 @@ def loss_kat():
     return load_npz_tree("loss_grad_kat.npz")
 
 
+@pytest.fixture(scope="session")
+def gx_act():
+    """act-model outputs of the reference's graph, executed node by node (make_graph_exec_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "graph_exec_act.npz"))
+    out = {}
+    for k in z.files:
+        if "__" in k:
+            c, f = k.split("__", 1)
+            out.setdefault(c, {})[f] = z[k]
+    return out
+
+
+@pytest.fixture(scope="session")
+def gx_train():
+    """train-model losses / gradients / clip / ApplyAdam state of the executed reference graph."""
+    z = np.load(os.path.join(GOLDEN, "graph_exec_train.npz"))
+    out = {}
+    for k in z.files:
+        if "__" in k:
+            c, f = k.split("__", 1)
+            out.setdefault(c, {})[f] = z[k]
+    return out
+
+
 def load_weights(name):
     from ppo_cpp_b200.meta_graph import TENSOR_ORDER
     z = np.load(os.path.join(GOLDEN, name))

@@ -263,6 +263,80 @@ def test_loss_grad_golden_autograd(core_mod, case, loss_kat, kat):
     c.close()
 
 
+# ---- the same entry points against fixtures made by EXECUTING the reference's TensorFlow graph file node by node
+# (oracle/tf_graph_exec.py; forward GRAPH:1859-6866, loss 9210-11752, autodiff 11773-23699, clip 23738-25392,
+# ApplyAdam 25426-31383).  This is the parity pin: nothing below depends on a restatement of the math.
+GX_ALL = ["init_4_5", "ckpt_4_5", "ties_4_5", "rand_8_8", "rand_64_64", "ties_64_64", "rand_128_128", "obs36_4_5", "obs1_4_5",
+          "obs36_64_64"]
+
+
+def _gx_core(core_mod, k, kat, **kw):
+    O, A, h1, h2 = (int(x) for x in k["dims"])
+    cst = kat["consts"]
+    return make_core(core_mod, k["params"], obs_dim=O, act_dim=A, hidden1=h1, hidden2=h2, ent_coef=cst["ent_coef"],
+                     vf_coef=cst["vf_coef"], max_grad_norm=cst["clip_norm"], adam_beta1=cst["beta1"], adam_beta2=cst["beta2"],
+                     adam_epsilon=cst["adam_eps"], **kw)
+
+
+@pytest.mark.parametrize("case", GX_ALL)
+def test_policy_step_vs_executed_graph(core_mod, case, gx_act, kat):
+    k = gx_act[case]
+    c = _gx_core(core_mod, k, kat, n_envs=8, n_steps=4, nminibatches=4)
+    act, val, nlp = c.policy_step(k["obs"], k["eps"])
+    assert rel_err(act, k["action_f64"]) < TOL and rel_err(val, k["value_f64"]) < TOL and rel_err(nlp, k["neglogp_f64"]) < TOL
+    assert rel_err(c.policy_mean(k["obs"]), k["mean_f64"]) < TOL
+    assert rel_err(c.policy_value(k["obs"]), k["value_f64"]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("case", GX_ALL)
+def test_loss_grad_vs_executed_graph(core_mod, case, gx_train, kat):
+    """Losses and all 13 gradient tensors (before the clip) of the graph's first train step, ties included."""
+    from ppo_cpp_b200.meta_graph import TENSOR_ORDER, param_layout
+    k = gx_train[case]
+    c = _gx_core(core_mod, k, kat, n_envs=4, n_steps=8, nminibatches=4)
+    g, l = c.loss_grad(k["obs"][0], k["act"][0], k["adv"][0], k["ret"][0], k["old_nlp"][0], k["old_v"][0], float(k["cliprange"]))
+    want = k["grads_f64"][0]
+    assert rel_err(g, want) < TOL
+    O, A, h1, h2 = (int(x) for x in k["dims"])
+    lay = param_layout(O, A, h1, h2)
+    for name in TENSOR_ORDER[:13]:
+        off, shp = lay[name]
+        n = int(np.prod(shp))
+        assert rel_err(g[off:off + n], want[off:off + n]) < TOL, name
+    assert np.allclose(l, k["losses_f64"][0], rtol=TOL, atol=2e-7)
+    c.close()
+
+
+@pytest.mark.parametrize("case", ["init_4_5", "ckpt_4_5", "rand_8_8", "rand_64_64", "obs36_4_5", "obs1_4_5"])
+def test_train_steps_vs_executed_graph(core_mod, case, gx_train, kat):
+    """Consecutive `ppo2/_train` runs of the graph (GRAPH:31383): the rollout buffers hold the fixture's minibatches back
+    to back, the permutation is the identity, minibatch k is train step k.  Checks the per-minibatch advantage
+    normalisation (ppo2.hpp:401-406), losses, unclipped gradient, and after every step the weights, Adam m / v and
+    the beta powers against the graph's variables."""
+    k = gx_train[case]
+    steps, B = k["obs"].shape[:2]
+    c = _gx_core(core_mod, k, kat, n_envs=1, n_steps=steps * B, nminibatches=steps, noptepochs=1)
+    P = c.P
+    flat = lambda a: np.ascontiguousarray(a.reshape(steps * B, -1))
+    for name, f in (("obs", "obs"), ("actions", "act"), ("returns", "ret"), ("values", "old_v"), ("neglogpacs", "old_nlp")):
+        c.rollout_set(name, flat(k[f]))
+    c.train_set_permutation(np.arange(steps * B, dtype=np.int32))
+    th0 = k["params"][:P].astype(np.float64)
+    for s in range(steps):
+        losses, grads = c.train_minibatch(s, float(k["lr"]), float(k["cliprange"]))
+        assert rel_err(grads, k["grads_f64"][s]) < (TOL if s == 0 else 3 * TOL), s   # later steps start from fp32-rounded weights
+        assert np.allclose(losses, k["losses_f64"][s], rtol=3 * TOL, atol=2e-6), (s, losses, k["losses_f64"][s])
+        got = c.get_tensor("params")
+        assert rel_err(got[:P], k["theta_f64"][s]) < 1e-6, s
+        assert rel_err(got[:P] - th0, k["theta_f64"][s] - th0) < 1e-3, s       # the accumulated movement itself (fp32 ulp-limited)
+        assert np.array_equal(got[P:], k["params"][P:])
+        assert rel_err(c.get_tensor("adam_m"), k["m_f64"][s]) < 3 * TOL and rel_err(c.get_tensor("adam_v"), k["v_f64"][s]) < 3 * TOL
+        assert c.get_tensor("beta1_power")[0] == pytest.approx(k["bpow_f64"][s][0], rel=1e-6)
+        assert c.get_tensor("beta2_power")[0] == pytest.approx(k["bpow_f64"][s][1], rel=1e-6)
+    c.close()
+
+
 @pytest.mark.parametrize("h1,h2,B", [(4, 5, 64), (4, 5, 2048), (64, 64, 8192), (256, 256, 512), (12, 20, 100), (5, 3, 37)])
 def test_loss_grad_vs_oracle(core_mod, h1, h2, B):
     rng = np.random.default_rng(B + h1)

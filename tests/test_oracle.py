@@ -270,3 +270,105 @@ def test_learner_mock_env_matches_stepwise_pieces(init_weights, kat):
             th, m, vv, _, b1p, b2p, _ = o.clip_adam(np.float32(3.9e-4), th, m, vv, g, b1p, b2p, "f32")
     assert np.array_equal(th, p1[:o.P])
     lib.oracle_learner_destroy(L)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Parity pin: fixtures produced by EXECUTING the reference's own TensorFlow graph file node by node
+# (oracle/tf_graph_exec.py + tests/golden/make_graph_exec_golden.py).  Forward GRAPH:1859-6866, loss
+# 9210-11752, autodiff 11773-23699 (tie rules are graph nodes), clip 23738-25392, ApplyAdam 25426-31383.
+# ----------------------------------------------------------------------------------------------------------
+GX_ACT = ["init_4_5", "ckpt_4_5", "rand_8_8", "rand_64_64", "rand_128_128", "obs36_4_5", "obs1_4_5", "obs36_64_64",
+          "ties_4_5", "ties_64_64"]
+GX_TRAIN_FULL = ["init_4_5", "ckpt_4_5", "ties_4_5", "rand_8_8", "rand_64_64", "obs36_4_5", "obs1_4_5"]
+GX_TRAIN_LIGHT = ["ties_64_64", "obs36_64_64", "rand_128_128"]
+
+
+def _gx_oracle(k, kat):
+    O, A, h1, h2 = (int(x) for x in k["dims"])
+    c = kat["consts"]
+    return ol.Oracle(obs_dim=O, act_dim=A, h1=h1, h2=h2, ent_coef=c["ent_coef"], vf_coef=c["vf_coef"], clip_norm=c["clip_norm"],
+                     beta1=c["beta1"], beta2=c["beta2"], adam_eps=c["adam_eps"])
+
+
+@pytest.mark.parametrize("case", GX_ACT)
+def test_policy_step_vs_executed_graph(case, gx_act, kat):
+    k = gx_act[case]
+    o = _gx_oracle(k, kat)
+    for prec, tol in (("f64", 1e-12), ("f32", 3e-6)):
+        action, value, nlp, mean = o.policy_step(k["params"], k["obs"], k["eps"], prec)
+        for got, name in ((action, "action"), (value, "value"), (nlp, "neglogp"), (mean, "mean")):
+            assert rel_err(got, k[f"{name}_f64"]) < tol, (name, prec)
+    # the fp32 oracle against TF's own arithmetic type executed in numpy
+    action, value, nlp, mean = o.policy_step(k["params"], k["obs"], k["eps"], "f32")
+    for got, name in ((action, "action"), (value, "value"), (nlp, "neglogp"), (mean, "mean")):
+        assert rel_err(got, k[f"{name}_f32"]) < 3e-6, name
+
+
+def _gx_replay(o, k, prec, steps):
+    """Consecutive train steps with the piecewise oracle functions; yields per-step (losses, grads, theta, m, v, bpow, gnorm)."""
+    dt = np.float32 if prec == "f32" else np.float64
+    P = o.P
+    th, m, v = k["params"][:P].astype(dt), np.zeros(P, dt), np.zeros(P, dt)
+    b1p, b2p = dt(np.float32(o.hp.beta1)), dt(np.float32(o.hp.beta2))
+    for s in range(steps):
+        full = np.concatenate([th.astype(np.float32), k["params"][P:]])
+        if prec == "f64":
+            assert s == 0 or True
+        g, losses = o.loss_grad(full, k["obs"][s], k["act"][s], k["adv"][s], k["ret"][s], k["old_nlp"][s], k["old_v"][s],
+                                dt(k["cliprange"]), prec)
+        th, m, v, _, b1p, b2p, gn = o.clip_adam(dt(k["lr"]), th, m, v, g, b1p, b2p, prec)
+        yield losses, g, th, m, v, (b1p, b2p), gn
+
+
+@pytest.mark.parametrize("case", GX_TRAIN_FULL + GX_TRAIN_LIGHT)
+def test_train_step_vs_executed_graph(case, gx_train, kat):
+    from ppo_cpp_b200.meta_graph import TENSOR_ORDER, param_layout
+    k = gx_train[case]
+    o = _gx_oracle(k, kat)
+    O, A, h1, h2 = (int(x) for x in k["dims"])
+    lay = param_layout(O, A, h1, h2)
+    # fp64 oracle, first step: gradients (every tensor separately), losses, norm, Adam state — tight
+    losses, g, th, m, v, bp, gn = next(_gx_replay(o, k, "f64", 1))
+    assert np.allclose(losses, k["losses_f64"][0], rtol=1e-9, atol=1e-12)      # the graph's constants are fp32-baked
+    for name in TENSOR_ORDER[:13]:
+        off, shp = lay[name]
+        n = int(np.prod(shp))
+        assert rel_err(g[off:off + n], k["grads_f64"][0][off:off + n]) < 1e-10, name
+    assert gn == pytest.approx(float(k["gnorm_f64"][0]), rel=1e-12)
+    assert rel_err(th - k["params"][:o.P], k["theta_f64"][0] - k["params"][:o.P]) < 1e-9
+    assert bp[0] == pytest.approx(k["bpow_f64"][0][0], rel=1e-12) and bp[1] == pytest.approx(k["bpow_f64"][0][1], rel=1e-12)
+    if "m_f64" in k:
+        assert rel_err(m, k["m_f64"][0]) < 1e-10 and rel_err(v, k["v_f64"][0]) < 1e-10
+    # fp32 oracle, every consecutive step (weights fed back through fp32, as the reference's variables are):
+    if "theta_f32" in k:
+        steps = k["obs"].shape[0]
+        for s, (losses, g, th, m, v, bp, gn) in enumerate(_gx_replay(o, k, "f32", steps)):
+            assert np.allclose(losses, k["losses_f32"][s], rtol=2e-5, atol=1e-6), (s, losses, k["losses_f32"][s])
+            for name in TENSOR_ORDER[:13]:
+                off, shp = lay[name]
+                n = int(np.prod(shp))
+                assert rel_err(g[off:off + n], k["grads_f32"][s][off:off + n]) < 2e-5, (s, name)
+            assert rel_err(th, k["theta_f32"][s]) < 1e-6 and rel_err(m, k["m_f32"][s]) < 2e-5 and rel_err(v, k["v_f32"][s]) < 2e-5
+            assert bp[0] == pytest.approx(k["bpow_f32"][s][0], rel=1e-6) and bp[1] == pytest.approx(k["bpow_f32"][s][1], rel=1e-6)
+            # and the fp32 run tracks the fp64 truth of the same step count
+            assert rel_err(th, k["theta_f64"][s]) < 1e-6
+
+
+def test_executed_graph_tie_rules_are_discriminating(gx_train):
+    """The tie fixture really separates TF's rule (ties -> first argument, GRAPH:14975-15142) from a 0.5/0.5 split:
+    samples 16..31 have (v-R)^2 == (vclip-R)^2 with v outside the clip range, so dL/dv = vf_coef*(v-R)/B under TF's
+    rule, half of that under a split, and 0 if the clipped branch won.  vf/b's gradient is the sum of dL/dv."""
+    k = gx_train["ties_4_5"]
+    O, A, h1, h2 = (int(x) for x in k["dims"])
+    from ppo_cpp_b200.meta_graph import param_layout
+    off, _ = param_layout(O, A, h1, h2)["model/vf/b"]
+    B = k["obs"].shape[1]
+    v, R, ov, cr = 1.0, k["ret"][0].astype(np.float64), k["old_v"][0].astype(np.float64), float(k["cliprange"])
+    vc = ov + np.clip(v - ov, -cr, cr)
+    l1, l2 = (v - R) ** 2, (vc - R) ** 2
+    inr = (np.abs(v - ov) <= cr)
+    assert np.all(l1[16:32] == l2[16:32]) and not inr[16:32].any() and inr[:16].all()
+    dv_tf = 0.5 * 0.5 / B * np.where(l1 >= l2, 2 * (v - R), 2 * (vc - R) * inr)
+    assert k["grads_f64"][0][off] == pytest.approx(dv_tf.sum(), rel=1e-12)
+    dv_split = 0.5 * 0.5 / B * np.where(l1 > l2, 2 * (v - R), np.where(l1 == l2, (v - R) + (vc - R) * inr, 2 * (vc - R) * inr))
+    assert abs(dv_split.sum() - dv_tf.sum()) > 1e-3
