@@ -11,7 +11,10 @@
  *   - plain pointers and sizes; no C++/torch types.  Every function returns 0 on success or a
  *     negative ppo_status; ppo_last_error() gives the message (thread-local).
  *   - `mem` says where caller buffers live: PPO_HOST (pageable or pinned host memory; the call does
- *     the H2D/D2H copies on the core's stream and returns after they completed) or PPO_DEVICE
+ *     the H2D/D2H copies on the core's stream and returns after they completed — with one exception:
+ *     PINNED input buffers of ppo_runner_observe are DMA'd in place and the call returns once the copies are
+ *     enqueued; they must stay valid and unmodified until the next call that returns data to the host
+ *     (ppo_runner_act, ppo_train_update with losses, ppo_core_sync ...)) or PPO_DEVICE
  *     (device pointers on the core's device; the call only enqueues work on the core's stream —
  *     use ppo_core_sync or your own event to wait).
  *   - all matrices are row-major fp32, shapes as in the reference (obs [n,O], actions [n,A], per-env
@@ -50,7 +53,7 @@ typedef struct ppo_core ppo_core; /* opaque */
 typedef struct {
     int abi_version; /* PPO_CORE_ABI_VERSION */
     int device;      /* CUDA ordinal */
-    int obs_dim, act_dim;   /* 18, 18 for every reference env */
+    int obs_dim, act_dim;   /* 1..64 each.  Reference envs: 18/18 closed loop (36/18 with velocities), 1/18 open loop */
     int hidden1, hidden2;   /* MLP [h1,h2] for both towers; overwritten by ppo_core_load_meta_txt */
     int n_envs;             /* envs owned by THIS rank */
     int n_steps;            /* --batch_steps: steps per env per update (ppo2.cpp:114) */

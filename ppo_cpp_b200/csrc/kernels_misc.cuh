@@ -549,9 +549,11 @@ __global__ void bump_counter_kernel(uint32_t* c) { *c += 1u; }
 // ------------------------------------------------------------------------------------------------
 // GAE(lambda) reverse scan (Runner::set_returns, runner.hpp:159-191) over time-major [T][N] buffers.
 // One thread per (env, chunk of `chunk` steps).  A chunk that does not end at T-1 first runs `warm` extra
-// steps ahead of it starting from lastgaelam = 0: the recurrence contracts by gamma*lam per step, so after
-// `warm` steps the carried value equals the sequential one to below fp32 resolution (0.9405^512 ~ 2e-14)
-// while every arithmetic operation stays the reference's (bit-identical results in practice).
+// steps ahead of it starting from lastgaelam = 0: the recurrence contracts by gamma*lam per step (and is reset exactly
+// by every done flag), so after `warm` steps the carried value equals the sequential one to below fp32 resolution
+// while every arithmetic operation stays the reference's (bit-identical results in practice).  The launcher derives
+// `warm` from gamma*lam ((gamma*lam)^warm <= 2^-46; 0.9405 -> 520) and switches to the affine-carry kernels below when
+// gamma*lam is too close to 1 for any warm-up to contract.
 __global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ dones,
                            const float* __restrict__ last_val, const float* __restrict__ last_done, int T, int N,
                            float gamma, float lam, int chunk, int warm, float* __restrict__ adv_out,
@@ -603,6 +605,66 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
         }
         nextv = v;
         nextnt = 1.0f - dones[idx];
+    }
+}
+
+// Exact chunking for ANY gamma, lam (gamma*lam close to or equal to 1, where no warm-up length contracts): pass 1 reduces
+// every (env, chunk) to the affine map  last_out = A * last_in + B  of its steps (fp64), pass 2 (gae_kernel_carry)
+// composes the maps of the chunks above it into the chunk's incoming `lastgaelam` and then runs the chunk with the
+// reference's fp32 operation order.  The carried value is the exact recurrence rounded once instead of the sequential
+// fp32 one: the two differ by the rounding the sequential fp32 scan itself accumulates (a few ulp).
+__global__ void gae_affine_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ dones,
+                                  const float* __restrict__ last_val, const float* __restrict__ last_done, int T, int N,
+                                  float gamma, float lam, int chunk, double2* __restrict__ ab) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (e >= N) return;
+    const int t_lo = c * chunk;
+    const int t_hi = min(T, t_lo + chunk) - 1;
+    const double g = (double)gamma, gl = (double)__fmul_rn(gamma, lam);
+    double A = 1.0, B = 0.0;
+    double nextv = (t_hi == T - 1) ? (double)last_val[e] : (double)val[(size_t)(t_hi + 1) * N + e];
+    double nextnt = 1.0 - ((t_hi == T - 1) ? (double)last_done[e] : (double)dones[(size_t)(t_hi + 1) * N + e]);
+    for (int t = t_hi; t >= t_lo; --t) {
+        const size_t idx = (size_t)t * N + e;
+        const double v = (double)__ldg(val + idx);
+        const double delta = (double)__ldg(rew + idx) + g * nextv * nextnt - v;
+        const double ct = gl * nextnt;
+        B = delta + ct * B;
+        A = ct * A;
+        nextv = v;
+        nextnt = 1.0 - (double)__ldg(dones + idx);
+    }
+    ab[(size_t)c * N + e] = make_double2(A, B);
+}
+
+__global__ void gae_kernel_carry(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ dones,
+                                 const float* __restrict__ last_val, const float* __restrict__ last_done, int T, int N,
+                                 float gamma, float lam, int chunk, int nchunks, const double2* __restrict__ ab,
+                                 float* __restrict__ adv_out, float* __restrict__ ret_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (e >= N) return;
+    double carry = 0.0;
+    for (int cc = nchunks - 1; cc > c; --cc) {
+        const double2 m = ab[(size_t)cc * N + e];
+        carry = m.x * carry + m.y;
+    }
+    const int t_lo = c * chunk;
+    const int t_hi = min(T, t_lo + chunk) - 1;
+    const float gl = __fmul_rn(gamma, lam);
+    float last = (float)carry;
+    float nextv = (t_hi == T - 1) ? last_val[e] : val[(size_t)(t_hi + 1) * N + e];
+    float nextnt = 1.0f - ((t_hi == T - 1) ? last_done[e] : dones[(size_t)(t_hi + 1) * N + e]);
+    for (int t = t_hi; t >= t_lo; --t) {
+        const size_t idx = (size_t)t * N + e;
+        const float v = __ldg(val + idx);
+        const float delta = __fsub_rn(__fadd_rn(__ldg(rew + idx), __fmul_rn(gamma, __fmul_rn(nextv, nextnt))), v);
+        last = __fadd_rn(delta, __fmul_rn(gl, __fmul_rn(nextnt, last)));
+        if (adv_out) adv_out[idx] = last;
+        ret_out[idx] = __fadd_rn(last, v);
+        nextv = v;
+        nextnt = 1.0f - __ldg(dones + idx);
     }
 }
 

@@ -182,6 +182,8 @@ struct ppo_core {
     unsigned stage_ctr = 0;
     float* scratch = nullptr;    // device scratch for host-pointer calls
     size_t scratch_floats = 0;
+    void* gae_ab = nullptr;      // per-(chunk, env) affine maps of the exact chunked GAE (gamma*lam near 1)
+    size_t gae_ab_bytes = 0;
 
     ncclComm_t comm = nullptr;
     // peer-memory mailbox (multi-GPU): this rank's allocation, the IPC mappings of the peers', device-resident
@@ -358,11 +360,12 @@ extern "C" int ppo_meta_parse(const char* path, ppo_meta_info* info, float* para
 }
 
 template <int TM>
-static int set_smem_attrs(const NetDims& d) {
-    CU(cudaFuncSetAttribute(train_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(train_smem_floats<TM>(d) * sizeof(float))));
-    CU(cudaFuncSetAttribute(policy_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(policy_smem_floats<TM>(d) * sizeof(float))));
+static int set_smem_attrs(size_t max_smem) {
+    // The attribute is per function and per device, i.e. shared by every core of the process: always raise it to the
+    // device's opt-in maximum, so that a core created later with smaller hidden sizes (EnvNormalize's private [4,5] core
+    // beside a [64,64] PPO2 core) cannot lower the limit under a live core.  What a launch uses is its own smem argument.
+    CU(cudaFuncSetAttribute(train_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(policy_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     return PPO_OK;
 }
 
@@ -374,6 +377,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     for (int r = 0; r < PPO_MAX_WORLD; ++r)
         if (c->mbox_peer[r] && r != c->desc.rank) cudaIpcCloseMemHandle(c->mbox_peer[r]);
     if (c->mbox_mem) cudaFree(c->mbox_mem);
+    if (c->gae_ab) cudaFree(c->gae_ab);
     if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
     for (auto& g : c->graphs)
@@ -506,8 +510,10 @@ static int core_alloc(ppo_core* c) {
 extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
     if (!desc || !out) return fail(PPO_ERR_INVALID, "ppo_core_create: NULL argument");
     if (desc->abi_version != PPO_CORE_ABI_VERSION) return fail(PPO_ERR_INVALID, "ABI version mismatch: header %d, library %d", desc->abi_version, PPO_CORE_ABI_VERSION);
-    if (desc->obs_dim < 1 || desc->obs_dim > 32 || desc->act_dim < 1 || desc->act_dim > 64 || desc->obs_dim != desc->act_dim)
-        return fail(PPO_ERR_UNSUPPORTED, "obs_dim/act_dim %d/%d unsupported (need 1..32 and equal, the reference uses 18/18)", desc->obs_dim, desc->act_dim);
+    // the reference's envs: closed loop 18/18 (36/18 with velocities, hexapod_closed_loop_env.hpp:20,61-72), open loop 1/18
+    // (hexapod_env.hpp:226-238).  18/18 selects the specialised S / U / W families; other widths run on the generic F / T families.
+    if (desc->obs_dim < 1 || desc->obs_dim > 64 || desc->act_dim < 1 || desc->act_dim > 64)
+        return fail(PPO_ERR_UNSUPPORTED, "obs_dim/act_dim %d/%d unsupported (need 1..64 each)", desc->obs_dim, desc->act_dim);
     if (desc->hidden1 < 1 || desc->hidden2 < 1 || desc->hidden1 > 1024 || desc->hidden2 > 1024)
         return fail(PPO_ERR_UNSUPPORTED, "hidden sizes [%d,%d] out of range 1..1024", desc->hidden1, desc->hidden2);
     if (desc->n_envs < 1 || desc->n_steps < 1 || desc->nminibatches < 1 || desc->noptepochs < 0)
@@ -542,7 +548,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
         else if (train_smem_floats<32>(c->d) * sizeof(float) <= max_smem) c->tm = 32;
         else { st = fail(PPO_ERR_UNSUPPORTED, "hidden sizes [%d,%d] need more shared memory than the device has", desc->hidden1, desc->hidden2); break; }
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaStreamCreate failed"); break; }
-        st = (c->tm == 64) ? set_smem_attrs<64>(c->d) : set_smem_attrs<32>(c->d);
+        st = set_smem_attrs<64>(max_smem);
+        if (st == PPO_OK) st = set_smem_attrs<32>(max_smem);
         if (st != PPO_OK) break;
         {
             FLayout lt, lp;
@@ -553,8 +560,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             c->fused = (c->d.H1 % 4 == 0) && (c->d.H2 % 4 == 0) && c->fused_train_smem <= max_smem && c->fused_policy_smem <= max_smem &&
                        getenv("PPO_DISABLE_FUSED") == nullptr;
             if (c->fused) {
-                if (cudaFuncSetAttribute(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fused_train_smem) != cudaSuccess ||
-                    cudaFuncSetAttribute(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fused_policy_smem) != cudaSuccess) {
+                if (cudaFuncSetAttribute(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+                    cudaFuncSetAttribute(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
                     st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(fused kernels) failed: %s", cudaGetErrorString(cudaGetLastError()));
                     break;
                 }
@@ -626,7 +633,7 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             c->graphs.resize(std::max(1, desc->noptepochs));
             // R family: one CTA per tile of R_TM envs (x tpc tiles) for the whole rollout; needs the parameter vector in
             // shared memory and all CTAs co-resident (grid barrier per env step)
-            if (coop_ok && c->d.O == c->d.A && getenv("PPO_DISABLE_PERSISTENT") == nullptr) {
+            if (coop_ok && c->d.O == c->d.A && c->d.O <= 32 && getenv("PPO_DISABLE_PERSISTENT") == nullptr) {
                 const int ntiles = (desc->n_envs + R_TM - 1) / R_TM;
                 for (int tpc = 1; tpc <= 8 && !c->persistent_rollout; ++tpc) {
                     RLayout L;
@@ -637,7 +644,7 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                     // cannot put two CTAs on one SM (they would run at half speed and everybody waits at the step barrier)
                     size_t smem = (size_t)L.total_bytes;
                     if (grid <= c->sm_count) smem = std::max(smem, std::min(max_smem, (size_t)120 * 1024));
-                    if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                    if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
                         cudaGetLastError();
                         break;
                     }
@@ -1213,16 +1220,41 @@ extern "C" int ppo_matrix_clamp(ppo_core* c, const float* x, size_t n, float lo,
 static int launch_gae(ppo_core* c, const float* rew, const float* val, const float* dones, const float* last_val,
                       const float* last_done, int T, int N, float gamma, float lam, float* adv, float* ret) {
     // enough (env, chunk) threads to fill the machine; chunks only when there are few envs
-    int chunk = T;
     const int want_threads = c->sm_count * 512;
-    if (N < want_threads && T > 1024) {
-        const int nchunks = std::min((T + 511) / 512, std::max(1, want_threads / std::max(N, 1)));
-        chunk = (T + nchunks - 1) / nchunks;
-        chunk = std::max(chunk, 256);
+    if (!(N < want_threads && T > 1024)) {
+        LAUNCH(c, gae_kernel, dim3((N + 127) / 128, 1), 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, T, 0, adv, ret);
+        CU(cudaGetLastError());
+        return PPO_OK;
     }
+    // warm-up length after which a wrong starting value has decayed far below fp32 resolution: (gamma*lam)^warm <= 2^-46
+    // (2^-22 of an ulp: the chance that the residue flips one rounding is ~2e-7 per chunk boundary)
+    const double gl = (double)gamma * (double)lam;
+    const double need = (gl > 0.0 && gl < 1.0) ? std::ceil(std::log(std::ldexp(1.0, -46)) / std::log(gl)) : (gl <= 0.0 ? 1.0 : 1e30);
+    if (need <= 4096.0) {
+        const int warm = std::max(512, (int)need);
+        const int nchunks = std::min((T + warm - 1) / warm, std::max(1, want_threads / std::max(N, 1)));
+        int chunk = std::max((T + nchunks - 1) / nchunks, std::max(256, warm / 2));
+        const dim3 grid((N + 127) / 128, (T + chunk - 1) / chunk);
+        LAUNCH(c, gae_kernel, grid, 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, chunk, warm, adv, ret);
+        CU(cudaGetLastError());
+        return PPO_OK;
+    }
+    // gamma*lam near (or at) 1: no warm-up contracts -> exact chunk carries (affine maps in fp64, then the reference's fp32 steps)
+    const int nchunks0 = std::min((T + 255) / 256, std::max(1, want_threads / std::max(N, 1)));
+    const int chunk = (T + nchunks0 - 1) / nchunks0;
     const int nchunks = (T + chunk - 1) / chunk;
+    const size_t need_bytes = (size_t)nchunks * N * sizeof(double2);
+    if (c->gae_ab_bytes < need_bytes) {
+        if (c->gae_ab) cudaFree(c->gae_ab);
+        c->gae_ab = nullptr;
+        c->gae_ab_bytes = 0;
+        CU(cudaMalloc(&c->gae_ab, need_bytes));
+        c->gae_ab_bytes = need_bytes;
+    }
     const dim3 grid((N + 127) / 128, nchunks);
-    LAUNCH(c, gae_kernel, grid, 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, chunk, 512, adv, ret);
+    LAUNCH(c, gae_affine_kernel, grid, 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, chunk, (double2*)c->gae_ab);
+    LAUNCH(c, gae_kernel_carry, grid, 128, 0, rew, val, dones, last_val, last_done, T, N, gamma, lam, chunk, nchunks,
+           (const double2*)c->gae_ab, adv, ret);
     CU(cudaGetLastError());
     return PPO_OK;
 }
@@ -1361,8 +1393,16 @@ extern "C" int ppo_runner_rollout_replay(ppo_core* c, const float* raw_obs, cons
     return ppo_runner_rollout_host(c, replay_env_step, &env, scratch.data());
 }
 
+// the synthetic env feeds action component k into state component k: it needs obs_dim == act_dim <= 32
+static int synth_env_check(const ppo_core* c) {
+    if (c->d.O != c->d.A || c->d.O > 32)
+        return fail(PPO_ERR_UNSUPPORTED, "the synthetic env needs obs_dim == act_dim <= 32 (have %d/%d); use the host-env protocol", c->d.O, c->d.A);
+    return PPO_OK;
+}
+
 extern "C" int ppo_synth_env_reset(ppo_core* c) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    TRY(synth_env_check(c));
     CU(cudaSetDevice(c->desc.device));
     LAUNCH(c, synth_env_reset_kernel, (c->desc.n_envs + 127) / 128, 128, 0, c->env, c->raw_obs);
     CU(cudaGetLastError());
@@ -1382,6 +1422,7 @@ static int rollout_synthetic_enqueue(ppo_core* c) {
 
 extern "C" int ppo_rollout_synthetic(ppo_core* c) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
+    TRY(synth_env_check(c));
     CU(cudaSetDevice(c->desc.device));
     TRY(prefetch_shuffle(c));  // the next update's permutations, on stream2, while this rollout runs
     if (c->persistent_rollout && fast_path(c)) {
@@ -1556,6 +1597,11 @@ static int ensure_wide(ppo_core* c, int tiles) {
         CU(cudaFree(c->wide_mem));
         c->wide_mem = nullptr;
         c->wide_cap = 0;
+        // captured graphs hold the old pointers: drop them, they are re-captured on their next use
+        for (auto& g : c->graphs)
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (c->update_graph.exec) { cudaGraphExecDestroy(c->update_graph.exec); c->update_graph.exec = nullptr; }
+        if (c->rollout_graph.exec) { cudaGraphExecDestroy(c->rollout_graph.exec); c->rollout_graph.exec = nullptr; }
     }
     wide::Geom G;
     G.init(c->d.H1, tiles, tiles);

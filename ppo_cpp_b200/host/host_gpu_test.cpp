@@ -80,6 +80,17 @@ int main(int argc, char** argv) {
         algo.reset_without_graph(64, 64, 3);
         algo.learn(256);
         REQUIRE(algo.last_fps > 0 && std::isfinite(algo.last_losses[0]));
+        // graph-less checkpoint round trip from a FRESH model that knows neither a graph file nor the hidden sizes
+        // (what `ppo_cpp -p ckpt` does): the .json sidecar carries the shape
+        algo.save(dir + "/graphless.pkl", 0);
+        Mat probe = Mat::Constant(1, 18, -0.5f);
+        const Mat want = algo.eval(probe);
+        EnvNormalize env2{std::make_unique<EnvMock>(1.0), false};
+        PPO2 algo2{"", env2, .99f, 128, 0.f, 1e-3f, .5f, .5f, .95f, 4, 2, 0.2f, -1.f, ""};
+        algo2.load(dir + "/graphless.pkl.0");
+        const Mat got = algo2.eval(probe);
+        REQUIRE((got - want).squaredNorm() == 0.f);
+        REQUIRE(ppo_core_tensor_size(algo2.core().get(), "model/pi_fc1/w") == 64 * 64);
     }
     std::printf(failures ? "FAILED (%d)\n" : "host_gpu_test OK\n", failures);
     return failures ? 1 : 0;

@@ -124,6 +124,11 @@ public:
         json["nminibatches"] = nminibatches; json["noptepochs"] = noptepochs; json["cliprange"] = cliprange;
         json["cliprange_vf"] = cliprange_vf; json["observation_space"] = observation_space; json["action_space"] = action_space;
         json["n_envs"] = n_envs; json["model_filename"] = model_filename;
+        // addition over the reference: a graph-less model (reset_without_graph) has no file to recover its shape from
+        if (hidden_override_[0] > 0) {
+            json["hidden1"] = hidden_override_[0];
+            json["hidden2"] = hidden_override_[1];
+        }
         std::ofstream myfile(save_path + ".json");
         if (myfile.is_open()) {
             myfile << json.dump();
@@ -159,6 +164,15 @@ public:
         }
         if (model_filename.empty()) model_filename = json["model_filename"].get<std::string>();
         else std::cout << "filename passed through CLI overrides deserialized one" << std::endl;
+        if (model_filename.empty() && hidden_override_[0] == 0) {  // written by a graph-less run: the sidecar holds the shape
+            if (!json.contains("hidden1") || !json.contains("hidden2")) {
+                std::cout << "checkpoint names no graph file and no hidden sizes" << std::endl;
+                assert(false);
+                throw std::runtime_error("checkpoint " + save_path + ".json names neither a graph file nor hidden sizes");
+            }
+            hidden_override_[0] = json["hidden1"].get<int>();
+            hidden_override_[1] = json["hidden2"].get<int>();
+        }
         reset();
         env.deserialize(json);  // after reset(): the statistics live in the (new) core
         ppo_check(ppo_core_load_checkpoint_data(core_.get(), save_path.c_str()), "Error loading checkpoint");

@@ -204,6 +204,33 @@ def test_gae_vs_oracle(core_mod, T, N):
     c.close()
 
 
+@pytest.mark.parametrize("gamma,lam", [(0.999, 1.0), (1.0, 1.0), (0.99, 0.95), (0.9999, 0.97), (0.5, 0.5)])
+@pytest.mark.parametrize("T,N,pdone", [(65536, 1, 1 / 334), (65536, 3, 1 / 334), (65536, 3, 0.0), (20000, 2, 1 / 50)])
+def test_gae_chunked_any_gamma_lambda(core_mod, gamma, lam, T, N, pdone):
+    """Few envs x long rollouts are scanned in chunks (the C2 shape, 1 x 65 536).  The carried lastgaelam must be right for
+    every gamma*lam (runner.hpp:159-191 takes them from the constructor): warm-up chunks when gamma*lam contracts, exact
+    affine carries when it is close to or equal to 1."""
+    rng = np.random.default_rng(int(gamma * 1e4) + T + N)
+    rew = (0.1 * rng.standard_normal((T, N))).astype(np.float32)
+    val = rng.standard_normal((T, N)).astype(np.float32)
+    done = (rng.random((T, N)) < pdone).astype(np.float32)
+    lv, ld = rng.standard_normal(N).astype(np.float32), np.zeros(N, np.float32)
+    c = make_core(core_mod, None, n_envs=4, n_steps=4, nminibatches=4)
+    g, l = np.float32(gamma), np.float32(lam)
+    adv, ret = c.gae(rew, val, done, lv, ld, g, l)
+    o = ol.Oracle()
+    a32, r32 = o.gae(rew, val, done, lv, ld, g, l, "f32")
+    a64, r64 = o.gae(rew, val, done, lv, ld, float(g), float(l), "f64")
+    # the fp32 sequential scan itself drifts from the exact recurrence when nothing contracts (gamma = lam = 1, no dones:
+    # a 65 536-term running sum); the kernel must be at least as close to the truth as the reference's own fp32 order is
+    ref_drift = rel_err(a32, a64)
+    assert rel_err(adv, a64) < max(TOL, 2 * ref_drift) and rel_err(ret, r64) < max(TOL, 2 * ref_drift)
+    assert rel_err(adv, a32) < max(TOL, 2 * ref_drift)
+    if float(g) * float(l) < 0.99:   # contracting: warm-up chunks reproduce the sequential fp32 scan bit for bit
+        assert np.array_equal(adv, a32) and np.array_equal(ret, r32)
+    c.close()
+
+
 def test_gae_full_size_properties(core_mod):
     """C5 size (16 M transitions): size-independent properties instead of an oracle run."""
     import torch
