@@ -39,6 +39,24 @@ LR, CLIPRANGE = 3.9e-4, 0.161
 METRIC, UNIT = "ppo_env_steps_per_sec", "env-steps/s"
 
 
+def make_config(workload, world):
+    """The `config` object of the JSON line — built by ONE function so that both arms print the same keys and values."""
+    n_envs, n_steps, h1, h2, nmb, epochs, desc = WORKLOADS[workload]
+    nbg = n_envs * n_steps * world
+    return {"workload": desc, "n_envs_per_gpu": n_envs, "n_steps": n_steps, "hidden": [h1, h2], "nminibatches": nmb,
+            "noptepochs": epochs, "global_batch": nbg, "minibatch": nbg // nmb, "parallelism": f"dp{world}",
+            "l2": "256 MiB memset between timed steps (L2 flush), outside the per-step event pairs",
+            "weights": "orthogonal random init (no graph file exists for this size)"}
+
+
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def train_flops_per_sample(O, A, h1, h2):
     fwd = 2 * (O * h1 + h1 * h2) + h2 * A + h2
     dx = 2 * (h1 * h2) + h2 * A + h2
@@ -61,14 +79,17 @@ def cpu_learner(workload, threads=0):
     return lib, o, params, (n_envs, n_steps, h1, h2, nmb, epochs)
 
 
-def time_cpu_update(workload, epochs_run, reps=1, threads=0):
-    """(seconds per full update extrapolated to all epochs, threads used, rollout s, per-epoch s)"""
+def time_cpu_update(workload, epochs_run, reps=1, threads=0, world=1):
+    """(seconds per full update extrapolated to all epochs, threads used, rollout s, per-epoch s).
+    world > 1: the GLOBAL batch of a `world`-GPU run (n_envs x world envs), as one CPU job."""
     import ctypes as C
 
     import numpy as np
 
     import oracle_lib as ol
+    threads = threads or host_threads()
     lib, o, params, (n_envs, n_steps, h1, h2, nmb, epochs) = cpu_learner(workload, threads)
+    n_envs *= world
     d = ol.LearnerDesc(ol.Dims(18, 18, h1, h2), ol.HParams(0.0007160293171182275, 0.5, 0.5, 0.9, 0.999, 1e-5), n_envs, n_steps, nmb,
                        epochs_run, 0.99, 0.95, LR, CLIPRANGE, 1, 42, 0, threads)
     L = lib.oracle_learner_create(C.byref(d), params)
@@ -89,31 +110,39 @@ def time_cpu_update(workload, epochs_run, reps=1, threads=0):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port: TF 1.14 / Eigen are not installable) on
+    ALL host cores, on the same GLOBAL config as `--impl ours --gpus N` (N x 4096 envs), each step a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
+    world = max(1, args.gpus)
     n_envs, n_steps, h1, h2, nmb, epochs, desc = WORKLOADS[args.workload]
-    n_batch = n_envs * n_steps
+    n_batch = n_envs * n_steps * world
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before libgomp initialises (torchrun set it to 1)
     # size the per-step sample so that (steps + warmup) steps end within a few minutes
-    probe_total, threads, r, e = time_cpu_update(args.workload, 1)
+    probe_total, threads, r, e = time_cpu_update(args.workload, 1, threads=threads, world=world)
     budget = 150.0 / max(args.steps + args.warmup, 1)
     epochs_run = max(1, min(epochs, int((budget - r) / max(e, 1e-9))))
-    times = []
+    runs, spent = [], 0.0
     for i in range(args.steps + args.warmup):
-        total, threads, r, e = time_cpu_update(args.workload, epochs_run)
-        if i >= args.warmup:
-            times.append(total)
+        if runs and spent + (r + epochs_run * e) > 200.0:
+            break  # bounded: never more than a few minutes in total
+        total, threads, r, e = time_cpu_update(args.workload, epochs_run, threads=threads, world=world)
+        spent += r + epochs_run * e
+        runs.append(total)
+    times = runs[args.warmup:] or runs[-1:]
     sec = statistics.mean(times) if times else probe_total
     value = n_batch / sec
-    sample = (f"per step: full rollout ({n_steps} steps x {n_envs} envs) + {epochs_run} of {epochs} epochs of {nmb} minibatches, "
-              f"train time scaled to {epochs} epochs")
+    sample = (f"per step: full rollout ({n_steps} steps x {n_envs * world} envs) + {epochs_run} of {epochs} epochs of {nmb} minibatches, "
+              f"train time scaled to {epochs} epochs; {len(times)} such steps timed")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "n_envs": n_envs, "n_steps": n_steps, "hidden": [h1, h2], "nminibatches": nmb, "noptepochs": epochs,
-                   "note": "CPU restatement of ppo_cpp (TensorFlow 1.14 / Eigen not installable); runs on rank 0 only, n_envs of ONE GPU's shard"},
-        "update_samples_per_sec": n_batch * epochs / (epochs * e),
+        "config": make_config(args.workload, world),
+        "note": "CPU restatement of ppo_cpp (TensorFlow 1.14 / Eigen not installable); rank 0 runs the GLOBAL batch of the N-GPU config on all host cores",
+        "update_samples_per_sec": n_batch / e,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -350,6 +379,19 @@ def run_ours(args):
                "path": "ppo_runner_rollout_replay (per env step: act -> D2H actions, H2D obs/rew/done -> observe) + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
                "final_losses": [float(x) for x in losses]}
 
+    # ---- multi-GPU parity, outside the timed region: the run sharded over `world` ranks against ONE GPU running the same
+    # global configuration (same Philox streams by global env id, same global permutation), and replica bit-identity
+    parity = None
+    if world > 1 and args.parity:
+        parity = multi_gpu_parity(rank, world, local, (h1, h2))
+
+    # ---- C5 microbench (BASELINE.json configs[4]): GAE / VecNormalize / loss kernels over a 16 M-transition buffer
+    microbench = None
+    if rank == 0 and world == 1 and args.microbench:
+        c.close()
+        c = None
+        microbench = c5_microbench(hbm_peak)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         total, threads, r, e = time_cpu_update(args.workload, 2)
@@ -360,21 +402,60 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "n_envs_per_gpu": n_envs, "n_steps": n_steps, "hidden": [h1, h2], "nminibatches": nmb,
-                       "noptepochs": epochs, "global_batch": n_batch_global, "minibatch": n_batch_global // nmb, "parallelism": f"dp{world}",
-                       "l2": "256 MiB memset between timed steps (L2 flush), outside the per-step event pairs",
-                       "weights": "orthogonal random init (no graph file exists for this size)"},
+            "config": make_config(args.workload, world),
             "update_samples_per_sec": upd_sps, "train_ms_per_step": ms_train / args.steps, "wall_ms_per_step": t_wall / args.steps * 1e3,
             "gpu_launches": int(ctr["kernel_launches"]), "clocks": clocks, "roofline": roofline, "kernel_ms": kernels,
             "cpu_baseline": cpu_baseline, "e2e": e2e,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if microbench is not None:
+            line["microbench"] = microbench
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    c.close()
+    if c is not None:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(rank, world, local, hidden):
+    """tests/mgpu_check.py's comparison at the bench's world size, for the bench's net: 2 updates of 48 envs per rank x 32
+    steps sharded over `world` ranks vs the same 48 x world envs on one GPU; then every rank's parameters against rank 0's."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mgpu_check
+    sharded = mgpu_check.run(world, rank, local, 48, hidden, p2p=True)
+    out = None
+    if rank == 0:
+        single = mgpu_check.run(1, 0, local, 48 * world, hidden)
+        scale = float(np.abs(single["params"]).max())
+        out = {"case": f"hidden {list(hidden)}, 48 envs/rank x 32 steps, 2 updates, peer-mailbox path",
+               "sharded_vs_single_gpu_param_rel_diff": float(np.abs(sharded["params"] - single["params"]).max() / scale),
+               "sharded_vs_single_gpu_loss_abs_diff": float(np.abs(sharded["losses"] - single["losses"]).max()),
+               "vecnorm_counts_equal": bool(sharded["stats"]["obs_count"] == single["stats"]["obs_count"])}
+    t = torch.tensor(sharded["params"], device=f"cuda:{local}")
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(torch.equal(t, ref)))
+    if rank == 0:
+        out["replicas_bit_identical"] = all(flags)
+    return out
+
+
+def c5_microbench(hbm_peak):
+    """Each kernel of the path alone over a 65 536-env x 256-step buffer (16.8 M transitions, 2.8 GB: far larger than L2),
+    CUDA events on the core's stream, algorithmic bytes against the measured HBM copy bandwidth."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import microbench_c5
+    rows = microbench_c5.measure(65536, 256, 4, 5, hbm_peak, 10)
+    return {"workload": "C5: 65536 envs x 256 steps = 16.8 M transitions, MLP [4,5]", "peak_gbs": hbm_peak,
+            "kernels": [{k: r[k] for k in ("kernel", "units_per_launch", "bytes_per_unit", "ms", "achieved_gbs", "frac")} for r in rows]}
 
 
 def main():
@@ -386,6 +467,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", dest="microbench", action="store_false")
+    ap.add_argument("--no-parity", dest="parity", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
