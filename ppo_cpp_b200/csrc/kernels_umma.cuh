@@ -6,14 +6,23 @@
 // Mapping to the hardware
 //   * one CTA = one tower (blockIdx.y: 0 = pi, 1 = V) of one tile of 128 samples (= the 128 TMEM lanes); the towers
 //     share nothing but the advantage / return inputs, so a minibatch of 8192 samples is 64 tiles x 2 towers = 128 CTAs.
-//   * every GEMM of the forward and the hand-derived backward pass runs on tcgen05.mma (kind::f16, bf16 operands,
-//     fp32 accumulators in TMEM).  fp32 parity (1e-5) is kept by splitting every fp32 operand x into three bf16
-//     pieces x = p0 + p1 + p2 (24 mantissa bits) and issuing the six products p0p0, p0p1, p1p0, p1p1, p0p2, p2p0
-//     (dropped terms are < 2^-24 relative).  kind::tf32 was measured first (tools/probe/umma_probe*.cu): it silently
-//     produces zeros for MN-major operands on sm_100a, and the dW GEMMs need MN-major views; bf16 supports both.
+//   * every GEMM of the forward and the hand-derived backward pass runs on tcgen05.mma (kind::f16, fp16 operands,
+//     fp32 accumulators in TMEM).  fp32 parity (1e-5) is kept by splitting every fp32 operand x into TWO fp16 pieces
+//     x = hi + lo (11 + 11 mantissa bits; lo is exact down to fp16's subnormal step 2^-24) and issuing the three
+//     products hi*hi, hi*lo, lo*hi (the dropped lo*lo is < 2^-22 relative).  Round 1 used three bf16 pieces and six
+//     products: twice the tensor-pipe time and 1.5x the shared-memory traffic for the same accuracy.  fp16 has a 5-bit
+//     exponent, so the operands must be O(1): observations are clipped to +-10 by VecNormalize, activations are tanh
+//     outputs, weights are O(1), and the BACKWARD tensors (which carry the 1/B of the batch mean, ~1e-4) are scaled by
+//     a power of two S with S/B in [1/16, 1/8) — exact in fp32 — and the weight gradients are multiplied by 1/S when
+//     they leave TMEM.  |x| * S/B > 65504 (a per-sample dL/dmu beyond ~5e5 / B) would overflow to inf and surface as a
+//     non-finite global norm (NaN update, as the graph's IsFinite select does for any non-finite gradient).
+//     kind::tf32 was measured first (tools/probe/umma_probe*.cu): it silently produces zeros for MN-major operands on
+//     sm_100a, and the dW GEMMs need MN-major views; kind::f16 supports both.
 //   * operands live in shared memory as [rows][64 bf16] blocks in the canonical SWIZZLE_128B layout, so the SAME bytes
 //     serve as K-major operand (forward: act x W, backward: dY x W^T) and as MN-major operand (dW = act^T x dY, reduced
-//     over the 128 samples of the tile).  dY overwrites the activation it was derived from in place.
+//     over the 128 samples of the tile).  The back-propagated dP2 / dP1 have their own blocks, so the weight-gradient
+//     GEMMs (which still read H2 / H1) never sit on the tile's critical path: they run on the tensor pipe while the CUDA
+//     cores do the next epilogue, and one commit at the end of the tile collects them.
 //   * bias gradients and the logstd gradient are column sums over samples: one extra N=8 MMA against a block whose
 //     first row is ones.  The V head (N = 1) is a dot product in the epilogue; its weight gradient is again an N=8 MMA.
 //   * weight gradients accumulate in TMEM across the tiles a CTA processes and are written once to the CTA's slab.
@@ -21,10 +30,11 @@
 //     32-column half (w>>2) of a 64-wide accumulator; activations stay in registers between forward and backward.
 //   * accuracy: the tensor core truncates (RZ) at every accumulation, a bias that grows with the number of MMAs chained
 //     into one accumulator and that the value loss amplifies (v - R cancels over the batch).  The leading product p0p0
-//     therefore accumulates alone, the five small cross products go to a second TMEM accumulator (2^-8 of the
-//     magnitude, so 2^-8 of the truncation error) and the epilogue adds the two in fp32 (round to nearest).
+//     therefore accumulates alone, the two small cross products go to a second TMEM accumulator (2^-11 of the
+//     magnitude, so 2^-11 of the truncation error) and the epilogue adds the two in fp32 (round to nearest).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "kernels_misc.cuh"
 #include "kernels_mlp2.cuh"
@@ -37,19 +47,22 @@ constexpr int NTH = 256;  // threads per CTA
 constexpr int HID = 64;   // hidden width handled by this family
 
 // ---- shared memory map (bytes from a 1024-aligned base)
-constexpr uint32_t ACT_PIECE = TM * 128;        // [128 x 64] bf16 = 16 KB
-constexpr uint32_t ACT_BLOCK = 3 * ACT_PIECE;   // three pieces
-constexpr uint32_t W0_PIECE = 32 * 128;         // [32 x 64] bf16 (rows: O inputs, bias row, zero padding)
+constexpr int NP = 2;                           // fp16 pieces per fp32 operand value
+constexpr uint32_t ACT_PIECE = TM * 128;        // [128 x 64] fp16 = 16 KB
+constexpr uint32_t ACT_BLOCK = NP * ACT_PIECE;  // both pieces
+constexpr uint32_t W0_PIECE = 32 * 128;         // [32 x 64] fp16 (rows: O inputs, bias row, zero padding)
 constexpr uint32_t W1_PIECE = 64 * 128;         // [64 x 64]
 constexpr uint32_t WP_PIECE = 64 * 128;         // [64 x 64], columns >= A are zero
-constexpr uint32_t ROW8_PIECE = 2 * 1024;       // [8 x 128] bf16, K-major operand over the 128 samples
+constexpr uint32_t ROW8_PIECE = 2 * 1024;       // [8 x 128] fp16, K-major operand over the 128 samples
 constexpr uint32_t OFF_H1 = 0;
 constexpr uint32_t OFF_H2 = OFF_H1 + ACT_BLOCK;
 constexpr uint32_t OFF_Y = OFF_H2 + ACT_BLOCK;  // X' (obs + ones column), later [dMU | dLS], later X' again
-constexpr uint32_t OFF_W0 = OFF_Y + ACT_BLOCK;
-constexpr uint32_t OFF_W1 = OFF_W0 + 3 * W0_PIECE;
-constexpr uint32_t OFF_WP = OFF_W1 + 3 * W1_PIECE;   // pi head weights; the V tower keeps its dv rows here
-constexpr uint32_t OFF_ONES = OFF_WP + 3 * WP_PIECE;
+constexpr uint32_t OFF_D2 = OFF_Y + ACT_BLOCK;  // dP2 = dL/d(pre-activation of layer 1)
+constexpr uint32_t OFF_D1 = OFF_D2 + ACT_BLOCK; // dP1
+constexpr uint32_t OFF_W0 = OFF_D1 + ACT_BLOCK;
+constexpr uint32_t OFF_W1 = OFF_W0 + NP * W0_PIECE;
+constexpr uint32_t OFF_WP = OFF_W1 + NP * W1_PIECE;   // pi head weights; the V tower keeps its dv rows here
+constexpr uint32_t OFF_ONES = OFF_WP + NP * WP_PIECE;
 constexpr uint32_t OFF_F32 = OFF_ONES + ROW8_PIECE;  // fp32 vectors
 constexpr uint32_t F32_B1 = 0, F32_BH = 64, F32_WV = 96, F32_SD = 160, F32_LS = 192, F32_MISC = 224, F32_PV = 256,
                    F32_DV = 512, F32_RED = 640, F32_ISD = 704, F32_COUNT = 736;
@@ -75,10 +88,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = f32, A = B = bf16
+// instruction descriptor: D = f32 (bits 4-5 = 1), A = B = fp16 (format fields 7-9 / 10-12 = 0)
 __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // One operand of a GEMM: descriptor of piece 0 / k-step 0 plus strides (in 16-byte units).
@@ -96,15 +108,41 @@ __device__ __forceinline__ Operand op_mnmajor(uint32_t base, uint32_t piece_byte
     return Operand{make_desc(base, (uint32_t)((rows >> 3) * 1024), 1024), piece_bytes >> 4, 2048 >> 4, 8192 >> 4};
 }
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
+// ---- bf16 x 3 flavour of the operand helpers, used by the W family (kernels_wide.cuh): three bf16 pieces per fp32 value,
+// six products.  Activations of a wide layer are not bounded the way the U family's fp16 scheme needs.
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+    return make_idesc(M, N, a_mn, b_mn) | (1u << 7) | (1u << 10);  // A = B = bf16
+}
+__device__ __forceinline__ void split_pair3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+    p0 = *reinterpret_cast<uint32_t*>(&b);
+    const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+    b = __floats2bfloat162_rn(r0, r1);
+    p1 = *reinterpret_cast<uint32_t*>(&b);
+    const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
+    b = __floats2bfloat162_rn(s0, s1);
+    p2 = *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ void store_chunk3(uint8_t* block, uint32_t piece_bytes, uint32_t off, const float* x) {
+    uint4 q0, q1, q2;
+    split_pair3(x[0], x[1], q0.x, q1.x, q2.x);
+    split_pair3(x[2], x[3], q0.y, q1.y, q2.y);
+    split_pair3(x[4], x[5], q0.z, q1.z, q2.z);
+    split_pair3(x[6], x[7], q0.w, q1.w, q2.w);
+    *reinterpret_cast<uint4*>(block + off) = q0;
+    *reinterpret_cast<uint4*>(block + piece_bytes + off) = q1;
+    *reinterpret_cast<uint4*>(block + 2 * piece_bytes + off) = q2;
+}
+
 // D (+)= A * B with split operands: the leading product goes to `dm`, the cross products to `dc`.
-// NPB == 3: six products (both operands in three pieces); NPB == 1: B is exact in bf16 (ones), three products.
+// NPB == 2: both operands in two pieces, three products; NPB == 1: B is exact in fp16 (ones), two products.
 template <int NPB, int KSTEPS>
 __device__ __forceinline__ void issue_gemm(uint32_t dm, uint32_t dc, const Operand& A, const Operand& B, uint32_t idesc, bool accumulate) {
     const uint32_t acc0 = accumulate ? 1u : 0u;
@@ -113,16 +151,12 @@ __device__ __forceinline__ void issue_gemm(uint32_t dm, uint32_t dc, const Opera
         const uint64_t a = A.desc + (uint64_t)((ks >> 2) * A.k_hi + (ks & 3) * A.k_lo);
         const uint64_t b = B.desc + (uint64_t)((ks >> 2) * B.k_hi + (ks & 3) * B.k_lo);
         const uint32_t acc = ks ? 1u : acc0;
-        mma_bf16(dm, a, b, idesc, acc);
-        if (NPB == 3) {
-            mma_bf16(dc, a, b + B.piece, idesc, acc);
-            mma_bf16(dc, a + A.piece, b, idesc, 1u);
-            mma_bf16(dc, a + A.piece, b + B.piece, idesc, 1u);
-            mma_bf16(dc, a, b + 2 * B.piece, idesc, 1u);
-            mma_bf16(dc, a + 2 * A.piece, b, idesc, 1u);
+        mma_f16(dm, a, b, idesc, acc);
+        if (NPB == 2) {
+            mma_f16(dc, a, b + B.piece, idesc, acc);
+            mma_f16(dc, a + A.piece, b, idesc, 1u);
         } else {
-            mma_bf16(dc, a + A.piece, b, idesc, acc);
-            mma_bf16(dc, a + 2 * A.piece, b, idesc, 1u);
+            mma_f16(dc, a + A.piece, b, idesc, acc);
         }
     }
 }
@@ -179,33 +213,23 @@ __device__ __forceinline__ void tmem_ld8_sum(uint32_t tmain, uint32_t tcross, fl
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
 }
 
-// x0, x1 -> three packed bf16 pairs (x0 in the low half = lower address)
-__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-    __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
-    p0 = *reinterpret_cast<uint32_t*>(&b);
-    const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
-    b = __floats2bfloat162_rn(r0, r1);
-    p1 = *reinterpret_cast<uint32_t*>(&b);
-    const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
-    b = __floats2bfloat162_rn(s0, s1);
-    p2 = *reinterpret_cast<uint32_t*>(&b);
+// x0, x1 -> two packed fp16 pairs hi, lo with x = hi + lo (x0 in the low half = lower address)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p0, uint32_t& p1) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    p0 = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    p1 = *reinterpret_cast<const uint32_t*>(&l);
 }
-// eight consecutive columns (one 16-byte chunk) -> the three pieces of a block
+// eight consecutive columns (one 16-byte chunk) -> the two pieces of a block
 __device__ __forceinline__ void store_chunk(uint8_t* block, uint32_t piece_bytes, uint32_t off, const float* x) {
-    uint4 q0, q1, q2;
-    split_pair(x[0], x[1], q0.x, q1.x, q2.x);
-    split_pair(x[2], x[3], q0.y, q1.y, q2.y);
-    split_pair(x[4], x[5], q0.z, q1.z, q2.z);
-    split_pair(x[6], x[7], q0.w, q1.w, q2.w);
+    uint4 q0, q1;
+    split_pair(x[0], x[1], q0.x, q1.x);
+    split_pair(x[2], x[3], q0.y, q1.y);
+    split_pair(x[4], x[5], q0.z, q1.z);
+    split_pair(x[6], x[7], q0.w, q1.w);
     *reinterpret_cast<uint4*>(block + off) = q0;
     *reinterpret_cast<uint4*>(block + piece_bytes + off) = q1;
-    *reinterpret_cast<uint4*>(block + 2 * piece_bytes + off) = q2;
-}
-__device__ __forceinline__ void zero_chunk(uint8_t* block, uint32_t piece_bytes, uint32_t off) {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(block + off) = z;
-    *reinterpret_cast<uint4*>(block + piece_bytes + off) = z;
-    *reinterpret_cast<uint4*>(block + 2 * piece_bytes + off) = z;
 }
 // 32 consecutive columns [32 * half, 32 * half + 32) of row r of an activation block
 __device__ __forceinline__ void store_row32(uint8_t* block, int r, int half, const float* x) {
@@ -250,6 +274,46 @@ struct EpochArgs {
     const float2* mbstats;  // [M]
     float* loss_rows;       // [M][5]
     ReduceAdamArgs ra;
+    // MODE 2 (LL hand-overs): slabs [G][PS], per-block sums of squares [nblk][2] (a double as two words), parameters [P];
+    // ll_seq: device-resident sequence number (one per minibatch ever trained), so that launches replay from a CUDA graph
+    uint2* ll_slab;
+    uint2* ll_sq;
+    uint2* ll_par;
+    unsigned* ll_seq;
+};
+
+// ---- LL consumers: all loads of a group are issued first, then checked together; a stale word re-polls the whole group
+// (intra-GPU words: gpu scope is enough; the cross-GPU mailbox words of sync_prims.cuh stay volatile = system scope)
+__device__ __forceinline__ uint4 ll_load2(const uint2* p) {  // two adjacent LL words, p 16-byte aligned
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ll_load1(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ll_store1(uint2* p, unsigned data, unsigned seq) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
+}
+// bounded spinning: after ~2 s (a CTA that never arrives) the error flag is raised and the poll loops give up
+struct LLSpin {
+    unsigned* err;
+    unsigned long long t0;
+    unsigned spins;
+    __device__ __forceinline__ explicit LLSpin(unsigned* e) : err(e), t0(0), spins(0) {}
+    __device__ __forceinline__ bool giveup() {
+        if (((++spins) & 0xffu) == 0u) {
+            if (t0 == 0) t0 = globaltimer_ns();
+            if (*reinterpret_cast<volatile unsigned*>(err)) return true;
+            if (globaltimer_ns() - t0 > 2000000000ull) {
+                *err = 1u;
+                return true;
+            }
+        }
+        return false;
+    }
 };
 
 #define UMMA_PROF()                                                                                              \
@@ -257,8 +321,203 @@ struct EpochArgs {
         if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 32) a.prof[tower * 32 + prof_i++] = clock64();      \
     } while (0)
 
-template <int O, int A, bool PERSIST>
+// MODE 2: the gradient step without grid barriers.  Block `blk` of `nblk` (256 threads) owns the 64-column chunks blk and
+// blk + nblk.  (1) poll the G slab rows of its chunks (LL words written by the tile CTAs' flush) and sum them in the same
+// fixed order as reduce_adam_device; (2) multi-GPU: the same mailbox exchange; (3) publish the chunk's sum of squares as two
+// LL words, poll everybody's, same fixed-order norm; (4) clip + TF ApplyAdam on its columns, parameters stored plainly (for
+// the kernels that follow the epoch) AND as LL words (for the staging of the next minibatch).  Arithmetic and summation
+// order are those of reduce_adam_device: results are bit-identical to the barrier path.
+__device__ __forceinline__ void reduce_adam_ll(const EpochArgs& ep, int blk, int nblk, unsigned seq, unsigned mseq, float b1p, float b2p,
+                                               float* loss_row, long long* prof = nullptr, long long* prof_all = nullptr) {
+    int pi_ = 0;
+#define RL_PROF()                                                                                   \
+    do {                                                                                            \
+        if (prof_all && threadIdx.x == 0 && pi_ < 8) prof_all[blk * 8 + pi_] = (long long)globaltimer_ns(); \
+        if (prof && threadIdx.x == 0 && pi_ < 8) prof[pi_] = clock64();                              \
+        ++pi_;                                                                                      \
+    } while (0)
+    RL_PROF();
+    __shared__ float part[4][64];
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    __shared__ float s_loss[8];
+    const ReduceAdamArgs& r = ep.ra;
+    const AdamArgs& a = r.adam;
+    const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int nchunks = (r.PS + 63) >> 6;
+    const int world = r.mbox.world;
+    const int loss_chunk = a.P >> 6;  // holds columns P .. P+4 (the host checks (P & 63) + 5 <= 64)
+    float gsum[2] = {0.f, 0.f};
+    float acc[2] = {0.f, 0.f};
+    {
+        // light pre-wait (one word per thread): the loss sums are the LAST words a tile CTA's flush stores, so poll those of
+        // the 2 x G producers first.  Polling the payload words themselves from every thread (32 loads each, 8 MB per
+        // round over the chip) saturates L2 and delays the very stores it waits for (measured: 3x slower).
+        LLSpin spin(r.mbox.err);
+        if (threadIdx.x < 2 * r.G) {
+            const uint2* p = ep.ll_slab + (size_t)(threadIdx.x >> 1) * r.PS + a.P + ((threadIdx.x & 1) ? L_VF : L_PG);
+            while (ll_load1(p).y != seq && !spin.giveup()) {
+            }
+        }
+        __syncthreads();
+        while (true) {
+            uint2 w[2][16];
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = (blk + j * nblk) * 64 + lane_c;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int g = rg + 4 * u;
+                    w[j][u] = (c < r.PS && g < r.G) ? ll_load1(ep.ll_slab + (size_t)g * r.PS + c) : make_uint2(0u, seq);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int u = 0; u < 16; ++u) ok = ok && w[j][u].y == seq;
+            if (ok || spin.giveup()) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc[j] += __uint_as_float(w[j][u].x);
+                break;
+            }
+        }
+    }
+    RL_PROF();  // slab rows arrived
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int chunk = blk + j * nblk;
+        if (chunk >= nchunks) break;  // block-uniform
+        const int c = chunk * 64 + lane_c;
+        __syncthreads();
+        part[rg][lane_c] = acc[j];
+        __syncthreads();
+        if (rg == 0) {
+            const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
+            gsum[j] = (float)t;
+            if (world > 1 && c < r.PS)
+                for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, mseq, r.mbox.rank) + c, __float_as_uint(gsum[j]), mseq);
+        }
+    }
+    if (world > 1 && rg == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int chunk = blk + j * nblk;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < r.PS) {
+                float t = 0.f;
+                for (int src = 0; src < world; ++src) t += __uint_as_float(r.mbox.ll_wait(mseq, src, (size_t)c));
+                gsum[j] = t;
+            }
+        }
+    }
+    if (rg == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int chunk = blk + j * nblk;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < r.PS) r.grad[c] = gsum[j];
+            if (c < a.P) q += (double)gsum[j] * (double)gsum[j];
+            if (chunk == loss_chunk && lane_c >= (a.P & 63) && lane_c < (a.P & 63) + 8) s_loss[lane_c - (a.P & 63)] = gsum[j];
+        }
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double sq = red[0] + red[1];  // warps 0, 1 hold rg == 0
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sq);
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ep.ll_sq + 2 * blk), "r"((unsigned)bits), "r"(seq),
+                     "r"((unsigned)(bits >> 32)), "r"(seq)
+                     : "memory");
+    }
+    RL_PROF();  // chunk sums + sum of squares published
+    // Adam state of this thread's columns: only this thread ever touches it
+    float am[2], av[2], ap[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = (blk + j * nblk) * 64 + lane_c;
+        const bool mine = rg == 0 && c < a.P;
+        am[j] = mine ? __ldcg(a.m + c) : 0.f;
+        av[j] = mine ? __ldcg(a.v + c) : 0.f;
+        ap[j] = mine ? __ldcg(a.params + c) : 0.f;
+    }
+    if (threadIdx.x < 32) {
+        double ss = 0.0;
+        LLSpin spin(r.mbox.err);
+        // nblk <= 128: up to four entries per lane, all four loads in flight at once; same lane order as reduce_adam_device
+        while (true) {
+            uint4 w[4];
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = threadIdx.x + 32 * u;
+                w[u] = b < nblk ? ll_load2(ep.ll_sq + 2 * b) : make_uint4(0u, seq, 0u, seq);
+                ok = ok && w[u].y == seq && w[u].w == seq;
+            }
+            if (ok || spin.giveup()) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (threadIdx.x + 32 * u < nblk)
+                        ss += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | (unsigned long long)w[u].x));
+                break;
+            }
+        }
+        ss = warp_sum(ss);  // same fixed-order combine as reduce_adam_device
+        if (threadIdx.x == 0) {
+            const float gnorm = (float)sqrt(ss);
+            const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
+            float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
+            if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
+            s_scale = scale;
+            if (blk == 0) *a.gnorm_out = gnorm;
+        }
+    }
+    __syncthreads();
+    RL_PROF();  // everybody's sums of squares arrived: norm known
+    if (blk == loss_chunk % nblk && threadIdx.x == 0) {
+        loss_row[0] = s_loss[L_PG] * a.invB;
+        loss_row[1] = 0.5f * (s_loss[L_VF] * a.invB);
+        loss_row[2] = s_loss[L_ENT] * a.inv_world;
+        loss_row[3] = 0.5f * (s_loss[L_KL] * a.invB);
+        loss_row[4] = s_loss[L_CLIP] * a.invB;
+    }
+    if (rg == 0) {
+        const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int chunk = blk + j * nblk;
+            if (chunk >= nchunks) break;
+            const int c = chunk * 64 + lane_c;
+            if (c < a.P) {
+                const float g = __fmul_rn(gsum[j], s_scale);
+                float m = am[j], v = av[j];
+                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+                const float th = __fsub_rn(ap[j], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+                a.m[c] = m;
+                a.v[c] = v;
+                a.params[c] = th;
+                ll_store1(ep.ll_par + c, __float_as_uint(th), seq);
+            }
+        }
+    }
+    RL_PROF();  // Adam done, parameters published
+#undef RL_PROF
+}
+
+// MODE 0: one minibatch per launch (slabs are reduced by another kernel).  MODE 1: persistent epoch, grid barriers.
+// MODE 2: persistent epoch, barrier-free: every cross-CTA hand-over is an LL word (payload + sequence number in one 8-byte
+// store, polled by the consumer): slabs -> chunk owners, chunk sums of squares -> everybody, updated parameters -> everybody.
+template <int O, int A, int MODE>
 __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, const EpochArgs ep) {
+    constexpr bool PERSIST = MODE != 0;
+    constexpr bool LL = MODE == 2;
     static_assert(O % 2 == 0 && O >= 2 && O <= 30 && A % 2 == 0 && A >= 2 && A <= 32, "unsupported obs/act width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -276,8 +535,12 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     uint8_t* sH2 = smem + OFF_H2;
     uint8_t* sY = smem + OFF_Y;
     float* f32 = reinterpret_cast<float*>(smem + OFF_F32);
-    const uint32_t barA = sbase + OFF_BAR, barB = barA + 8;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+    // barA: the GEMM the next epilogue waits for; barB: the MMAs that read [dMU | dLS] out of Y (pi tower, before X' returns
+    // there); barC: everything a tile issued (weight gradients included), waited once at the tile's end
+    const uint32_t barA = sbase + OFF_BAR, barB = barA + 8, barC = barA + 16;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+    uint8_t* sD2 = smem + OFF_D2;
+    uint8_t* sD1 = smem + OFF_D1;
     const int ntiles = (a.count + TM - 1) / TM;
 
     // ---------------------------------------------------------------- inputs of the first tile (latency overlaps the setup)
@@ -321,6 +584,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barB));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barC));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -328,16 +592,17 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // constant operand blocks: the V tower's dv rows (row 0 is rewritten per tile, rows 1..7 stay zero) and the ones block
-    // (row 0 of each 8-row group = 1.0 = bf16 0x3F80, rows 1..7 = 0)
+    // (row 0 of each 8-row group = 1.0 = fp16 0x3C00, rows 1..7 = 0)
     if (tower != 0)
-        for (int i = tid; i < 3 * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < NP * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
     if (tid < (int)ROW8_PIECE / 16) {
-        const uint32_t v = ((tid & 63) < 8) ? 0x3F803F80u : 0u;
+        const uint32_t v = ((tid & 63) < 8) ? 0x3C003C00u : 0u;
         reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
     }
     // persistent state: grid barrier generation, mailbox sequence number, Adam's beta powers (every CTA tracks them)
     GridBarrier bar{PERSIST ? ep.ra.bar_ctr : nullptr, 2u * gridDim.x, PERSIST ? *ep.ra.bar_gen : 0u};
     unsigned mseq = (PERSIST && ep.ra.mbox.world > 1) ? *ep.ra.mbox_seq : 0u;
+    const unsigned ll_seq0 = LL ? *ep.ll_seq : 0u;  // minibatch mb of this launch hands over with sequence number ll_seq0 + mb + 1
     float b1p = PERSIST ? ep.ra.adam.bpow_in[0] : 0.f, b2p = PERSIST ? ep.ra.adam.bpow_in[1] : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -352,6 +617,9 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     const Operand opH1_mn = op_mnmajor(sbase + OFF_H1, ACT_PIECE, TM);
     const Operand opH2_k = op_kmajor(sbase + OFF_H2, ACT_PIECE, TM);
     const Operand opH2_mn = op_mnmajor(sbase + OFF_H2, ACT_PIECE, TM);
+    const Operand opD2_k = op_kmajor(sbase + OFF_D2, ACT_PIECE, TM);
+    const Operand opD2_mn = op_mnmajor(sbase + OFF_D2, ACT_PIECE, TM);
+    const Operand opD1_mn = op_mnmajor(sbase + OFF_D1, ACT_PIECE, TM);
     const Operand opW0_f = op_mnmajor(sbase + OFF_W0, W0_PIECE, 32);    // forward: B(n = out, k = in)
     const Operand opW1_f = op_mnmajor(sbase + OFF_W1, W1_PIECE, 64);
     const Operand opW1_b = op_kmajor(sbase + OFF_W1, W1_PIECE, 64);     // backward: B(n = in, k = out)
@@ -367,7 +635,12 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     const uint32_t id_s8 = make_idesc(64, 8, 1, 0);       // column sums / V head: MN-major A x K-major [8 x 128] B
 
     const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
-    uint32_t phA = 0, phB = 0;
+    // the backward tensors (which carry the 1/B of the batch mean) are stored times a power of two so that they are O(1) as
+    // fp16 operands (see the header); exponents are chosen per minibatch when the weights are staged
+    int invB_exp;
+    (void)frexpf(a.invB, &invB_exp);  // invB = m * 2^e, m in [0.5, 1)
+    int k_w0 = 0, k_w1 = 0, k_hd = 0, n_s = 0;
+    uint32_t phA = 0, phB = 0, phC = 0;
     float l_0, l_1, l_2, l_dbv;  // pi: pg, kl, clipfrac sums; V: vf sum, dbv (per minibatch)
     bool accw;
     float h1r[32], h2r[32];
@@ -376,13 +649,93 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
 #define LDW(p) (PERSIST ? __ldcg(p) : __ldg(p))  // the persistent kernel re-reads parameters that it updates itself
     for (int mb = 0; mb < n_mb; ++mb) {
         {
-            // weights -> three bf16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
+            // weights -> two fp16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
             const float* P = a.params;
             const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
             const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
             const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
             float4 w1v[2][2], w0v[2];
             float wpv[8];
+            float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
+            if (LL && mb > 0) {
+                // the parameters as LL words, published by the chunk owners' Adam of the previous minibatch (sequence number
+                // ll_seq0 + mb): all loads in flight at once, one check, stale words re-poll the group
+                const unsigned pseq = ll_seq0 + (unsigned)mb;
+                const uint2* Q = ep.ll_par;
+                const int o_w1 = d.off[tower ? T_VF_FC1_W : T_PI_FC1_W], o_w0 = d.off[tower ? T_VF_FC0_W : T_PI_FC0_W],
+                          o_b0 = d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+                LLSpin spin(ep.ra.mbox.err);
+                {   // light pre-wait: the last word of every 64-column chunk (one word per thread) before the bulk loads
+                    const int nch = (d.P + 63) >> 6;
+                    if (tid < nch) {
+                        const uint2* pw = Q + min(tid * 64 + 63, d.P - 1);
+                        while (ll_load1(pw).y != pseq && !spin.giveup()) {
+                        }
+                    }
+                    __syncthreads();
+                }
+                while (true) {
+                    uint4 r1[2][4], r0[4];
+                    uint2 rp[8], rb1, rwv, rls, rbh, rbv;
+                    const uint4 z4 = make_uint4(0u, pseq, 0u, pseq);
+                    const uint2 z2 = make_uint2(0u, pseq);
+    #pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int e = tid + NTH * i, r = e >> 3, j = e & 7;
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) r1[i][k] = ll_load2(Q + o_w1 + r * HID + 8 * j + 2 * k);
+                    }
+                    {
+                        const int r = tid >> 3, j = tid & 7;
+                        const int idx = r < O ? (o_w0 + r * HID + 8 * j) : (o_b0 + 8 * j);
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) r0[k] = (r <= O) ? ll_load2(Q + idx + 2 * k) : z4;
+                    }
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) rp[k] = z2;
+                    if (tower == 0) {
+                        const int r = tid >> 2, j = tid & 3;
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (8 * j + k < A) rp[k] = ll_load1(Q + d.off[T_PI_W] + r * A + 8 * j + k);
+                    }
+                    rb1 = rwv = rls = rbh = rbv = z2;
+                    if (tid < HID) {
+                        rb1 = ll_load1(Q + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
+                        rwv = ll_load1(Q + d.off[T_VF_W] + tid);
+                    }
+                    if (tid < 32) {
+                        if (tid < A) {
+                            rls = ll_load1(Q + d.off[T_LOGSTD] + tid);
+                            rbh = ll_load1(Q + d.off[T_PI_B] + tid);
+                        }
+                        rbv = ll_load1(Q + d.off[T_VF_B]);
+                    }
+                    bool ok = rb1.y == pseq && rwv.y == pseq && rls.y == pseq && rbh.y == pseq && rbv.y == pseq;
+    #pragma unroll
+                    for (int i = 0; i < 2; ++i)
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) ok = ok && r1[i][k].y == pseq && r1[i][k].w == pseq;
+    #pragma unroll
+                    for (int k = 0; k < 4; ++k) ok = ok && r0[k].y == pseq && r0[k].w == pseq;
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) ok = ok && rp[k].y == pseq;
+                    if (ok || spin.giveup()) {
+    #pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            w1v[i][0] = make_float4(__uint_as_float(r1[i][0].x), __uint_as_float(r1[i][0].z), __uint_as_float(r1[i][1].x), __uint_as_float(r1[i][1].z));
+                            w1v[i][1] = make_float4(__uint_as_float(r1[i][2].x), __uint_as_float(r1[i][2].z), __uint_as_float(r1[i][3].x), __uint_as_float(r1[i][3].z));
+                        }
+                        w0v[0] = make_float4(__uint_as_float(r0[0].x), __uint_as_float(r0[0].z), __uint_as_float(r0[1].x), __uint_as_float(r0[1].z));
+                        w0v[1] = make_float4(__uint_as_float(r0[2].x), __uint_as_float(r0[2].z), __uint_as_float(r0[3].x), __uint_as_float(r0[3].z));
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k) wpv[k] = __uint_as_float(rp[k].x);
+                        b1 = __uint_as_float(rb1.x); wv = __uint_as_float(rwv.x); ls = __uint_as_float(rls.x);
+                        bh = __uint_as_float(rbh.x); bv = __uint_as_float(rbv.x);
+                        break;
+                    }
+                }
+            } else {
     #pragma unroll
             for (int i = 0; i < 2; ++i) {  // W1: 64 rows x 8 chunks = 512 tasks
                 const int e = tid + NTH * i, r = e >> 3, j = e & 7;
@@ -396,13 +749,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 w0v[0] = nz ? LDW(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 w0v[1] = nz ? LDW(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+    #pragma unroll
+            for (int k = 0; k < 8; ++k) wpv[k] = 0.f;
             if (tower == 0) {  // Wpi [64 x A] -> chunks 0..3 of every row (columns >= A zero): 256 tasks
                 const int r = tid >> 2, j = tid & 3;
                 const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
     #pragma unroll
                 for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? LDW(src + k) : 0.f;
             }
-            float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
             if (tid < HID) {
                 b1 = LDW(P + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
                 wv = LDW(P + d.off[T_VF_W] + tid);
@@ -412,20 +766,76 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 bh = tid < A ? LDW(P + d.off[T_PI_B] + tid) : 0.f;
                 bv = LDW(P + d.off[T_VF_B]);
             }
+            }
+            // ---- block floating point: every weight matrix is stored times a power of two that brings its largest entry into
+            // [1, 2) (exact in fp32; undone in the fp32 epilogues), so that both fp16 pieces of the entries that matter are
+            // normal numbers whatever the scale of the matrix (the policy head starts at 1e-3, GRAPH:4843).  The same powers
+            // of two ride along the backward pass (dH2 = dMU * (Wpi * 2^k)^T ...) and keep dP2 / dP1 at O(1) as well.
+            {
+                float mx[4] = {0.f, 0.f, 0.f, -3.0e38f};
+                mx[0] = fmaxf(fmaxf(fmaxf(fabsf(w0v[0].x), fabsf(w0v[0].y)), fmaxf(fabsf(w0v[0].z), fabsf(w0v[0].w))),
+                              fmaxf(fmaxf(fabsf(w0v[1].x), fabsf(w0v[1].y)), fmaxf(fabsf(w0v[1].z), fabsf(w0v[1].w))));
+    #pragma unroll
+                for (int i = 0; i < 2; ++i)
+    #pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        mx[1] = fmaxf(mx[1], fmaxf(fmaxf(fabsf(w1v[i][h].x), fabsf(w1v[i][h].y)), fmaxf(fabsf(w1v[i][h].z), fabsf(w1v[i][h].w))));
+                if (tower == 0) {
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) mx[2] = fmaxf(mx[2], fabsf(wpv[k]));
+                } else if (tid < HID) {
+                    mx[2] = fabsf(wv);
+                }
+                if (tid < A) mx[3] = -ls;  // max(-logstd) = -min(logstd)
+    #pragma unroll
+                for (int k = 0; k < 4; ++k)
+    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+                if (lane == 0) {
+    #pragma unroll
+                    for (int k = 0; k < 4; ++k) f32[F32_RED + warp * 4 + k] = mx[k];
+                }
+                __syncthreads();
+    #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float m = f32[F32_RED + k];
+                    for (int w = 1; w < NTH / 32; ++w) m = fmaxf(m, f32[F32_RED + w * 4 + k]);
+                    mx[k] = m;
+                }
+                auto pow2_to_unit = [](float m) {  // k with m * 2^k in [1, 2); 0 for a zero / non-finite matrix
+                    int e = 0;
+                    if (!(m > 0.f) || !isfinite(m)) return 0;
+                    (void)frexpf(m, &e);
+                    return max(-24, min(24, 1 - e));
+                };
+                k_w0 = pow2_to_unit(mx[0]);
+                k_w1 = pow2_to_unit(mx[1]);
+                k_hd = pow2_to_unit(mx[2]);
+                int e_sig = 0;
+                (void)frexpf(expf(-mx[3]), &e_sig);           // sigma_min = f * 2^e, f in [0.5, 1)
+                const int k_sig = max(-24, min(8, e_sig - 1));  // 2^k_sig <= sigma_min
+                // backward scale S = 2^n_s: pi  S * invB / sigma_min in (1/8, 1/2];  V  S * invB in [4, 8)
+                n_s = tower == 0 ? (-invB_exp + k_sig - 1) : (-invB_exp + 3);
+            }
+            const float s_w0 = ldexpf(1.f, k_w0), s_w1 = ldexpf(1.f, k_w1), s_hd = ldexpf(1.f, k_hd);
             // ---- consume
     #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int e = tid + NTH * i, r = e >> 3, j = e & 7;
-                const float x[8] = {w1v[i][0].x, w1v[i][0].y, w1v[i][0].z, w1v[i][0].w, w1v[i][1].x, w1v[i][1].y, w1v[i][1].z, w1v[i][1].w};
+                const float x[8] = {w1v[i][0].x * s_w1, w1v[i][0].y * s_w1, w1v[i][0].z * s_w1, w1v[i][0].w * s_w1,
+                                    w1v[i][1].x * s_w1, w1v[i][1].y * s_w1, w1v[i][1].z * s_w1, w1v[i][1].w * s_w1};
                 store_chunk(smem + OFF_W1, W1_PIECE, chunk_off(r, j), x);
             }
             {
                 const int r = tid >> 3, j = tid & 7;
-                const float x[8] = {w0v[0].x, w0v[0].y, w0v[0].z, w0v[0].w, w0v[1].x, w0v[1].y, w0v[1].z, w0v[1].w};
+                const float x[8] = {w0v[0].x * s_w0, w0v[0].y * s_w0, w0v[0].z * s_w0, w0v[0].w * s_w0,
+                                    w0v[1].x * s_w0, w0v[1].y * s_w0, w0v[1].z * s_w0, w0v[1].w * s_w0};
                 store_chunk(smem + OFF_W0, W0_PIECE, chunk_off(r, j), x);
             }
             if (tower == 0) {
                 const int r = tid >> 2, j = tid & 3;
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) wpv[k] *= s_hd;
                 store_chunk(smem + OFF_WP, WP_PIECE, chunk_off(r, j), wpv);
             }
             if (tid < HID) {
@@ -444,6 +854,12 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 }
             }
         }
+        // epilogue factors of this minibatch (exact powers of two)
+        const float u_w0 = ldexpf(1.f, -k_w0), u_w1 = ldexpf(1.f, -k_w1), u_hd = ldexpf(1.f, -k_hd), s_hd_v = ldexpf(1.f, k_hd);
+        const float S_b = ldexpf(1.f, n_s);                      // backward tensors are stored times S_b
+        const float un_hd = ldexpf(1.f, -n_s);                   // head-level accumulators (dWpi, column sums, dWv)
+        const float un_w1 = ldexpf(1.f, -n_s - k_hd);            // dW1, db1: carry the head matrix's power of two as well
+        const float un_w0 = ldexpf(1.f, -n_s - k_hd - k_w1);     // dW0': ... and W1's
         xin.store(sY, gr, gh);
         fence_async_smem();
         tc_fence_before();
@@ -466,7 +882,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<3, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opW0_f, id_f64, false);
+                issue_gemm<2, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opW0_f, id_f64, false);
                 umma_commit(barA);
             }
             __syncwarp();
@@ -478,7 +894,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float v[32];
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h1r[j] = tanhf(v[j]);
+            for (int j = 0; j < 32; ++j) h1r[j] = tanhf(v[j] * u_w0);
             store_row32(sH1, row, half, h1r);
         }
         fence_async_smem();
@@ -490,7 +906,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH1_k, opW1_f, id_f64, false);
+                issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH1_k, opW1_f, id_f64, false);
                 umma_commit(barA);
             }
             __syncwarp();
@@ -511,7 +927,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float pv = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                h2r[j] = tanhf(v[j] + f32[F32_B1 + 32 * half + j]);
+                h2r[j] = tanhf(fmaf(v[j], u_w1, f32[F32_B1 + 32 * half + j]));
                 pv = fmaf(h2r[j], f32[F32_WV + 32 * half + j], pv);
             }
             store_row32(sH2, row, half, h2r);
@@ -527,7 +943,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opWP_f, id_f32, false);
+                    issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opWP_f, id_f32, false);
                     umma_commit(barA);
                 }
                 __syncwarp();
@@ -537,7 +953,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             UMMA_PROF();
             {
                 // loss stage (GRAPH:9428-11446).  Both column halves evaluate the sample's scalars; half 0 then emits
-                // dL/dmu (columns 0..31 of Y), half 1 the logstd contributions (columns 32..63).
+                // dL/dmu (columns 0..31 of Y), half 1 the logstd contributions (columns 32..63) — both times S_b.
                 float z[32];
                 float ss = 0.f;
                 {
@@ -548,7 +964,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                         z[j] = 0.f;
                         if (j < A) {
                             const float aj = (j & 1) ? act2[j >> 1].y : act2[j >> 1].x;
-                            z[j] = (aj - (mu[j] + f32[F32_BH + j])) * f32[F32_ISD + j];  // (a - mu) / sigma
+                            z[j] = (aj - fmaf(mu[j], u_hd, f32[F32_BH + j])) * f32[F32_ISD + j];  // (a - mu) / sigma
                             ss += z[j] * z[j];
                         }
                     }
@@ -567,7 +983,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     const float pg1 = -adv * ratio;
                     const float pg2 = -adv * fmaxf(fminf(ratio, hi), lo);          // clip_by_value = max(min(x,hi),lo)
                     const bool take1 = pg1 >= pg2;                                 // ties -> unclipped branch
-                    g_nlp = take1 ? (adv * ratio) * a.invB : 0.f;
+                    g_nlp = take1 ? ((adv * ratio) * a.invB) * S_b : 0.f;
                     if (half == 0) {
                         l_0 += take1 ? pg1 : pg2;
                         const float dn = nlp - oldn;
@@ -588,13 +1004,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             tc_fence_before();
             __syncthreads();
             UMMA_PROF();
-            // ---- backward through the head: dH2 = dMU * Wpi^T ; dWpi += H2^T * dMU ; column sums of [dMU | dLS]
+            // ---- backward through the head: dH2 = dMU * Wpi^T (the epilogue below waits for it); behind it, off the
+            // critical path: dWpi += H2^T * dMU ; column sums of [dMU | dLS]
             if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_gemm<3, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opWP_b, id_b64, false);
+                    issue_gemm<2, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opWP_b, id_b64, false);
                     umma_commit(barA);
-                    issue_gemm<3, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opY_mn, id_w32, accw);
+                    issue_gemm<2, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opY_mn, id_w32, accw);
                     issue_gemm<1, 8>(tmem + ACC_CS, tmem + ACC_CS_C, opY_mn, opONES, id_s8, accw);
                     umma_commit(barB);
                 }
@@ -602,13 +1019,12 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             }
             mbar_wait(barA, phA); phA ^= 1;
             tc_fence_after();
+            UMMA_PROF();
             float v[32];
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= (1.f - h2r[j] * h2r[j]);
-            mbar_wait(barB, phB); phB ^= 1;  // dWpi has read H2
-            UMMA_PROF();
-            store_row32(sH2, row, half, v);  // dP2 in place of H2
+            store_row32(sD2, row, half, v);  // dP2 (its own block: the dWpi GEMM may still be reading H2)
         } else {
             // ---- V head (GRAPH:10213-10400): value, clipped value loss and dL/dv on the CUDA cores
             if (half == 0) {
@@ -623,71 +1039,65 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     const bool inr = (dvo <= a.cliprange) && (dvo >= -a.cliprange);
                     dv = a.vf_coef * 0.5f * a.invB * (tk ? 2.f * (v - c_ret) : (inr ? 2.f * (vc - c_ret) : 0.f));
                     l_dbv += dv;
+                    dv *= S_b;  // as an operand: times S
                 }
                 f32[F32_DV + row] = dv;
-                uint32_t p0, p1, p2;
-                split_pair(dv, 0.f, p0, p1, p2);
+                uint32_t p0, p1;
+                split_pair(dv, 0.f, p0, p1);
                 const uint32_t o = (uint32_t)((row >> 6) * 1024 + (((row & 63) >> 3) << 4) + (row & 7) * 2);  // row 0 of the [8 x 128] block
                 *reinterpret_cast<uint16_t*>(smem + OFF_WP + o) = (uint16_t)p0;
                 *reinterpret_cast<uint16_t*>(smem + OFF_WP + ROW8_PIECE + o) = (uint16_t)p1;
-                *reinterpret_cast<uint16_t*>(smem + OFF_WP + 2 * ROW8_PIECE + o) = (uint16_t)p2;
             }
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
             UMMA_PROF();
-            // dWv += H2^T * dv
+            // dWv += H2^T * dv (off the critical path; collected by barC)
             if (warp == 0) {
                 tc_fence_after();
-                if (elect_one()) {
-                    issue_gemm<3, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opDV, id_s8, accw);
-                    umma_commit(barB);
-                }
+                if (elect_one()) issue_gemm<2, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opDV, id_s8, accw);
                 __syncwarp();
             }
             const float dvr = f32[F32_DV + row];
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = dvr * f32[F32_WV + 32 * half + j] * (1.f - h2r[j] * h2r[j]);
-            mbar_wait(barB, phB); phB ^= 1;  // dWv has read H2
-            tc_fence_after();
+            for (int j = 0; j < 32; ++j) v[j] = dvr * (f32[F32_WV + 32 * half + j] * s_hd_v) * (1.f - h2r[j] * h2r[j]);
             UMMA_PROF();
-            store_row32(sH2, row, half, v);  // dP2 in place of H2
+            store_row32(sD2, row, half, v);  // dP2
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         UMMA_PROF();
 
-        // ---- hidden layer 1 backward: dH1 = dP2 * W1^T ; dW1^T += dP2^T * H1 ; db1 += colsum(dP2)
+        // ---- hidden layer 1 backward: dH1 = dP2 * W1^T (waited for); behind it dW1^T += dP2^T * H1 ; db1 += colsum(dP2)
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<3, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opW1_b, id_b64, false);
+                issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opD2_k, opW1_b, id_b64, false);
                 umma_commit(barA);
-                issue_gemm<3, 8>(tmem + ACC_DW1, tmem + ACC_DW1_C, opH2_mn, opH1_mn, id_w64, accw);
-                issue_gemm<1, 8>(tmem + ACC_DB1, tmem + ACC_DB1_C, opH2_mn, opONES, id_s8, accw);
-                umma_commit(barB);
+                issue_gemm<2, 8>(tmem + ACC_DW1, tmem + ACC_DW1_C, opD2_mn, opH1_mn, id_w64, accw);
+                issue_gemm<1, 8>(tmem + ACC_DB1, tmem + ACC_DB1_C, opD2_mn, opONES, id_s8, accw);
             }
             __syncwarp();
         }
-        // pi tower: X' again for the layer-0 weight gradient (its block held [dMU | dLS] in between; the MMAs that read
-        // those completed before the dP2 epilogue)
+        // pi tower: X' again for the layer-0 weight gradient (its block held [dMU | dLS] in between; barB says the MMAs
+        // that read those have completed)
         if (tower == 0) {
             ObsRegs<O> xr;
             xr.load(a.obs, c_grow, gh, valid);
+            mbar_wait(barB, phB); phB ^= 1;
             xr.store(sY, gr, gh);
         }
         mbar_wait(barA, phA); phA ^= 1;
         tc_fence_after();
+        UMMA_PROF();
         {
             float v[32];
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= (1.f - h1r[j] * h1r[j]);
-            mbar_wait(barB, phB); phB ^= 1;  // dW1 has read H1
-            UMMA_PROF();
-            store_row32(sH1, row, half, v);  // dP1 in place of H1
+            store_row32(sD1, row, half, v);  // dP1
         }
         fence_async_smem();
         tc_fence_before();
@@ -697,15 +1107,15 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<3, 8>(tmem + ACC_DW0, tmem + ACC_DW0_C, opH1_mn, opY_mn, id_w32, accw);
-                umma_commit(barB);
+                issue_gemm<2, 8>(tmem + ACC_DW0, tmem + ACC_DW0_C, opD1_mn, opY_mn, id_w32, accw);
+                umma_commit(barC);
             }
             __syncwarp();
         }
         accw = true;
         const bool more = tile + (int)gridDim.x < ntiles;
         if (more) load_inputs(tile + gridDim.x);
-        mbar_wait(barB, phB); phB ^= 1;
+        mbar_wait(barC, phC); phC ^= 1;  // every MMA of this tile has completed: all operand blocks are free again
         tc_fence_after();
         UMMA_PROF();
         if (more) {
@@ -722,64 +1132,69 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         load_index(blockIdx.x);
     }
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
+    const unsigned seq = LL ? ll_seq0 + (unsigned)mb + 1u : 0u;  // LL: this minibatch's sequence number
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
+    uint2* my_ll = LL ? ep.ll_slab + (size_t)blockIdx.x * a.PS : nullptr;
+    auto put = [&](int col, float val) {
+        if (LL) ll_store1(my_ll + col, __float_as_uint(val), seq);
+        else my[col] = val;
+    };
     // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15)
     const int r64 = q * 16 + lane;
     const bool has = lane < 16;
     if (!accw) {  // no tile for this CTA: write zeros
         if (tower == 0) {
-            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) my[d.off[T_PI_FC0_W] + i] = 0.f;
-            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) my[d.off[T_PI_FC1_W] + i] = 0.f;
-            for (int i = tid; i < d.H2 * A + 2 * A; i += NTH) my[d.off[T_PI_W] + i] = 0.f;
+            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) put(d.off[T_PI_FC0_W] + i, 0.f);
+            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) put(d.off[T_PI_FC1_W] + i, 0.f);
+            for (int i = tid; i < d.H2 * A + 2 * A; i += NTH) put(d.off[T_PI_W] + i, 0.f);
         } else {
-            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) my[d.off[T_VF_FC0_W] + i] = 0.f;
-            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) my[d.off[T_VF_FC1_W] + i] = 0.f;
-            for (int i = tid; i < d.H2 + 1; i += NTH) my[d.off[T_VF_W] + i] = 0.f;
+            for (int i = tid; i < d.H1 * O + d.H1; i += NTH) put(d.off[T_VF_FC0_W] + i, 0.f);
+            for (int i = tid; i < d.H1 * d.H2 + d.H2; i += NTH) put(d.off[T_VF_FC1_W] + i, 0.f);
+            for (int i = tid; i < d.H2; i += NTH) put(d.off[T_VF_W] + i, 0.f);  // vf/b comes with the loss sums below
         }
     } else {
         float v[32];
         // dW1^T[j][k] -> W1[k][j]
         tmem_ld32_sum(tlane + ACC_DW1 + 32 * half, tlane + ACC_DW1_C + 32 * half, v);
         if (has) {
-            float* g = my + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
+            const int g = d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) g[(size_t)(32 * half + k) * HID + r64] = v[k];
+            for (int k = 0; k < 32; ++k) put(g + (32 * half + k) * HID + r64, v[k] * un_w1);
         }
         if (half == 0) {
             // dW0'^T[j][k]: k < O -> W0[k][j], k == O -> b0[j]
             tmem_ld32_sum(tlane + ACC_DW0, tlane + ACC_DW0_C, v);
             if (has) {
-                float* g = my + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
-                float* gb = my + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
+                const int g = d.off[tower ? T_VF_FC0_W : T_PI_FC0_W], gb = d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    if (k < O) g[(size_t)k * HID + r64] = v[k];
-                    else if (k == O) gb[r64] = v[k];
+                    if (k < O) put(g + k * HID + r64, v[k] * un_w0);
+                    else if (k == O) put(gb + r64, v[k] * un_w0);
                 }
             }
         } else {
             float b[8];
             tmem_ld8_sum(tlane + ACC_DB1, tlane + ACC_DB1_C, b);
-            if (has) my[d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + r64] = b[0];
+            if (has) put(d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + r64, b[0] * un_w1);
             if (tower == 0) {
                 // dWpi[k][j]
                 tmem_ld32_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, v);
                 if (has) {
-                    float* g = my + d.off[T_PI_W] + (size_t)r64 * A;
+                    const int g = d.off[T_PI_W] + r64 * A;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < A) g[j] = v[j];
+                        if (j < A) put(g + j, v[j] * un_hd);
                 }
                 // column sums: rows < A -> dbpi, rows 32 .. 32 + A -> dlogstd
                 tmem_ld8_sum(tlane + ACC_CS, tlane + ACC_CS_C, b);
                 if (has) {
-                    if (r64 < A) my[d.off[T_PI_B] + r64] = b[0];
+                    if (r64 < A) put(d.off[T_PI_B] + r64, b[0] * un_hd);
                     // d(-ent_coef*entropy)/dlogstd_j = -ent_coef, once (a.ent_coef is pre-divided by the number of ranks)
-                    if (r64 >= 32 && r64 < 32 + A) my[d.off[T_LOGSTD] + r64 - 32] = b[0] - (blockIdx.x == 0 ? a.ent_coef : 0.f);
+                    if (r64 >= 32 && r64 < 32 + A) put(d.off[T_LOGSTD] + r64 - 32, b[0] * un_hd - (blockIdx.x == 0 ? a.ent_coef : 0.f));
                 }
             } else {
                 tmem_ld8_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, b);
-                if (has) my[d.off[T_VF_W] + r64] = b[0];
+                if (has) put(d.off[T_VF_W] + r64, b[0] * un_hd);
             }
         }
     }
@@ -798,22 +1213,34 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float t[4] = {0.f, 0.f, 0.f, 0.f};
             for (int w = 0; w < NTH / 32; ++w)
                 for (int k = 0; k < 4; ++k) t[k] += f32[F32_RED + w * 4 + k];
-            float* Lp = my + d.P;
+            const int Lp = d.P;
             if (tower == 0) {
-                Lp[L_PG] = t[0]; Lp[L_KL] = t[1]; Lp[L_CLIP] = t[2];
+                put(Lp + L_PG, t[0]); put(Lp + L_KL, t[1]); put(Lp + L_CLIP, t[2]);
                 float ent = 0.f;
                 if (blockIdx.x == 0)
                     for (int j = 0; j < A; ++j) ent += f32[F32_LS + j] + PPO_HALF_LOG_2PIE;  // GRAPH:10021-10180
-                Lp[L_ENT] = ent;
-                Lp[5] = 0.f; Lp[6] = 0.f; Lp[7] = 0.f;
+                put(Lp + L_ENT, ent);
+                put(Lp + 5, 0.f); put(Lp + 6, 0.f); put(Lp + 7, 0.f);
             } else {
-                Lp[L_VF] = t[0];
-                my[d.off[T_VF_B]] = t[3];
+                put(Lp + L_VF, t[0]);
+                put(d.off[T_VF_B], accw ? t[3] : 0.f);
             }
         }
     }
     UMMA_PROF();
-        if (PERSIST) {
+        if (LL) {
+            // no grid barrier anywhere: the chunk owners poll the slab words, everybody polls the sums of squares, and the
+            // next minibatch's staging polls the parameter words
+            if (mb + 1 < n_mb) load_rows();
+            tc_fence_before();
+            ++mseq;
+            reduce_adam_ll(ep, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), seq, mseq, b1p, b2p,
+                           ep.loss_rows + (size_t)mb * 5, (a.prof && blockIdx.x == 0 && mb == 1) ? a.prof + 64 + tower * 8 : nullptr,
+                           (a.prof && mb == 1) ? a.prof + 96 : nullptr);
+            b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
+            b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
+            UMMA_PROF();  // reduce + norm + Adam done
+        } else if (PERSIST) {
             // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
             if (mb + 1 < n_mb) load_rows();  // next minibatch's first tile (index issued before the flush): lands during the barriers
             tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
@@ -835,6 +1262,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     if (PERSIST && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         ep.ra.adam.bpow_out[0] = b1p;
         ep.ra.adam.bpow_out[1] = b2p;
+        if (LL) *ep.ll_seq = ll_seq0 + (unsigned)n_mb;
         *ep.ra.bar_gen = bar.gen;
         if (ep.ra.mbox.world > 1) *ep.ra.mbox_seq = mseq;
     }

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
                     a_mn = 1; a_lbo = BLK8; a_piece = (2 * BLK8) >> 4; a_ks = 2048 >> 4;
                     b_mn = 1; b_lbo = BLK8; b_piece = (uint32_t)(NG * BLK8) >> 4; b_ks = 2048 >> 4;
                 }
-                const uint32_t idesc = umma::make_idesc(128, n_tile, a_mn, b_mn);
+                const uint32_t idesc = umma::make_idesc_bf16(128, n_tile, a_mn, b_mn);
                 const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
                 mbar_wait_b(BAR_ACCEMPTY(ab), aph ^ 1u);
                 umma::tc_fence_after();
@@ -298,12 +298,12 @@ __global__ void __launch_bounds__(GEMM_NTH, 1) wgemm_kernel(const GemmArgs g) {
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t a = ad + (uint64_t)(ks * a_ks), b = bd + (uint64_t)(ks * b_ks);
                         const uint32_t acc = (kb > kb0 || ks > 0) ? 1u : 0u;
-                        umma::mma_bf16(dm, a, b, idesc, acc);
-                        umma::mma_bf16(dc, a, b + b_piece, idesc, acc);
-                        umma::mma_bf16(dc, a + a_piece, b, idesc, 1u);
-                        umma::mma_bf16(dc, a + a_piece, b + b_piece, idesc, 1u);
-                        umma::mma_bf16(dc, a, b + 2 * b_piece, idesc, 1u);
-                        umma::mma_bf16(dc, a + 2 * a_piece, b, idesc, 1u);
+                        umma::mma_f16(dm, a, b, idesc, acc);
+                        umma::mma_f16(dc, a, b + b_piece, idesc, acc);
+                        umma::mma_f16(dc, a + a_piece, b, idesc, 1u);
+                        umma::mma_f16(dc, a + a_piece, b + b_piece, idesc, 1u);
+                        umma::mma_f16(dc, a, b + 2 * b_piece, idesc, 1u);
+                        umma::mma_f16(dc, a + 2 * a_piece, b, idesc, 1u);
                     }
                     umma::umma_commit(BAR_EMPTY(s));  // the stage is free once these MMAs have read it
                 }
@@ -626,7 +626,7 @@ __global__ void wide_prep_weights_kernel(const float* __restrict__ P, const NetD
             dst = w.WH + tower * G.wh_tower + (size_t)ri * BLK8 + chunk_off(r, j);
             piece = G.wh_piece;
         }
-        umma::store_chunk(dst, (uint32_t)piece, 0, x);
+        umma::store_chunk3(dst, (uint32_t)piece, 0, x);
     }
 }
 
@@ -648,7 +648,7 @@ __global__ void wide_gather_kernel(const TrainArgs a, const WideBufs w) {
                 x[i] = c < O ? __ldg(a.obs + src * O + c) : (c == O ? 1.f : 0.f);
             }
         }
-        umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
+        umma::store_chunk3(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
     }
 }
 
@@ -671,7 +671,7 @@ __global__ void wide_policy_gather_kernel(const float* __restrict__ obs, int n, 
                 } else if (c == O) x[i] = 1.f;
             }
         }
-        umma::store_chunk(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
+        umma::store_chunk3(w.X + (size_t)(row >> 7) * G.x_tile, BLK16, chunk_off(row & 127, j), x);
     }
 }
 
