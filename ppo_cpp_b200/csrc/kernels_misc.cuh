@@ -951,7 +951,13 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
             const int c = chunk * 64 + lane_c;
             if (c < r.PS) {
                 float t = 0.f;
-                for (int src = 0; src < world; ++src) t += __uint_as_float(r.mbox.ll_wait(seq, src, (size_t)c));
+                for (int s0 = 0; s0 < world; s0 += 4) {  // four ranks' values of this column in flight together, added in rank order
+                    unsigned w[4];
+                    r.mbox.ll_wait4(seq, (size_t)c, s0, w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (s0 + k < world) t += __uint_as_float(w[k]);
+                }
                 gsum[j] = t;
             }
         }

@@ -355,10 +355,12 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 __syncthreads();  // CTA 0: csum has been read before it is overwritten below
                 if (tid < 2 * (D + 1)) {
                     double v = 0.0;
-                    for (int src = 0; src < world; ++src) {
-                        const unsigned lo = a.mbox.ll_wait(seq, src, (size_t)(2 * tid));
-                        const unsigned hi = a.mbox.ll_wait(seq, src, (size_t)(2 * tid + 1));
-                        v += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                    for (int s0 = 0; s0 < world; s0 += 4) {  // four ranks' words in flight together, added in rank order
+                        unsigned long long w[4];
+                        a.mbox.ll_wait4_pair(seq, (size_t)(2 * tid), s0, w);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (s0 + k < world) v += __longlong_as_double((long long)w[k]);
                     }
                     csum[tid] = v;
                 }

@@ -274,46 +274,6 @@ struct EpochArgs {
     const float2* mbstats;  // [M]
     float* loss_rows;       // [M][5]
     ReduceAdamArgs ra;
-    // MODE 2 (LL hand-overs): slabs [G][PS], per-block sums of squares [nblk][2] (a double as two words), parameters [P];
-    // ll_seq: device-resident sequence number (one per minibatch ever trained), so that launches replay from a CUDA graph
-    uint2* ll_slab;
-    uint2* ll_sq;
-    uint2* ll_par;
-    unsigned* ll_seq;
-};
-
-// ---- LL consumers: all loads of a group are issued first, then checked together; a stale word re-polls the whole group
-// (intra-GPU words: gpu scope is enough; the cross-GPU mailbox words of sync_prims.cuh stay volatile = system scope)
-__device__ __forceinline__ uint4 ll_load2(const uint2* p) {  // two adjacent LL words, p 16-byte aligned
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 ll_load1(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void ll_store1(uint2* p, unsigned data, unsigned seq) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
-}
-// bounded spinning: after ~2 s (a CTA that never arrives) the error flag is raised and the poll loops give up
-struct LLSpin {
-    unsigned* err;
-    unsigned long long t0;
-    unsigned spins;
-    __device__ __forceinline__ explicit LLSpin(unsigned* e) : err(e), t0(0), spins(0) {}
-    __device__ __forceinline__ bool giveup() {
-        if (((++spins) & 0xffu) == 0u) {
-            if (t0 == 0) t0 = globaltimer_ns();
-            if (*reinterpret_cast<volatile unsigned*>(err)) return true;
-            if (globaltimer_ns() - t0 > 2000000000ull) {
-                *err = 1u;
-                return true;
-            }
-        }
-        return false;
-    }
 };
 
 #define UMMA_PROF()                                                                                              \
@@ -321,203 +281,13 @@ struct LLSpin {
         if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 32) a.prof[tower * 32 + prof_i++] = clock64();      \
     } while (0)
 
-// MODE 2: the gradient step without grid barriers.  Block `blk` of `nblk` (256 threads) owns the 64-column chunks blk and
-// blk + nblk.  (1) poll the G slab rows of its chunks (LL words written by the tile CTAs' flush) and sum them in the same
-// fixed order as reduce_adam_device; (2) multi-GPU: the same mailbox exchange; (3) publish the chunk's sum of squares as two
-// LL words, poll everybody's, same fixed-order norm; (4) clip + TF ApplyAdam on its columns, parameters stored plainly (for
-// the kernels that follow the epoch) AND as LL words (for the staging of the next minibatch).  Arithmetic and summation
-// order are those of reduce_adam_device: results are bit-identical to the barrier path.
-__device__ __forceinline__ void reduce_adam_ll(const EpochArgs& ep, int blk, int nblk, unsigned seq, unsigned mseq, float b1p, float b2p,
-                                               float* loss_row, long long* prof = nullptr, long long* prof_all = nullptr) {
-    int pi_ = 0;
-#define RL_PROF()                                                                                   \
-    do {                                                                                            \
-        if (prof_all && threadIdx.x == 0 && pi_ < 8) prof_all[blk * 8 + pi_] = (long long)globaltimer_ns(); \
-        if (prof && threadIdx.x == 0 && pi_ < 8) prof[pi_] = clock64();                              \
-        ++pi_;                                                                                      \
-    } while (0)
-    RL_PROF();
-    __shared__ float part[4][64];
-    __shared__ double red[8];
-    __shared__ float s_scale;
-    __shared__ float s_loss[8];
-    const ReduceAdamArgs& r = ep.ra;
-    const AdamArgs& a = r.adam;
-    const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    const int nchunks = (r.PS + 63) >> 6;
-    const int world = r.mbox.world;
-    const int loss_chunk = a.P >> 6;  // holds columns P .. P+4 (the host checks (P & 63) + 5 <= 64)
-    float gsum[2] = {0.f, 0.f};
-    float acc[2] = {0.f, 0.f};
-    {
-        // light pre-wait (one word per thread): the loss sums are the LAST words a tile CTA's flush stores, so poll those of
-        // the 2 x G producers first.  Polling the payload words themselves from every thread (32 loads each, 8 MB per
-        // round over the chip) saturates L2 and delays the very stores it waits for (measured: 3x slower).
-        LLSpin spin(r.mbox.err);
-        if (threadIdx.x < 2 * r.G) {
-            const uint2* p = ep.ll_slab + (size_t)(threadIdx.x >> 1) * r.PS + a.P + ((threadIdx.x & 1) ? L_VF : L_PG);
-            while (ll_load1(p).y != seq && !spin.giveup()) {
-            }
-        }
-        __syncthreads();
-        while (true) {
-            uint2 w[2][16];
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int c = (blk + j * nblk) * 64 + lane_c;
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int g = rg + 4 * u;
-                    w[j][u] = (c < r.PS && g < r.G) ? ll_load1(ep.ll_slab + (size_t)g * r.PS + c) : make_uint2(0u, seq);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int u = 0; u < 16; ++u) ok = ok && w[j][u].y == seq;
-            if (ok || spin.giveup()) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) acc[j] += __uint_as_float(w[j][u].x);
-                break;
-            }
-        }
-    }
-    RL_PROF();  // slab rows arrived
-    double q = 0.0;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int chunk = blk + j * nblk;
-        if (chunk >= nchunks) break;  // block-uniform
-        const int c = chunk * 64 + lane_c;
-        __syncthreads();
-        part[rg][lane_c] = acc[j];
-        __syncthreads();
-        if (rg == 0) {
-            const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
-            gsum[j] = (float)t;
-            if (world > 1 && c < r.PS)
-                for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, mseq, r.mbox.rank) + c, __float_as_uint(gsum[j]), mseq);
-        }
-    }
-    if (world > 1 && rg == 0) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < r.PS) {
-                float t = 0.f;
-                for (int src = 0; src < world; ++src) t += __uint_as_float(r.mbox.ll_wait(mseq, src, (size_t)c));
-                gsum[j] = t;
-            }
-        }
-    }
-    if (rg == 0) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < r.PS) r.grad[c] = gsum[j];
-            if (c < a.P) q += (double)gsum[j] * (double)gsum[j];
-            if (chunk == loss_chunk && lane_c >= (a.P & 63) && lane_c < (a.P & 63) + 8) s_loss[lane_c - (a.P & 63)] = gsum[j];
-        }
-    }
-    q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double sq = red[0] + red[1];  // warps 0, 1 hold rg == 0
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(sq);
-        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ep.ll_sq + 2 * blk), "r"((unsigned)bits), "r"(seq),
-                     "r"((unsigned)(bits >> 32)), "r"(seq)
-                     : "memory");
-    }
-    RL_PROF();  // chunk sums + sum of squares published
-    // Adam state of this thread's columns: only this thread ever touches it
-    float am[2], av[2], ap[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int c = (blk + j * nblk) * 64 + lane_c;
-        const bool mine = rg == 0 && c < a.P;
-        am[j] = mine ? __ldcg(a.m + c) : 0.f;
-        av[j] = mine ? __ldcg(a.v + c) : 0.f;
-        ap[j] = mine ? __ldcg(a.params + c) : 0.f;
-    }
-    if (threadIdx.x < 32) {
-        double ss = 0.0;
-        LLSpin spin(r.mbox.err);
-        // nblk <= 128: up to four entries per lane, all four loads in flight at once; same lane order as reduce_adam_device
-        while (true) {
-            uint4 w[4];
-            bool ok = true;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int b = threadIdx.x + 32 * u;
-                w[u] = b < nblk ? ll_load2(ep.ll_sq + 2 * b) : make_uint4(0u, seq, 0u, seq);
-                ok = ok && w[u].y == seq && w[u].w == seq;
-            }
-            if (ok || spin.giveup()) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (threadIdx.x + 32 * u < nblk)
-                        ss += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | (unsigned long long)w[u].x));
-                break;
-            }
-        }
-        ss = warp_sum(ss);  // same fixed-order combine as reduce_adam_device
-        if (threadIdx.x == 0) {
-            const float gnorm = (float)sqrt(ss);
-            const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
-            float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
-            if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
-            s_scale = scale;
-            if (blk == 0) *a.gnorm_out = gnorm;
-        }
-    }
-    __syncthreads();
-    RL_PROF();  // everybody's sums of squares arrived: norm known
-    if (blk == loss_chunk % nblk && threadIdx.x == 0) {
-        loss_row[0] = s_loss[L_PG] * a.invB;
-        loss_row[1] = 0.5f * (s_loss[L_VF] * a.invB);
-        loss_row[2] = s_loss[L_ENT] * a.inv_world;
-        loss_row[3] = 0.5f * (s_loss[L_KL] * a.invB);
-        loss_row[4] = s_loss[L_CLIP] * a.invB;
-    }
-    if (rg == 0) {
-        const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < a.P) {
-                const float g = __fmul_rn(gsum[j], s_scale);
-                float m = am[j], v = av[j];
-                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
-                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
-                const float th = __fsub_rn(ap[j], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
-                a.m[c] = m;
-                a.v[c] = v;
-                a.params[c] = th;
-                ll_store1(ep.ll_par + c, __float_as_uint(th), seq);
-            }
-        }
-    }
-    RL_PROF();  // Adam done, parameters published
-#undef RL_PROF
-}
-
-// MODE 0: one minibatch per launch (slabs are reduced by another kernel).  MODE 1: persistent epoch, grid barriers.
-// MODE 2: persistent epoch, barrier-free: every cross-CTA hand-over is an LL word (payload + sequence number in one 8-byte
-// store, polled by the consumer): slabs -> chunk owners, chunk sums of squares -> everybody, updated parameters -> everybody.
+// MODE 0: one minibatch per launch (slabs are reduced by another kernel).  MODE 1: persistent epoch, three grid barriers per
+// minibatch.  (A barrier-free variant — every cross-CTA hand-over an LL word polled by its consumer — was built and measured
+// in round 2: 7.22 ms per C3 update against 6.97 ms; each dependent global hop costs ~0.8 us either way and the LL slabs
+// double the bytes of the largest exchange.  profiles/r2_u_family_ll_experiment.txt; not kept.)
 template <int O, int A, int MODE>
 __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, const EpochArgs ep) {
     constexpr bool PERSIST = MODE != 0;
-    constexpr bool LL = MODE == 2;
     static_assert(O % 2 == 0 && O >= 2 && O <= 30 && A % 2 == 0 && A >= 2 && A <= 32, "unsupported obs/act width");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -602,7 +372,6 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     // persistent state: grid barrier generation, mailbox sequence number, Adam's beta powers (every CTA tracks them)
     GridBarrier bar{PERSIST ? ep.ra.bar_ctr : nullptr, 2u * gridDim.x, PERSIST ? *ep.ra.bar_gen : 0u};
     unsigned mseq = (PERSIST && ep.ra.mbox.world > 1) ? *ep.ra.mbox_seq : 0u;
-    const unsigned ll_seq0 = LL ? *ep.ll_seq : 0u;  // minibatch mb of this launch hands over with sequence number ll_seq0 + mb + 1
     float b1p = PERSIST ? ep.ra.adam.bpow_in[0] : 0.f, b2p = PERSIST ? ep.ra.adam.bpow_in[1] : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -657,85 +426,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float4 w1v[2][2], w0v[2];
             float wpv[8];
             float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
-            if (LL && mb > 0) {
-                // the parameters as LL words, published by the chunk owners' Adam of the previous minibatch (sequence number
-                // ll_seq0 + mb): all loads in flight at once, one check, stale words re-poll the group
-                const unsigned pseq = ll_seq0 + (unsigned)mb;
-                const uint2* Q = ep.ll_par;
-                const int o_w1 = d.off[tower ? T_VF_FC1_W : T_PI_FC1_W], o_w0 = d.off[tower ? T_VF_FC0_W : T_PI_FC0_W],
-                          o_b0 = d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
-                LLSpin spin(ep.ra.mbox.err);
-                {   // light pre-wait: the last word of every 64-column chunk (one word per thread) before the bulk loads
-                    const int nch = (d.P + 63) >> 6;
-                    if (tid < nch) {
-                        const uint2* pw = Q + min(tid * 64 + 63, d.P - 1);
-                        while (ll_load1(pw).y != pseq && !spin.giveup()) {
-                        }
-                    }
-                    __syncthreads();
-                }
-                while (true) {
-                    uint4 r1[2][4], r0[4];
-                    uint2 rp[8], rb1, rwv, rls, rbh, rbv;
-                    const uint4 z4 = make_uint4(0u, pseq, 0u, pseq);
-                    const uint2 z2 = make_uint2(0u, pseq);
-    #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int e = tid + NTH * i, r = e >> 3, j = e & 7;
-    #pragma unroll
-                        for (int k = 0; k < 4; ++k) r1[i][k] = ll_load2(Q + o_w1 + r * HID + 8 * j + 2 * k);
-                    }
-                    {
-                        const int r = tid >> 3, j = tid & 7;
-                        const int idx = r < O ? (o_w0 + r * HID + 8 * j) : (o_b0 + 8 * j);
-    #pragma unroll
-                        for (int k = 0; k < 4; ++k) r0[k] = (r <= O) ? ll_load2(Q + idx + 2 * k) : z4;
-                    }
-    #pragma unroll
-                    for (int k = 0; k < 8; ++k) rp[k] = z2;
-                    if (tower == 0) {
-                        const int r = tid >> 2, j = tid & 3;
-    #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (8 * j + k < A) rp[k] = ll_load1(Q + d.off[T_PI_W] + r * A + 8 * j + k);
-                    }
-                    rb1 = rwv = rls = rbh = rbv = z2;
-                    if (tid < HID) {
-                        rb1 = ll_load1(Q + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
-                        rwv = ll_load1(Q + d.off[T_VF_W] + tid);
-                    }
-                    if (tid < 32) {
-                        if (tid < A) {
-                            rls = ll_load1(Q + d.off[T_LOGSTD] + tid);
-                            rbh = ll_load1(Q + d.off[T_PI_B] + tid);
-                        }
-                        rbv = ll_load1(Q + d.off[T_VF_B]);
-                    }
-                    bool ok = rb1.y == pseq && rwv.y == pseq && rls.y == pseq && rbh.y == pseq && rbv.y == pseq;
-    #pragma unroll
-                    for (int i = 0; i < 2; ++i)
-    #pragma unroll
-                        for (int k = 0; k < 4; ++k) ok = ok && r1[i][k].y == pseq && r1[i][k].w == pseq;
-    #pragma unroll
-                    for (int k = 0; k < 4; ++k) ok = ok && r0[k].y == pseq && r0[k].w == pseq;
-    #pragma unroll
-                    for (int k = 0; k < 8; ++k) ok = ok && rp[k].y == pseq;
-                    if (ok || spin.giveup()) {
-    #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            w1v[i][0] = make_float4(__uint_as_float(r1[i][0].x), __uint_as_float(r1[i][0].z), __uint_as_float(r1[i][1].x), __uint_as_float(r1[i][1].z));
-                            w1v[i][1] = make_float4(__uint_as_float(r1[i][2].x), __uint_as_float(r1[i][2].z), __uint_as_float(r1[i][3].x), __uint_as_float(r1[i][3].z));
-                        }
-                        w0v[0] = make_float4(__uint_as_float(r0[0].x), __uint_as_float(r0[0].z), __uint_as_float(r0[1].x), __uint_as_float(r0[1].z));
-                        w0v[1] = make_float4(__uint_as_float(r0[2].x), __uint_as_float(r0[2].z), __uint_as_float(r0[3].x), __uint_as_float(r0[3].z));
-    #pragma unroll
-                        for (int k = 0; k < 8; ++k) wpv[k] = __uint_as_float(rp[k].x);
-                        b1 = __uint_as_float(rb1.x); wv = __uint_as_float(rwv.x); ls = __uint_as_float(rls.x);
-                        bh = __uint_as_float(rbh.x); bv = __uint_as_float(rbv.x);
-                        break;
-                    }
-                }
-            } else {
+            {
     #pragma unroll
             for (int i = 0; i < 2; ++i) {  // W1: 64 rows x 8 chunks = 512 tasks
                 const int e = tid + NTH * i, r = e >> 3, j = e & 7;
@@ -1132,13 +823,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         load_index(blockIdx.x);
     }
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
-    const unsigned seq = LL ? ll_seq0 + (unsigned)mb + 1u : 0u;  // LL: this minibatch's sequence number
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
-    uint2* my_ll = LL ? ep.ll_slab + (size_t)blockIdx.x * a.PS : nullptr;
-    auto put = [&](int col, float val) {
-        if (LL) ll_store1(my_ll + col, __float_as_uint(val), seq);
-        else my[col] = val;
-    };
+    auto put = [&](int col, float val) { my[col] = val; };
     // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15)
     const int r64 = q * 16 + lane;
     const bool has = lane < 16;
@@ -1228,19 +914,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         }
     }
     UMMA_PROF();
-        if (LL) {
-            // no grid barrier anywhere: the chunk owners poll the slab words, everybody polls the sums of squares, and the
-            // next minibatch's staging polls the parameter words
-            if (mb + 1 < n_mb) load_rows();
-            tc_fence_before();
-            ++mseq;
-            reduce_adam_ll(ep, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), seq, mseq, b1p, b2p,
-                           ep.loss_rows + (size_t)mb * 5, (a.prof && blockIdx.x == 0 && mb == 1) ? a.prof + 64 + tower * 8 : nullptr,
-                           (a.prof && mb == 1) ? a.prof + 96 : nullptr);
-            b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
-            b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
-            UMMA_PROF();  // reduce + norm + Adam done
-        } else if (PERSIST) {
+        if (PERSIST) {
             // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
             if (mb + 1 < n_mb) load_rows();  // next minibatch's first tile (index issued before the flush): lands during the barriers
             tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
@@ -1262,7 +936,6 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     if (PERSIST && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         ep.ra.adam.bpow_out[0] = b1p;
         ep.ra.adam.bpow_out[1] = b2p;
-        if (LL) *ep.ll_seq = ll_seq0 + (unsigned)n_mb;
         *ep.ra.bar_gen = bar.gen;
         if (ep.ra.mbox.world > 1) *ep.ra.mbox_seq = mseq;
     }

@@ -151,9 +151,6 @@ struct ppo_core {
     EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
     bool persistent_epoch = false;    // U family: all minibatches of an epoch in one cooperative launch
     int epoch_grid = 0;
-    bool epoch_ll = false;            // ... with LL hand-overs instead of grid barriers (kernels_umma.cuh MODE 2)
-    unsigned char* ll_mem = nullptr;  // LL slabs [G][PS], sums of squares [nblk][2], parameters [P] (uint2 words, zero-initialised)
-    size_t ll_sq_off = 0, ll_par_off = 0;
     bool persistent_rollout = false;  // R family: the whole rollout as one cooperative kernel
     int roll_grid = 0, roll_tpc = 0;
     size_t roll_smem = 0;
@@ -201,7 +198,7 @@ struct ppo_core {
     ppo_counters ctr{};
 };
 // sync_vars layout: scalars first, then three barrier flag arrays of SV_MAXBLK words each
-enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_LL_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
+enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
        SV_COOP_FLAGS = SV_SCALARS, SV_ROLL_FLAGS = SV_COOP_FLAGS + SV_MAXBLK, SV_EPOCH_FLAGS = SV_ROLL_FLAGS + SV_MAXBLK,
        SV_COUNT = SV_EPOCH_FLAGS + SV_MAXBLK };
 
@@ -381,7 +378,6 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
         if (c->mbox_peer[r] && r != c->desc.rank) cudaIpcCloseMemHandle(c->mbox_peer[r]);
     if (c->mbox_mem) cudaFree(c->mbox_mem);
     if (c->gae_ab) cudaFree(c->gae_ab);
-    if (c->ll_mem) cudaFree(c->ll_mem);
     if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
     for (auto& g : c->graphs)
@@ -595,8 +591,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             if (st != PPO_OK) break;
         }
         if (c->umma && getenv("PPO_UMMA_PROF")) {
-            if (cudaMalloc(&c->umma_prof, sizeof(long long) * (96 + 128 * 8)) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
-            cudaMemset(c->umma_prof, 0, sizeof(long long) * (96 + 128 * 8));
+            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 96) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
+            cudaMemset(c->umma_prof, 0, sizeof(long long) * 96);
         }
         {
             int per_sm = 0, coop_ok = 0;
@@ -617,36 +613,19 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             if (c->umma && coop_ok && getenv("PPO_DISABLE_PERSISTENT") == nullptr) {
                 const int per_rank = (int)(nbg / desc->nminibatches / desc->world_size);
                 const int ntiles = (per_rank + umma::TM - 1) / umma::TM;
-                int grid = std::max(1, std::min(ntiles, c->sm_count / 2));
-                // barrier-free hand-overs (MODE 2): a block owns two 64-column chunks and sums 64 slab rows
-                bool ll = getenv("PPO_DISABLE_LL") == nullptr && ntiles >= 64 && nchunks <= 2 * 2 * 64 && (c->d.P & 63) + 5 <= 64;
-                if (ll) grid = 64;
+                const int grid = std::max(1, std::min(ntiles, c->sm_count / 2));
                 int per = 0;
-                bool attr_ok = ll ? cudaFuncSetAttribute(umma::train_umma_kernel<18, 18, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) == cudaSuccess
-                                  : cudaFuncSetAttribute(umma::train_umma_kernel<18, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) == cudaSuccess;
-                if (attr_ok) {
-                    if (ll) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, umma::train_umma_kernel<18, 18, 2>, umma::NTH, umma::SMEM_BYTES);
-                    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, umma::train_umma_kernel<18, 18, 1>, umma::NTH, umma::SMEM_BYTES);
-                } else {
+                if (cudaFuncSetAttribute(umma::train_umma_kernel<18, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES) == cudaSuccess)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, umma::train_umma_kernel<18, 18, 1>, umma::NTH, umma::SMEM_BYTES);
+                else
                     cudaGetLastError();
-                }
                 if (per > 0 && 2 * grid <= per * c->sm_count && nchunks <= 2 * grid * RA_MAXJ && 2 * grid <= PPO_MBOX_CHANNELS - 1) {
                     c->persistent_epoch = true;
                     c->epoch_grid = grid;
-                    c->epoch_ll = ll;
                     if (2 * grid > std::max(c->coop_grid, c->n_sq_blocks)) {
                         cudaFree(c->sq_partial);
                         c->sq_partial = nullptr;
                         if (cudaMalloc(&c->sq_partial, sizeof(double) * 2 * grid) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_partial) failed"); break; }
-                    }
-                    if (ll) {
-                        const size_t slab_bytes = (((size_t)grid * c->PS * sizeof(uint2)) + 255) & ~(size_t)255;
-                        const size_t sq_bytes = (((size_t)2 * grid * 2 * sizeof(uint2)) + 255) & ~(size_t)255;
-                        c->ll_sq_off = slab_bytes;
-                        c->ll_par_off = slab_bytes + sq_bytes;
-                        const size_t total = c->ll_par_off + (size_t)c->d.P * sizeof(uint2);
-                        if (cudaMalloc(&c->ll_mem, total) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(ll_mem) failed"); break; }
-                        cudaMemset(c->ll_mem, 0, total);  // sequence numbers start at 1: a zeroed word is never current
                     }
                 }
             }
@@ -1977,17 +1956,8 @@ static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
     ad.invB = a.invB; ad.inv_world = 1.0f / (float)W;
     ad.loss_row = nullptr; ad.gnorm_out = c->gnorm;
     void* kargs[] = {&a, &ep};
-    if (c->epoch_ll) {
-        ep.ll_slab = reinterpret_cast<uint2*>(c->ll_mem);
-        ep.ll_sq = reinterpret_cast<uint2*>(c->ll_mem + c->ll_sq_off);
-        ep.ll_par = reinterpret_cast<uint2*>(c->ll_mem + c->ll_par_off);
-        ep.ll_seq = c->sync_vars + SV_LL_SEQ;
-        CU(cudaLaunchCooperativeKernel((void*)umma::train_umma_kernel<18, 18, 2>, dim3(c->epoch_grid, 2), dim3(umma::NTH), kargs,
-                                       umma::SMEM_BYTES, c->stream));
-    } else {
-        CU(cudaLaunchCooperativeKernel((void*)umma::train_umma_kernel<18, 18, 1>, dim3(c->epoch_grid, 2), dim3(umma::NTH), kargs,
-                                       umma::SMEM_BYTES, c->stream));
-    }
+    CU(cudaLaunchCooperativeKernel((void*)umma::train_umma_kernel<18, 18, 1>, dim3(c->epoch_grid, 2), dim3(umma::NTH), kargs,
+                                   umma::SMEM_BYTES, c->stream));
     c->ctr.kernel_launches++;
     c->bpow_slot ^= 1;
     return PPO_OK;
@@ -2229,8 +2199,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
         if (c->wide) return "wgemm_kernel (tcgen05.mma kind::f16, bf16x3 split operand images, layer-wise GEMMs with bulk-copy pipeline)";
         if (c->small) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums)";
         if (c->umma && c->persistent_epoch && fast_path(c))
-            return c->epoch_ll ? "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, barrier-free LL hand-overs, reduce + Adam inside)"
-                               : "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";
+            return "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";
         if (c->umma) return "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators)";
         if (c->fused) return "train_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "train_tile_kernel (fp32 FFMA, generic hidden sizes)";
@@ -2332,17 +2301,6 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
             fprintf(stderr, "\n   reduce phases:");
             for (int i = 1; i < 8 && h[64 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[64 + t * 8 + i] - h[64 + t * 8 + i - 1]);
             fprintf(stderr, "\n");
-        }
-        if (c->epoch_ll) {  // per-block global-timer stamps (ns) of the LL gradient step of minibatch 1, relative to the earliest
-            static long long g[128 * 8];
-            cudaMemcpy(g, c->umma_prof + 96, sizeof(g), cudaMemcpyDeviceToHost);
-            long long t0 = 0;
-            for (int b = 0; b < 128; ++b) if (g[b * 8] && (!t0 || g[b * 8] < t0)) t0 = g[b * 8];
-            for (int b = 0; b < 128; b += 1) {
-                fprintf(stderr, "blk %3d:", b);
-                for (int i = 0; i < 5; ++i) fprintf(stderr, " %6lld", g[b * 8 + i] ? g[b * 8 + i] - t0 : -1);
-                fprintf(stderr, "\n");
-            }
         }
     }
     *avg_ms = ms / (float)iters;
