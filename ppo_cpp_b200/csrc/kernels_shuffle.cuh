@@ -90,17 +90,22 @@ __device__ __forceinline__ void extend_window(const uint32_t* win, uint32_t* S) 
     for (int i = DEG; i < 2 * DEG - 1; ++i) S[i] = S[i - 3] + S[i - DEG];
 }
 
-// j[e][i] = rand() % (i + 1) for i = 1..n-1 of every epoch e (stream position k = e*(n-1) + i-1); j[e][0] = 0
+// j[e][i] = rand() % (i + 1) for i = 1..n-1 of every epoch e (stream position k = e*(n-1) + i-1); j[e][0] = 0.
+// Epoch subsets (multi-GPU: rank r builds the permutations of epochs r, r + R, ... and the ranks exchange them): blockIdx.y
+// selects epoch e = e0 + blockIdx.y * estride and the threads cover the L-blocks of the stream that overlap that epoch
+// (draws of a neighbouring epoch inside the first / last block are written too: they are correct, just not needed).
 __global__ void __launch_bounds__(128) shuffle_draw_kernel(const uint32_t* __restrict__ win, const Tables* __restrict__ tab, int n,
-                                                           int epochs, int* __restrict__ jbuf) {
+                                                           int epochs, int* __restrict__ jbuf, int e0, int estride) {
     __shared__ uint32_t S[2 * DEG - 1];
     if (threadIdx.x == 0) extend_window(win, S);
     __syncthreads();
     const long long total = (long long)epochs * (n - 1);
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int my_e = e0 + (int)blockIdx.y * estride;
+    const long long g_lo = ((long long)my_e * (n - 1)) / L;
+    const long long g = g_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long k0 = g * L;
-    if (g < epochs) jbuf[(size_t)g * n] = 0;
-    if (k0 >= total) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) jbuf[(size_t)my_e * n] = 0;
+    if (k0 >= total || k0 >= (long long)(my_e + 1) * (n - 1)) return;
     uint32_t c[DEG], w[DEG];
     poly_pow(tab->powL, (unsigned long long)g, c);
 #pragma unroll
@@ -150,8 +155,8 @@ __global__ void shuffle_advance_kernel(uint32_t* __restrict__ win, const Tables*
 }
 
 // cnt[e][p] = |S_p| = #{ s > p : j_s = p }
-__global__ void shuffle_count_kernel(const int* __restrict__ jbuf, int n, int* __restrict__ cnt) {
-    const int e = blockIdx.y;
+__global__ void shuffle_count_kernel(const int* __restrict__ jbuf, int n, int* __restrict__ cnt, int e0, int estride) {
+    const int e = e0 + blockIdx.y * estride;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < 1 || s >= n) return;
     const int j = jbuf[(size_t)e * n + s];
@@ -188,16 +193,17 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total) {
     return incl - v + (wid ? warp_tot[wid - 1] : 0);
 }
 
-__global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_totals_kernel(const int* __restrict__ cnt, int n, int nb, int* __restrict__ btot) {
-    const int e = blockIdx.y, i = blockIdx.x * SCAN_TILE + threadIdx.x;
+__global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_totals_kernel(const int* __restrict__ cnt, int n, int nb, int* __restrict__ btot, int e0,
+                                                                       int estride) {
+    const int e = e0 + blockIdx.y * estride, i = blockIdx.x * SCAN_TILE + threadIdx.x;
     const int v = (i <= n) ? cnt[(size_t)e * (n + 1) + i] : 0;
     int total;
     block_exclusive_scan_1024(v, &total);
     if (threadIdx.x == 0) btot[(size_t)e * nb + blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_blocks_kernel(int nb, int* __restrict__ btot) {  // nb <= 1024 * 1024
+__global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_blocks_kernel(int nb, int* __restrict__ btot, int e0, int estride) {  // nb <= 1024 * 1024
     __shared__ int carry_s;
-    const int e = blockIdx.x;
+    const int e = e0 + blockIdx.x * estride;
     int* b = btot + (size_t)e * nb;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -214,8 +220,8 @@ __global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_blocks_kernel(int nb, 
     }
 }
 __global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_final_kernel(const int* __restrict__ cnt, int n, int nb, const int* __restrict__ btot,
-                                                                      int* __restrict__ off, int* __restrict__ cur) {
-    const int e = blockIdx.y, i = blockIdx.x * SCAN_TILE + threadIdx.x;
+                                                                      int* __restrict__ off, int* __restrict__ cur, int e0, int estride) {
+    const int e = e0 + blockIdx.y * estride, i = blockIdx.x * SCAN_TILE + threadIdx.x;
     const int v = (i <= n) ? cnt[(size_t)e * (n + 1) + i] : 0;
     const int ex = block_exclusive_scan_1024(v, nullptr) + btot[(size_t)e * nb + blockIdx.x];
     if (i <= n) {
@@ -225,8 +231,8 @@ __global__ void __launch_bounds__(SCAN_TILE) shuffle_scan_final_kernel(const int
 }
 
 // list[e][off[j_s] ...] <- s   (order inside a bucket is arbitrary: the resolver takes maxima)
-__global__ void shuffle_scatter_kernel(const int* __restrict__ jbuf, int n, int* __restrict__ cur, int* __restrict__ list) {
-    const int e = blockIdx.y;
+__global__ void shuffle_scatter_kernel(const int* __restrict__ jbuf, int n, int* __restrict__ cur, int* __restrict__ list, int e0, int estride) {
+    const int e = e0 + blockIdx.y * estride;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < 1 || s >= n) return;
     const int j = jbuf[(size_t)e * n + s];
@@ -238,8 +244,8 @@ __global__ void shuffle_scatter_kernel(const int* __restrict__ jbuf, int n, int*
 
 // sigma[e][p] = value at position p after the swap chain applied to the identity
 __global__ void shuffle_resolve_kernel(const int* __restrict__ jbuf, const int* __restrict__ off, const int* __restrict__ list, int n,
-                                       int* __restrict__ sigma) {
-    const int e = blockIdx.y;
+                                       int* __restrict__ sigma, int e0, int estride) {
+    const int e = e0 + blockIdx.y * estride;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int* j = jbuf + (size_t)e * n;
@@ -280,6 +286,23 @@ __global__ void shuffle_compose_kernel(const int* __restrict__ prev, const int* 
     const int env_g = i / T, t = i - env_g * T;
     const int r = env_g / Nl, el = env_g - r * Nl;
     gather[pv] = r * T * Nl + t * Nl + el;
+}
+
+// Multi-GPU: sigma of the epochs this rank resolved -> the same place in every peer's sigma array (NVLink P2P stores;
+// peer[r] = this rank's mapping of rank r's array, peer[my rank] is skipped).  16-byte accesses where n allows.
+struct SigmaPeers {
+    int* p[8];
+    int rank, world;
+};
+__global__ void shuffle_publish_kernel(SigmaPeers peers, const int* __restrict__ sigma, int n, int e0, int estride) {
+    const int e = e0 + blockIdx.y * estride;
+    const size_t base = (size_t)e * n;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = sigma[base + i];
+        for (int r = 0; r < peers.world; ++r)
+            if (r != peers.rank) peers.p[r][base + i] = v;
+    }
 }
 
 }  // namespace shuf

@@ -192,13 +192,14 @@ struct ppo_core {
     unsigned char* mbox_peer[PPO_MAX_WORLD] = {};
     size_t mbox_bytes = 0, mbox_grad_off = 0, mbox_grad_slot = 0;
     size_t arena_off[8] = {};      // byte offsets of the five train-input buffers inside the arena
+    size_t arena_sigma_off = 0;    // ... and of the per-epoch swap-chain results (sh_sigma) when the ranks share their construction
     bool gathered = false;         // the train inputs of every rank are already in place (persistent rollout, P2P stores)
     bool mbox_ready = false;
     unsigned* sync_vars = nullptr;
     ppo_counters ctr{};
 };
 // sync_vars layout: scalars first, then three barrier flag arrays of SV_MAXBLK words each
-enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
+enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SHUF_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
        SV_COOP_FLAGS = SV_SCALARS, SV_ROLL_FLAGS = SV_COOP_FLAGS + SV_MAXBLK, SV_EPOCH_FLAGS = SV_ROLL_FLAGS + SV_MAXBLK,
        SV_COUNT = SV_EPOCH_FLAGS + SV_MAXBLK };
 
@@ -396,8 +397,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
                         c->cur_obs, c->cur_dones, c->cur_actions, c->last_values, c->raw_obs, c->raw_rew, c->raw_done,
                         c->nrew, c->step_ctr, c->env.state, c->env.t_env, c->env.resets, c->perm_dev, c->gather,
                         c->mbstats, c->partial, c->grad, c->loss_rows, c->loss_mean, c->gnorm, c->sq_partial, c->scratch,
-                        c->roll_partial, c->rng_win, c->shuf_tab, c->sh_j, c->sh_cnt, c->sh_off, c->sh_cur, c->sh_list, c->sh_sigma,
-                        c->sh_perm, c->sh_gather, c->sh_btot, c->sh_mbstats};
+                        c->roll_partial, c->rng_win, c->shuf_tab, c->sh_j, c->sh_cnt, c->sh_off, c->sh_cur, c->sh_list,
+                        c->arena_sigma_off ? nullptr : c->sh_sigma, c->sh_perm, c->sh_gather, c->sh_btot, c->sh_mbstats};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < B_COUNT; ++i)
@@ -452,6 +453,14 @@ static int core_alloc(ppo_core* c) {
             c->arena_off[i] = off;
             off += (((size_t)c->n_batch_global * widths[i] * sizeof(float)) + 255) & ~(size_t)255;
         }
+        // permutations: rank r resolves the swap chains of epochs r, r + W, ... and stores them into every rank's sigma array
+        {
+            const long long E = D.noptepochs, nbg = c->n_batch_global;
+            if (E >= 1 && nbg >= 2 && E * (nbg - 1) < 0x7fffffffLL) {
+                c->arena_sigma_off = off;
+                off += (((size_t)E * nbg * sizeof(int)) + 255) & ~(size_t)255;
+            }
+        }
         c->mbox_bytes = off;
         CU(cudaMalloc(&c->mbox_mem, c->mbox_bytes));
         CU(cudaMemsetAsync(c->mbox_mem, 0, c->mbox_bytes, c->stream));
@@ -471,7 +480,9 @@ static int core_alloc(ppo_core* c) {
             const size_t en = (size_t)E * nbg, en1 = (size_t)E * (nbg + 1);
             const int nb = (int)((nbg + 1 + shuf::SCAN_TILE - 1) / shuf::SCAN_TILE);
             ZA(c->rng_win, 31); ZA(c->shuf_tab, 1);
-            ZA(c->sh_j, en); ZA(c->sh_cnt, en1); ZA(c->sh_off, en1); ZA(c->sh_cur, en1); ZA(c->sh_list, en); ZA(c->sh_sigma, en);
+            ZA(c->sh_j, en); ZA(c->sh_cnt, en1); ZA(c->sh_off, en1); ZA(c->sh_cur, en1); ZA(c->sh_list, en);
+            if (c->arena_sigma_off) c->sh_sigma = reinterpret_cast<int*>(c->mbox_mem + c->arena_sigma_off);
+            else ZA(c->sh_sigma, en);
             ZA(c->sh_perm, en); ZA(c->sh_gather, en); ZA(c->sh_btot, (size_t)E * nb); ZA(c->sh_mbstats, (size_t)E * D.nminibatches);
             CU(cudaMallocHost(&c->win_pinned, 31 * sizeof(uint32_t)));
             static shuf::Tables host_tab;
@@ -1828,22 +1839,52 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
 // (kernels_shuffle.cuh), then the epochs back to back.  Nothing here waits for the host.
 static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int loss_row);
 static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e);
+// end of the sigma exchange: "my epochs are in your array" to every rank, then wait for every rank's (fenced flag protocol)
+__global__ void shuffle_exchange_kernel(PeerMailbox mbox, unsigned* seq_var) {
+    if (threadIdx.x == 0) {
+        const unsigned seq = *seq_var + 1u;
+        mbox.signal_all(PPO_MBOX_SHUF_CHANNEL, seq);
+        mbox.wait_all(PPO_MBOX_SHUF_CHANNEL, seq);
+        *seq_var = seq;
+    }
+}
+
 static int enqueue_shuffle(ppo_core* c) {
     const int n = c->n_batch_global, E = c->desc.noptepochs;
     const long long total = (long long)E * (n - 1);
-    CU(cudaMemsetAsync(c->sh_cnt, 0, sizeof(int) * (size_t)E * (n + 1), c->stream));
-    const int draw_threads = (int)((total + shuf::L - 1) / shuf::L);
-    LAUNCH(c, shuf::shuffle_draw_kernel, (std::max(draw_threads, E) + 127) / 128, 128, 0, c->rng_win, c->shuf_tab, n, E, c->sh_j);
+    // multi-GPU with mapped peer memory: rank r builds sigma of epochs r, r + W, ... (the swap chains of different epochs are
+    // independent, only the composition is sequential) and stores them into every rank's array over NVLink; every rank used
+    // to build all E x n_global of it (2.8 ms at 8 x 262 144 transitions, the longest thing beside the rollout)
+    const bool sharded = c->desc.world_size > 1 && c->mbox_ready && c->arena_sigma_off != 0 && getenv("PPO_DISABLE_SHUFFLE_SHARDING") == nullptr;
+    const int e0 = sharded ? c->desc.rank : 0, es = sharded ? c->desc.world_size : 1;
+    const int Emy = e0 < E ? (E - e0 + es - 1) / es : 0;
+    if (Emy > 0) {
+        for (int y = 0; y < Emy; ++y)
+            CU(cudaMemsetAsync(c->sh_cnt + (size_t)(e0 + y * es) * (n + 1), 0, sizeof(int) * (size_t)(n + 1), c->stream));
+        const int draw_blocks = (int)(((long long)(n - 1) + shuf::L - 1) / shuf::L) + 1;  // L-blocks of the stream overlapping one epoch
+        LAUNCH(c, shuf::shuffle_draw_kernel, dim3((draw_blocks + 127) / 128, Emy), 128, 0, c->rng_win, c->shuf_tab, n, E, c->sh_j, e0, es);
+    }
     LAUNCH(c, shuf::shuffle_advance_kernel, 1, 32, 0, c->rng_win, c->shuf_tab, (unsigned long long)total);
-    const dim3 gn((n + 255) / 256, E);
-    LAUNCH(c, shuf::shuffle_count_kernel, gn, 256, 0, c->sh_j, n, c->sh_cnt);
-    const int nb = (n + 1 + shuf::SCAN_TILE - 1) / shuf::SCAN_TILE;
-    LAUNCH(c, shuf::shuffle_scan_totals_kernel, dim3(nb, E), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot);
-    LAUNCH(c, shuf::shuffle_scan_blocks_kernel, E, shuf::SCAN_TILE, 0, nb, c->sh_btot);
-    LAUNCH(c, shuf::shuffle_scan_final_kernel, dim3(nb, E), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot, c->sh_off, c->sh_cur);
-    LAUNCH(c, shuf::shuffle_scatter_kernel, gn, 256, 0, c->sh_j, n, c->sh_cur, c->sh_list);
-    LAUNCH(c, shuf::shuffle_resolve_kernel, gn, 256, 0, c->sh_j, c->sh_off, c->sh_list, n, c->sh_sigma);
-    // (resolving the epochs one after the other on an L2-resident working set was measured at n = 2 M: no gain)
+    if (Emy > 0) {
+        const dim3 gn((n + 255) / 256, Emy);
+        LAUNCH(c, shuf::shuffle_count_kernel, gn, 256, 0, c->sh_j, n, c->sh_cnt, e0, es);
+        const int nb = (n + 1 + shuf::SCAN_TILE - 1) / shuf::SCAN_TILE;
+        LAUNCH(c, shuf::shuffle_scan_totals_kernel, dim3(nb, Emy), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot, e0, es);
+        LAUNCH(c, shuf::shuffle_scan_blocks_kernel, Emy, shuf::SCAN_TILE, 0, nb, c->sh_btot, e0, es);
+        LAUNCH(c, shuf::shuffle_scan_final_kernel, dim3(nb, Emy), shuf::SCAN_TILE, 0, c->sh_cnt, n, nb, c->sh_btot, c->sh_off, c->sh_cur, e0, es);
+        LAUNCH(c, shuf::shuffle_scatter_kernel, gn, 256, 0, c->sh_j, n, c->sh_cur, c->sh_list, e0, es);
+        LAUNCH(c, shuf::shuffle_resolve_kernel, gn, 256, 0, c->sh_j, c->sh_off, c->sh_list, n, c->sh_sigma, e0, es);
+        // (resolving the epochs one after the other on an L2-resident working set was measured at n = 2 M: no gain)
+    }
+    if (sharded) {
+        if (Emy > 0) {
+            shuf::SigmaPeers sp{};
+            sp.rank = c->desc.rank; sp.world = c->desc.world_size;
+            for (int r = 0; r < sp.world; ++r) sp.p[r] = reinterpret_cast<int*>(c->mbox_peer[r] + c->arena_sigma_off);
+            LAUNCH(c, shuf::shuffle_publish_kernel, dim3(std::min((n + 255) / 256, 4 * c->sm_count), Emy), 256, 0, sp, c->sh_sigma, n, e0, es);
+        }
+        LAUNCH(c, shuffle_exchange_kernel, 1, 32, 0, make_mailbox(c, false), c->sync_vars + SV_SHUF_SEQ);
+    }
     for (int e = 0; e < E; ++e)
         LAUNCH(c, shuf::shuffle_compose_kernel, (n + 255) / 256, 256, 0, e ? c->sh_perm + (size_t)(e - 1) * n : (const int*)nullptr,
                c->sh_sigma + (size_t)e * n, n, c->desc.n_steps, c->desc.n_envs, c->sh_perm + (size_t)e * n, c->sh_gather + (size_t)e * n);

@@ -83,6 +83,7 @@ constexpr int PPO_MAX_WORLD = 8;
 constexpr int PPO_MBOX_CHANNELS = 1024;  // channel = cooperating CTA index (gradient slices); the last one carries the moments
 constexpr int PPO_MBOX_MOMENT_CHANNEL = PPO_MBOX_CHANNELS - 1;
 constexpr int PPO_MBOX_DONE_CHANNEL = PPO_MBOX_CHANNELS - 2;  // end-of-rollout "my rows are in your buffers"
+constexpr int PPO_MBOX_SHUF_CHANNEL = PPO_MBOX_CHANNELS - 3;  // "the permutations of my epochs are in your array"
 constexpr size_t PPO_MBOX_MOMENT_SLOT = 2048;  // bytes: 2*(D+1) doubles as 2 LL words each, D <= 32
 constexpr size_t PPO_MBOX_FLAG_BYTES = (size_t)PPO_MBOX_CHANNELS * PPO_MAX_WORLD * sizeof(unsigned);
 
