@@ -385,6 +385,14 @@ def run_ours(args):
     if world > 1 and args.parity:
         parity = multi_gpu_parity(rank, world, local, (h1, h2))
 
+    # ---- BASELINE.json configs[3] (C4): 65 536 envs, MLP [256,256] (W family, tcgen05 layer-wise GEMMs), 4 M transitions per
+    # update sharded over the `world` GPUs — strong scaling: the global batch is fixed, every rank owns 65 536 / world envs
+    c4 = None
+    if world > 1 and args.c4 and 65536 % world == 0:
+        c.close()
+        c = None
+        c4 = c4_sharded(core, rank, world, local, dev, None)
+
     # ---- C5 microbench (BASELINE.json configs[4]): GAE / VecNormalize / loss kernels over a 16 M-transition buffer
     microbench = None
     if rank == 0 and world == 1 and args.microbench:
@@ -411,6 +419,8 @@ def run_ours(args):
             line["parity"] = parity
         if microbench is not None:
             line["microbench"] = microbench
+        if c4 is not None:
+            line["c4"] = c4
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
@@ -419,6 +429,54 @@ def run_ours(args):
         c.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def c4_sharded(core, rank, world, local, dev, _unused):
+    """One C4 update = rollout of 64 steps x 65 536 envs + 10 epochs x 32 minibatches of 131 072 samples, [256,256], sharded."""
+    import torch
+    import torch.distributed as dist
+    from ppo_cpp_b200.dist import setup_comm
+    n_envs = 65536 // world
+    c = core.PPOCore(device=local, hidden1=256, hidden2=256, n_envs=n_envs, n_steps=64, nminibatches=32, noptepochs=10, seed=1234,
+                     rank=rank, world_size=world, env_offset=rank * n_envs, n_envs_global=65536)
+    c.init_orthogonal(7)
+    setup_comm(core, c, rank, world)
+    c.shuffle_seed(42)
+    c.synth_env_reset()
+    stream = torch.cuda.ExternalStream(c.stream, device=dev)
+
+    def sync():
+        c.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(2):
+        c.rollout_synthetic()
+        c.train_update(LR, CLIPRANGE, want_losses=False)
+    sync()
+    c.counters(reset=True)
+    K = 3
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for e0, e1, em in evs:
+        e0.record(stream)
+        c.rollout_synthetic()
+        em.record(stream)
+        c.train_update(LR, CLIPRANGE, want_losses=False)
+        e1.record(stream)
+    sync()
+    ctr = c.counters()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b, _ in evs), sum(m.elapsed_time(b) for _, b, m in evs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fam = c.kernel_family("train")
+    err = c.comm_error()
+    c.close()
+    nb = 65536 * 64
+    ms, ms_train = float(t[0]) / K, float(t[1]) / K
+    return {"workload": "C4: 65536 envs, MLP [256,256], 4194304 transitions per update, sharded over %d GPUs (strong scaling)" % world,
+            "n_envs_per_gpu": n_envs, "minibatch_per_gpu": nb // 32 // world, "steps": K, "warmup": 2, "ms_per_step": ms, "train_ms_per_step": ms_train,
+            "value": nb / (ms * 1e-3), "unit": UNIT, "update_samples_per_sec": nb * 10 / (ms_train * 1e-3), "kernel_family": fam,
+            "train_tflops_algorithmic": nb * 10 * train_flops_per_sample(18, 18, 256, 256) / (ms_train * 1e-3) / 1e12,
+            "gpu_launches": int(ctr["kernel_launches"]), "graph_launches": int(ctr["graph_launches"]), "mailbox_timeout": bool(err)}
 
 
 def multi_gpu_parity(rank, world, local, hidden):
@@ -469,6 +527,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", dest="microbench", action="store_false")
     ap.add_argument("--no-parity", dest="parity", action="store_false")
+    ap.add_argument("--no-c4", dest="c4", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1051,6 +1051,132 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const Reduce
     }
 }
 
+// The same gradient step for parameter vectors too long for RA_MAXJ chunks per block (the W family: [256,256] has 2 285
+// chunks): a block walks its chunks blk, blk + nblk, ... in passes — (A) column sums of every owned chunk, stored to r.grad
+// and, multi-GPU, into every rank's mailbox slot; (B) multi-GPU: all peers' values of every owned chunk (the NVLink flights of
+// all chunks overlap), summed in rank order; sum of squares; grid barrier; (C) clip + Adam per chunk, the gradient re-read
+// from r.grad (this block wrote it).  Same arithmetic and summation order as reduce_adam_device.
+__global__ void __launch_bounds__(256) grad_reduce_adam_big_kernel(const ReduceAdamArgs r) {
+    __shared__ float part[4][64];
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    GridBarrier bar{r.bar_ctr, gridDim.x, *r.bar_gen};
+    const AdamArgs& a = r.adam;
+    const int blk = blockIdx.x, nblk = gridDim.x;
+    const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int nchunks = (r.PS + 63) >> 6;
+    const int world = r.mbox.world;
+    const unsigned seq = world > 1 ? (*r.mbox_seq + 1u) : 0u;
+    const float b1p = a.bpow_in[0], b2p = a.bpow_in[1];
+    double q = 0.0;
+    for (int chunk0 = blk; chunk0 < nchunks; chunk0 += 4 * nblk) {  // pass A, four chunks per trip: their loads are in flight together
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int g0 = rg; g0 < r.G; g0 += 64) {
+            float v[4][16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (chunk0 + j * nblk) * 64 + lane_c;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int g = g0 + 4 * u;
+                    v[j][u] = (c < r.PS && g < r.G) ? __ldcg(r.partial + (size_t)g * r.PS + c) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc[j] += v[j][u];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int chunk = chunk0 + j * nblk;
+            if (chunk >= nchunks) break;  // block-uniform
+            const int c = chunk * 64 + lane_c;
+            __syncthreads();
+            part[rg][lane_c] = acc[j];
+            __syncthreads();
+            if (rg == 0 && c < r.PS) {
+                const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
+                const float gs = (float)t;
+                if (world > 1) {
+                    for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gs), seq);
+                } else {
+                    r.grad[c] = gs;
+                    if (c < a.P) q += (double)gs * (double)gs;
+                }
+            }
+        }
+    }
+    if (world > 1 && rg == 0) {  // pass B
+        for (int chunk = blk; chunk < nchunks; chunk += nblk) {
+            const int c = chunk * 64 + lane_c;
+            if (c < r.PS) {
+                float t = 0.f;
+                for (int s0 = 0; s0 < world; s0 += 4) {
+                    unsigned w[4];
+                    r.mbox.ll_wait4(seq, (size_t)c, s0, w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (s0 + k < world) t += __uint_as_float(w[k]);
+                }
+                r.grad[c] = t;
+                if (c < a.P) q += (double)t * (double)t;
+            }
+        }
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) r.sq_partial[blk] = red[0] + red[1];
+    bar.sync();
+    if (threadIdx.x < 32) {
+        double ss = 0.0;
+        for (int b = threadIdx.x; b < nblk; b += 32) ss += __ldcg(r.sq_partial + b);
+        ss = warp_sum(ss);
+        if (threadIdx.x == 0) {
+            const float gnorm = (float)sqrt(ss);
+            const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, a.clip_norm);
+            float scale = __fmul_rn(a.clip_norm, fminf(inv, invc));
+            if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);
+            s_scale = scale;
+            if (blk == 0) *a.gnorm_out = gnorm;
+        }
+    }
+    __syncthreads();
+    if (blk == 0 && threadIdx.x == 0) {  // the loss sums may sit in another block's chunk: every chunk passed the barrier
+        const float* Ls = r.grad + a.P;
+        float L[5];
+        for (int k = 0; k < 5; ++k) L[k] = __ldcg(Ls + k);
+        a.loss_row[0] = L[L_PG] * a.invB;
+        a.loss_row[1] = 0.5f * (L[L_VF] * a.invB);
+        a.loss_row[2] = L[L_ENT] * a.inv_world;
+        a.loss_row[3] = 0.5f * (L[L_KL] * a.invB);
+        a.loss_row[4] = L[L_CLIP] * a.invB;
+    }
+    if (rg == 0) {  // pass C
+        const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+        for (int chunk = blk; chunk < nchunks; chunk += nblk) {
+            const int c = chunk * 64 + lane_c;
+            if (c < a.P) {
+                const float g = __fmul_rn(__ldcg(r.grad + c), s_scale);
+                float m = a.m[c], v = a.v[c];
+                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+                a.m[c] = m;
+                a.v[c] = v;
+                a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.bpow_out[0] = __fmul_rn(b1p, a.beta1);
+        a.bpow_out[1] = __fmul_rn(b2p, a.beta2);
+        *r.bar_gen = bar.gen;
+        if (world > 1) *r.mbox_seq = seq;
+    }
+}
+
 // mean over the rows of the per-step loss table (colwise().mean(), ppo2.hpp:335)
 __global__ void loss_mean_kernel(const float* __restrict__ rows, int nrows, float* __restrict__ out) {
     const int c = threadIdx.x;

@@ -138,6 +138,7 @@ struct ppo_core {
     int n_sq_blocks = 0;
     bool perm_set = false;
     bool coop = false;        // fused cooperative reduce+Adam kernel usable (single GPU, grid co-resident)
+    bool coop_big = false;    // ... in its many-chunks-per-block form
     int coop_grid = 0;
     bool use_graph = false;   // replay each epoch's launches as a CUDA graph
     struct EpochGraph {
@@ -609,11 +610,17 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             int per_sm = 0, coop_ok = 0;
             cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, desc->device);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grad_reduce_adam_coop_kernel, 256, 0);
+            {
+                int per_big = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_big, grad_reduce_adam_big_kernel, 256, 0);
+                per_sm = std::min(per_sm, per_big);
+            }
             // cooperative reduce(+allreduce)+Adam: blocks own 64-column chunks, up to RA_MAXJ chunks each; multi-GPU runs
             // use it once the peer mailboxes are mapped (fast_path), with one mailbox channel per block
             const int nchunks = (c->PS + 63) / 64;
             c->coop_grid = std::min(nchunks, std::min(per_sm * c->sm_count, PPO_MBOX_CHANNELS - 1));
-            c->coop = coop_ok && c->coop_grid > 0 && nchunks <= c->coop_grid * RA_MAXJ && getenv("PPO_DISABLE_COOP") == nullptr;
+            c->coop = coop_ok && c->coop_grid > 0 && getenv("PPO_DISABLE_COOP") == nullptr;
+            c->coop_big = nchunks > c->coop_grid * RA_MAXJ;  // long parameter vectors (W family): grad_reduce_adam_big_kernel
             if (c->coop && c->coop_grid > c->n_sq_blocks) {  // sq_partial is sized for 256-column blocks
                 cudaFree(c->sq_partial);
                 c->sq_partial = nullptr;
@@ -1812,7 +1819,8 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
         ad.invB = a.invB; ad.inv_world = 1.0f / (float)W;
         ad.loss_row = c->loss_rows + (size_t)loss_row * 5; ad.gnorm_out = c->gnorm;
         void* kargs[] = {&r};
-        CU(cudaLaunchCooperativeKernel((void*)grad_reduce_adam_coop_kernel, dim3(c->coop_grid), dim3(256), kargs, 0, c->stream));
+        CU(cudaLaunchCooperativeKernel(c->coop_big ? (void*)grad_reduce_adam_big_kernel : (void*)grad_reduce_adam_coop_kernel, dim3(c->coop_grid),
+                                       dim3(256), kargs, 0, c->stream));
         c->ctr.kernel_launches++;
         c->bpow_slot ^= 1;
         return PPO_OK;
