@@ -49,6 +49,15 @@ struct RolloutArgs {
     size_t off_obs, off_act, off_val, off_nlp, off_ret;
     size_t row_off;
     unsigned* done_seq;  // sequence number of the end-of-rollout cross-rank barrier
+    // host-env mode (h_actions != NULL; Runner::run against a host env, runner.hpp:116-129): instead of the synthetic env the
+    // CTA writes its actions into mapped pinned host memory, raises its flag, and polls the host's flag for the env's answer
+    // (raw observation, reward, done in mapped pinned memory).  One kernel for the whole rollout: no launch, no stream
+    // synchronisation and no cudaMemcpy per env step — per step it costs one PCIe write, one host poll, one PCIe read.
+    float* h_actions;             // [n][A]   device -> host
+    const float *h_obs, *h_rew, *h_done;  // [n][O], [n], [n]   host -> device
+    unsigned* h_act_flag;         // [gridDim.x]: t + 1 once this CTA's actions of step t are in h_actions
+    const unsigned* h_obs_flag;   // t + 1 once the env's answer to step t is in place; PPO_HOST_ENV_ABORT = stop
+    unsigned* host_err;           // set when the host never answered (bounded wait)
     long long* prof;  // optional [32] phase timestamps of CTA 0 during env step 1 (PPO_ROLLOUT_PROF=1)
 };
 
@@ -58,6 +67,7 @@ struct RolloutArgs {
     } while (0)
 
 constexpr int R_TM = 32, R_NTH = 256;
+constexpr unsigned PPO_HOST_ENV_ABORT = 0xffffffffu;
 
 // rank r's copy of THIS rank's slab of a train-input buffer (row t = 0), or the local slab on a single GPU
 __device__ __forceinline__ float* rslab(const RolloutArgs& a, int r, size_t off, int width, float* local) {
@@ -127,6 +137,9 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
     const bool merge = a.upd_obs || a.upd_ret;
     GridBarrier bar{a.bar_ctr, gridDim.x, *a.bar_gen};
     const int world = a.mbox.world;
+    const bool host_env = a.h_actions != nullptr;
+    __shared__ int s_abort;
+    if (tid == 0) s_abort = 0;
     const unsigned seq0 = world > 1 ? *a.mbox_seq : 0u;
     const unsigned dseq0 = world > 1 ? *a.done_seq : 0u;
 
@@ -169,9 +182,33 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
         R_PROF();  // step start
         double ps = 0.0, pq = 0.0;  // this thread's column partial over the CTA's envs (threads 0..D)
         const float pivot = (tid < D) ? s_mean[tid] : 0.f;
+        // host-env mode runs the tile loop twice: pass 0 = policy step of every tile + actions to the host, then the
+        // exchange with the host, pass 1 = the env's answer of every tile + moments
+        for (int pass = 0; pass < (host_env ? 2 : 1); ++pass) {
+        if (pass == 1) {
+            __syncthreads();  // every action store of this CTA has been issued
+            if (tid == 0) {
+                __threadfence_system();
+                st_release_sys(a.h_act_flag + blockIdx.x, (unsigned)t + 1u);
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned v, spins = 0;
+                while ((v = *reinterpret_cast<const volatile unsigned*>(a.h_obs_flag)) != (unsigned)t + 1u && v != PPO_HOST_ENV_ABORT) {
+                    if (((++spins) & 0xffu) == 0u && globaltimer_ns() - t0 > 120000000000ull) {  // 120 s: the host is gone
+                        *a.host_err = 1u;
+                        v = PPO_HOST_ENV_ABORT;
+                        break;
+                    }
+                }
+                s_abort = (v == PPO_HOST_ENV_ABORT) ? 1 : 0;
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (s_abort) break;
+        }
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int r0 = (tile0 + tl) * TM, nv = min(TM, a.n - r0);
             float* Xs = OBS + tl * O * TM;
+            if (pass == 0) {
             // -- store the observation the policy acts on (runner.hpp:75-78)
             for (int r = 0; r < world; ++r) {
                 float* dst = rslab(a, r, a.off_obs, O, a.obs_store) + ((size_t)t * a.n + r0) * O;
@@ -233,6 +270,26 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 }
             }
             R_PROF();  // sample + stores issued
+            }  // pass 0
+            if (host_env) {
+                if (pass == 0) {  // actions of this tile -> the host's array (clipping is the env's business, hexapod_env.hpp:140)
+                    for (int e = tid; e < nv * A; e += NTH) {
+                        const int m = e / A, j = e - m * A;
+                        a.h_actions[(size_t)r0 * A + e] = Ac[j * (TM + 1) + m];
+                    }
+                    __syncthreads();  // Ac is reused by the next tile
+                    continue;
+                }
+                // the env's answer (mapped host memory, read past every cache: the same addresses carry new data every step)
+                for (int e = tid; e < nv * D; e += NTH) RAW[tl * TM * D + e] = __ldcv(a.h_obs + (size_t)r0 * D + e);
+                if (tid < nv) {
+                    REW[tl * TM + tid] = __ldcv(a.h_rew + r0 + tid);
+                    DONE[tl * TM + tid] = __ldcv(a.h_done + r0 + tid);
+                }
+                __syncthreads();
+                if (tid < nv) RET[tl * TM + tid] = __fadd_rn(__fmul_rn(RET[tl * TM + tid], a.norm_gamma), REW[tl * TM + tid]);  // env_normalize.hpp:71
+                __syncthreads();
+            } else {
             // -- synthetic env step: thread (m, blk) advances 4 state dims
             for (int e = tid; e < TM * nblk; e += NTH) {
                 const int m = e % TM, blk = e / TM;
@@ -272,6 +329,7 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 RET[tl * TM + m] = __fadd_rn(__fmul_rn(RET[tl * TM + m], a.norm_gamma), REW[tl * TM + m]);  // env_normalize.hpp:71
             }
             __syncthreads();
+            }  // synthetic env
             R_PROF();  // env step done
             // -- batch moments of this tile (fp64 around the running mean), accumulated over the CTA's tiles
             if (merge) {
@@ -290,6 +348,8 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 }
             }
         }
+        }  // passes
+        if (s_abort) break;  // host-env mode: the env aborted (every CTA sees the same flag at the same step)
         if (merge) {
             // -- RunningStatistics::update over ALL envs: partials -> grid barrier -> fixed-order total in every CTA
             // partial layout [parity][column][cta]: the totals below read 32 consecutive CTAs per load instruction

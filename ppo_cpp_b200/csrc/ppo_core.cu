@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "device_common.cuh"
@@ -183,6 +184,8 @@ struct ppo_core {
     unsigned stage_ctr = 0;
     float* scratch = nullptr;    // device scratch for host-pointer calls
     size_t scratch_floats = 0;
+    float* hx_mem = nullptr;     // host-env exchange of the persistent rollout kernel: flags, actions, obs / rew / done (mapped pinned)
+    float* hx_dev = nullptr;     // ... its device address
     void* gae_ab = nullptr;      // per-(chunk, env) affine maps of the exact chunked GAE (gamma*lam near 1)
     size_t gae_ab_bytes = 0;
 
@@ -361,13 +364,24 @@ extern "C" int ppo_meta_parse(const char* path, ppo_meta_info* info, float* para
     return PPO_OK;
 }
 
+// the largest dynamic shared memory a kernel may ask for: the device's opt-in maximum minus the kernel's static shared memory
+template <class K>
+static int max_dynamic_smem(K kernel, size_t max_smem) {
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) {
+        cudaGetLastError();
+        return (int)max_smem;
+    }
+    return (int)(max_smem - std::min(max_smem, (size_t)fa.sharedSizeBytes));
+}
+
 template <int TM>
 static int set_smem_attrs(size_t max_smem) {
     // The attribute is per function and per device, i.e. shared by every core of the process: always raise it to the
     // device's opt-in maximum, so that a core created later with smaller hidden sizes (EnvNormalize's private [4,5] core
     // beside a [64,64] PPO2 core) cannot lower the limit under a live core.  What a launch uses is its own smem argument.
-    CU(cudaFuncSetAttribute(train_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    CU(cudaFuncSetAttribute(policy_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(train_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(train_tile_kernel<TM>, max_smem)));
+    CU(cudaFuncSetAttribute(policy_tile_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(policy_tile_kernel<TM>, max_smem)));
     return PPO_OK;
 }
 
@@ -380,6 +394,7 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
         if (c->mbox_peer[r] && r != c->desc.rank) cudaIpcCloseMemHandle(c->mbox_peer[r]);
     if (c->mbox_mem) cudaFree(c->mbox_mem);
     if (c->gae_ab) cudaFree(c->gae_ab);
+    if (c->hx_mem) cudaFreeHost(c->hx_mem);
     if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
     for (auto& g : c->graphs)
@@ -572,8 +587,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             c->fused = (c->d.H1 % 4 == 0) && (c->d.H2 % 4 == 0) && c->fused_train_smem <= max_smem && c->fused_policy_smem <= max_smem &&
                        getenv("PPO_DISABLE_FUSED") == nullptr;
             if (c->fused) {
-                if (cudaFuncSetAttribute(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
-                    cudaFuncSetAttribute(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
+                if (cudaFuncSetAttribute(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(train_fused_kernel<F_TM_TRAIN, F_NT_TRAIN>, max_smem)) != cudaSuccess ||
+                    cudaFuncSetAttribute(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(policy_fused_kernel<F_TM_POLICY, F_NT_POLICY>, max_smem)) != cudaSuccess) {
                     st = fail(PPO_ERR_CUDA, "cudaFuncSetAttribute(fused kernels) failed: %s", cudaGetErrorString(cudaGetLastError()));
                     break;
                 }
@@ -662,7 +677,7 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                     // cannot put two CTAs on one SM (they would run at half speed and everybody waits at the step barrier)
                     size_t smem = (size_t)L.total_bytes;
                     if (grid <= c->sm_count) smem = std::max(smem, std::min(max_smem, (size_t)120 * 1024));
-                    if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
+                    if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(rollout_persistent_kernel, max_smem)) != cudaSuccess) {
                         cudaGetLastError();
                         break;
                     }
@@ -1368,8 +1383,115 @@ extern "C" int ppo_runner_finish(ppo_core* c) {
                       c->desc.n_steps, c->desc.n_envs, c->desc.gamma, c->desc.lam, nullptr, slab(c, B_RETURNS, 0));
 }
 
+// launch arguments of rollout_persistent_kernel for the core's current state (synthetic env; the host-env mode adds its buffers)
+static RolloutArgs make_rollout_args(ppo_core* c) {
+    const ppo_core_desc& D = c->desc;
+    RolloutArgs r{};
+    r.d = c->d; r.params = c->params; r.n = D.n_envs; r.T = D.n_steps; r.tpc = c->roll_tpc;
+    r.seed = D.seed; r.env_id0 = (uint32_t)D.env_offset; r.step_ctr = c->step_ctr; r.env = c->env; r.st = c->st; r.ret = c->ret;
+    r.norm_gamma = D.norm_gamma; r.clip_obs = D.clip_obs; r.clip_rew = D.clip_reward; r.eps = D.norm_epsilon;
+    r.norm_obs = D.norm_obs; r.norm_reward = D.norm_reward;
+    r.upd_obs = D.training && D.norm_obs; r.upd_ret = D.training && D.norm_reward;
+    r.partial = c->roll_partial; r.cur_obs = c->cur_obs; r.cur_dones = c->cur_dones; r.last_values = c->last_values;
+    r.obs_store = slab(c, B_OBS, 0); r.act_store = slab(c, B_ACTIONS, 0); r.val_store = slab(c, B_VALUES, 0);
+    r.nlp_store = slab(c, B_NEGLOGP, 0); r.dones_store = slab(c, B_DONES, 0); r.rew_store = slab(c, B_TRUE_REW, 0);
+    r.urew_store = slab(c, B_UNNORM_REW, 0); r.ret_store = slab(c, B_RETURNS, 0);
+    r.gamma = D.gamma; r.lam = D.lam;
+    r.bar_ctr = c->sync_vars + SV_ROLL_FLAGS; r.bar_gen = c->sync_vars + SV_ROLL_GEN;
+    r.n_global = D.n_envs * D.world_size;
+    r.mbox = make_mailbox(c, false); r.mbox_seq = c->sync_vars + SV_MOM_SEQ; r.done_seq = c->sync_vars + SV_DONE_SEQ;
+    r.off_obs = c->arena_off[B_OBS]; r.off_act = c->arena_off[B_ACTIONS]; r.off_val = c->arena_off[B_VALUES];
+    r.off_nlp = c->arena_off[B_NEGLOGP]; r.off_ret = c->arena_off[B_RETURNS];
+    r.row_off = (size_t)D.rank * c->n_batch_local;
+    r.host_err = c->sync_vars + SV_ERR;
+    return r;
+}
+
+static int prefetch_shuffle(ppo_core* c);
+
+// The one-kernel host-env rollout pays one PCIe round trip per env step and reads the env's answer with SM loads from
+// mapped host memory: a win while a step is latency-bound (C1: 1 env, 49 -> 17 us per env step), a loss once the
+// observations are hundreds of KB per step (C3, 4096 envs: measured 326 us per step against 64 us with the copy engine).
+static bool host_persistent_ok(const ppo_core* c) {
+    return c->persistent_rollout && c->desc.world_size == 1 && c->desc.n_envs <= 512 && getenv("PPO_DISABLE_HOST_PERSISTENT") == nullptr;
+}
+
+// Host-env rollout as ONE persistent kernel (kernels_rollout.cuh, host-env mode): the kernel and this loop hand the actions
+// and the env's answers back and forth through mapped pinned memory and two flags.
+static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user, float* actions) {
+    const ppo_core_desc& D = c->desc;
+    const size_t N = (size_t)D.n_envs, O = (size_t)c->d.O, A = (size_t)c->d.A;
+    if (!c->hx_mem) {
+        // [obs flag | act flags (grid) | actions N*A | obs N*O | rew N | done N], mapped + pinned
+        const size_t words = 64 + (size_t)((c->roll_grid + 63) & ~63) + N * A + N * O + 2 * N;
+        CU(cudaHostAlloc(reinterpret_cast<void**>(&c->hx_mem), words * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(c->hx_mem, 0, words * sizeof(float));
+        CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hx_dev), c->hx_mem, 0));
+    }
+    const size_t off_actf = 64, off_act = off_actf + (size_t)((c->roll_grid + 63) & ~63), off_obs = off_act + N * A, off_rew = off_obs + N * O,
+                 off_done = off_rew + N;
+    volatile unsigned* obs_flag = reinterpret_cast<volatile unsigned*>(c->hx_mem);
+    volatile unsigned* act_flag = reinterpret_cast<volatile unsigned*>(c->hx_mem) + off_actf;
+    float* h_act = c->hx_mem + off_act;
+    CU(cudaStreamSynchronize(c->stream));  // nothing of an earlier kernel may still look at the flags
+    *obs_flag = 0u;
+    for (int b = 0; b < c->roll_grid; ++b) act_flag[b] = 0u;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    TRY(prefetch_shuffle(c));
+    RolloutArgs r = make_rollout_args(c);
+    r.h_actions = c->hx_dev + off_act;
+    r.h_obs = c->hx_dev + off_obs; r.h_rew = c->hx_dev + off_rew; r.h_done = c->hx_dev + off_done;
+    r.h_act_flag = reinterpret_cast<unsigned*>(c->hx_dev) + off_actf;
+    r.h_obs_flag = reinterpret_cast<const unsigned*>(c->hx_dev);
+    void* kargs[] = {&r};
+    CU(cudaLaunchCooperativeKernel((void*)rollout_persistent_kernel, dim3(c->roll_grid), dim3(R_NTH), kargs, c->roll_smem, c->stream));
+    c->ctr.kernel_launches++;
+    int st = PPO_OK;
+    for (int t = 0; t < D.n_steps && st == PPO_OK; ++t) {
+        // the CTAs' actions of step t
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        for (int b = 0; b < c->roll_grid; ++b) {
+            while (act_flag[b] != (unsigned)t + 1u) {
+                if (((++spins) & 0xfffffu) == 0u) {
+                    if (cudaStreamQuery(c->stream) != cudaErrorNotReady) { st = fail(PPO_ERR_CUDA, "host-env rollout: the kernel ended at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); break; }
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) { st = fail(PPO_ERR_CUDA, "host-env rollout: no actions from the device at step %d", t); break; }
+                }
+            }
+            if (st != PPO_OK) break;
+        }
+        if (st != PPO_OK) break;
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        memcpy(actions, h_act, N * A * sizeof(float));
+        c->ctr.d2h_bytes += N * A * sizeof(float);
+        const float *o = nullptr, *rw = nullptr, *dn = nullptr;
+        if (step(user, t, actions, &o, &rw, &dn) != 0 || !o || !rw || !dn) {
+            st = fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: the env aborted at step %d", t);
+            break;
+        }
+        memcpy(c->hx_mem + off_obs, o, N * O * sizeof(float));
+        memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
+        memcpy(c->hx_mem + off_done, dn, N * sizeof(float));
+        c->ctr.h2d_bytes += N * (O + 2) * sizeof(float);
+        __atomic_thread_fence(__ATOMIC_RELEASE);
+        *obs_flag = (unsigned)t + 1u;
+    }
+    if (st != PPO_OK) {
+        char keep[1024];
+        strncpy(keep, g_err, sizeof(keep));
+        *obs_flag = PPO_HOST_ENV_ABORT;  // releases the kernel
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        cudaStreamSynchronize(c->stream);
+        strncpy(g_err, keep, sizeof(g_err));
+        return st;
+    }
+    return PPO_OK;  // bootstrap value + GAE run at the kernel's end (asynchronous, like ppo_runner_finish)
+}
+
 extern "C" int ppo_runner_rollout_host(ppo_core* c, ppo_env_step_fn step, void* user, float* actions) {
     if (!c || !step || !actions) return fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: NULL argument");
+    CU(cudaSetDevice(c->desc.device));
+    if (host_persistent_ok(c)) return rollout_host_persistent(c, step, user, actions);
     for (int t = 0; t < c->desc.n_steps; ++t) {
         TRY(ppo_runner_act(c, t, actions, PPO_HOST));
         const float *o = nullptr, *r = nullptr, *d = nullptr;
@@ -1399,7 +1521,8 @@ extern "C" int ppo_runner_rollout_replay(ppo_core* c, const float* raw_obs, cons
     if (!c || !raw_obs || !raw_rew || !done) return fail(PPO_ERR_INVALID, "ppo_runner_rollout_replay: NULL argument");
     const size_t N = (size_t)c->desc.n_envs;
     ReplayEnv env{raw_obs, raw_rew, done, actions_out, N * c->d.O, N, N * c->d.A};
-    if (actions_out) {  // every step's actions land directly in their row of actions_out
+    const bool persistent = host_persistent_ok(c);
+    if (actions_out && !persistent) {  // every step's actions land directly in their row of actions_out
         for (int t = 0; t < c->desc.n_steps; ++t) {
             float* a = actions_out + (size_t)t * env.na;
             TRY(ppo_runner_act(c, t, a, PPO_HOST));
@@ -1445,23 +1568,7 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
     TRY(prefetch_shuffle(c));  // the next update's permutations, on stream2, while this rollout runs
     if (c->persistent_rollout && fast_path(c)) {
         const ppo_core_desc& D = c->desc;
-        RolloutArgs r{};
-        r.d = c->d; r.params = c->params; r.n = D.n_envs; r.T = D.n_steps; r.tpc = c->roll_tpc;
-        r.seed = D.seed; r.env_id0 = (uint32_t)D.env_offset; r.step_ctr = c->step_ctr; r.env = c->env; r.st = c->st; r.ret = c->ret;
-        r.norm_gamma = D.norm_gamma; r.clip_obs = D.clip_obs; r.clip_rew = D.clip_reward; r.eps = D.norm_epsilon;
-        r.norm_obs = D.norm_obs; r.norm_reward = D.norm_reward;
-        r.upd_obs = D.training && D.norm_obs; r.upd_ret = D.training && D.norm_reward;
-        r.partial = c->roll_partial; r.cur_obs = c->cur_obs; r.cur_dones = c->cur_dones; r.last_values = c->last_values;
-        r.obs_store = slab(c, B_OBS, 0); r.act_store = slab(c, B_ACTIONS, 0); r.val_store = slab(c, B_VALUES, 0);
-        r.nlp_store = slab(c, B_NEGLOGP, 0); r.dones_store = slab(c, B_DONES, 0); r.rew_store = slab(c, B_TRUE_REW, 0);
-        r.urew_store = slab(c, B_UNNORM_REW, 0); r.ret_store = slab(c, B_RETURNS, 0);
-        r.gamma = D.gamma; r.lam = D.lam;
-        r.bar_ctr = c->sync_vars + SV_ROLL_FLAGS; r.bar_gen = c->sync_vars + SV_ROLL_GEN;
-        r.n_global = D.n_envs * D.world_size;
-        r.mbox = make_mailbox(c, false); r.mbox_seq = c->sync_vars + SV_MOM_SEQ; r.done_seq = c->sync_vars + SV_DONE_SEQ;
-        r.off_obs = c->arena_off[B_OBS]; r.off_act = c->arena_off[B_ACTIONS]; r.off_val = c->arena_off[B_VALUES];
-        r.off_nlp = c->arena_off[B_NEGLOGP]; r.off_ret = c->arena_off[B_RETURNS];
-        r.row_off = (size_t)D.rank * c->n_batch_local;
+        RolloutArgs r = make_rollout_args(c);
         static long long* s_prof = nullptr;
         if (getenv("PPO_ROLLOUT_PROF") && !s_prof) {
             cudaMalloc(&s_prof, sizeof(long long) * 32);
