@@ -251,6 +251,27 @@ class PPOCore:
         _check(self.lib, self.lib.ppo_runner_rollout_replay(self._h, _addr(raw), _addr(rew), _addr(dn),
                                                             _addr(actions_out) if actions_out is not None else None))
 
+    def runner_rollout_host(self, step_fn):
+        """ppo_runner_rollout_host with a Python env: step_fn(t, actions[n_envs, A]) -> (raw_obs, raw_rew, done) or None to abort."""
+        n = self.n_envs
+        keep = {}
+        fpp = C.POINTER(C.POINTER(C.c_float))
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float), fpp, fpp, fpp)
+        def cb(_user, t, actions, po, pr, pd):
+            act = np.ctypeslib.as_array(actions, (n, self.A))
+            out = step_fn(t, act)
+            if out is None:
+                return 1
+            keep["o"], keep["r"], keep["d"] = (_f32(x).ravel() for x in out)  # alive until the next call
+            po[0] = keep["o"].ctypes.data_as(C.POINTER(C.c_float))
+            pr[0] = keep["r"].ctypes.data_as(C.POINTER(C.c_float))
+            pd[0] = keep["d"].ctypes.data_as(C.POINTER(C.c_float))
+            return 0
+
+        actions = np.zeros((n, self.A), np.float32)
+        _check(self.lib, self.lib.ppo_runner_rollout_host(self._h, C.cast(cb, C.c_void_p), None, _addr(actions)))
+
     def synth_env_reset(self):
         _check(self.lib, self.lib.ppo_synth_env_reset(self._h))
 

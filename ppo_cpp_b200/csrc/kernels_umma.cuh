@@ -42,6 +42,10 @@
 namespace ppo {
 namespace umma {
 
+// Operand blocks sit high in fp16's range (an fp16 lo piece below 2^-14 is subnormal: values whose hi piece is below ~0.25
+// would lose relative accuracy): weights max in [2^8, 2^9), activations and the ones block times 2^8, observations times 2^5
+// (|obs| <= clip_obs = 10), back-propagated tensors times S and renormalised by 2^-8 after every product with a weight block.
+constexpr int PW_W = 8, PW_H = 8, PW_X = 5;
 constexpr int TM = 128;   // samples per tile
 constexpr int NTH = 256;  // threads per CTA
 constexpr int HID = 64;   // hidden width handled by this family
@@ -232,9 +236,14 @@ __device__ __forceinline__ void store_chunk(uint8_t* block, uint32_t piece_bytes
     *reinterpret_cast<uint4*>(block + piece_bytes + off) = q1;
 }
 // 32 consecutive columns [32 * half, 32 * half + 32) of row r of an activation block
-__device__ __forceinline__ void store_row32(uint8_t* block, int r, int half, const float* x) {
+__device__ __forceinline__ void store_row32(uint8_t* block, int r, int half, const float* x, float scale = 1.f) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) store_chunk(block, ACT_PIECE, chunk_off(r, 4 * half + j), x + 8 * j);
+    for (int j = 0; j < 4; ++j) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = x[8 * j + i] * scale;
+        store_chunk(block, ACT_PIECE, chunk_off(r, 4 * half + j), y);
+    }
 }
 
 // Observation row of a sample, as the registers of the two threads (h = 0, 1) that stage it: columns [16h, 16h+16)
@@ -254,10 +263,10 @@ struct ObsRegs {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            v[2 * i] = x[i].x;
-            v[2 * i + 1] = x[i].y;
+            v[2 * i] = x[i].x * (float)(1 << PW_X);
+            v[2 * i + 1] = x[i].y * (float)(1 << PW_X);
         }
-        if (O >= 16 * h && O < 16 * h + 16) v[O - 16 * h] = 1.f;
+        if (O >= 16 * h && O < 16 * h + 16) v[O - 16 * h] = (float)(1 << PW_X);
         store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h), v);
         store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h + 1), v + 8);
     }
@@ -362,11 +371,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // constant operand blocks: the V tower's dv rows (row 0 is rewritten per tile, rows 1..7 stay zero) and the ones block
-    // (row 0 of each 8-row group = 1.0 = fp16 0x3C00, rows 1..7 = 0)
+    // (row 0 of each 8-row group = 2^PW_H = 256.0 = fp16 0x5C00, the scale of the activation blocks; rows 1..7 = 0)
     if (tower != 0)
         for (int i = tid; i < NP * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
     if (tid < (int)ROW8_PIECE / 16) {
-        const uint32_t v = ((tid & 63) < 8) ? 0x3C003C00u : 0u;
+        const uint32_t v = ((tid & 63) < 8) ? 0x5C005C00u : 0u;
         reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
     }
     // persistent state: grid barrier generation, mailbox sequence number, Adam's beta powers (every CTA tracks them)
@@ -499,14 +508,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     (void)frexpf(m, &e);
                     return max(-24, min(24, 1 - e));
                 };
-                k_w0 = pow2_to_unit(mx[0]);
-                k_w1 = pow2_to_unit(mx[1]);
-                k_hd = pow2_to_unit(mx[2]);
+                k_w0 = pow2_to_unit(mx[0]) + PW_W;  // block = W * 2^k, max in [2^8, 2^9)
+                k_w1 = pow2_to_unit(mx[1]) + PW_W;
+                k_hd = pow2_to_unit(mx[2]) + PW_W;
                 int e_sig = 0;
                 (void)frexpf(expf(-mx[3]), &e_sig);           // sigma_min = f * 2^e, f in [0.5, 1)
                 const int k_sig = max(-24, min(8, e_sig - 1));  // 2^k_sig <= sigma_min
-                // backward scale S = 2^n_s: pi  S * invB / sigma_min in (1/8, 1/2];  V  S * invB in [4, 8)
-                n_s = tower == 0 ? (-invB_exp + k_sig - 1) : (-invB_exp + 3);
+                // backward scale S = 2^n_s: pi  S * invB / sigma_min in (4, 16];  V  S * invB in [32, 64)
+                n_s = tower == 0 ? (-invB_exp + k_sig + 4) : (-invB_exp + 6);
             }
             const float s_w0 = ldexpf(1.f, k_w0), s_w1 = ldexpf(1.f, k_w1), s_hd = ldexpf(1.f, k_hd);
             // ---- consume
@@ -546,11 +555,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             }
         }
         // epilogue factors of this minibatch (exact powers of two)
-        const float u_w0 = ldexpf(1.f, -k_w0), u_w1 = ldexpf(1.f, -k_w1), u_hd = ldexpf(1.f, -k_hd), s_hd_v = ldexpf(1.f, k_hd);
+        const float u_w0 = ldexpf(1.f, -k_w0 - PW_X), u_w1 = ldexpf(1.f, -k_w1 - PW_H), u_hd = ldexpf(1.f, -k_hd - PW_H);
+        const float s_hd_v = ldexpf(1.f, k_hd - PW_W);           // V tower: dP2 = dv * (wv 2^kh) (1 - g2^2), kh = k_hd - PW_W
         const float S_b = ldexpf(1.f, n_s);                      // backward tensors are stored times S_b
-        const float un_hd = ldexpf(1.f, -n_s);                   // head-level accumulators (dWpi, column sums, dWv)
-        const float un_w1 = ldexpf(1.f, -n_s - k_hd);            // dW1, db1: carry the head matrix's power of two as well
-        const float un_w0 = ldexpf(1.f, -n_s - k_hd - k_w1);     // dW0': ... and W1's
+        constexpr float RENORM = 1.0f / (float)(1 << PW_W);      // after a product with a weight block (W * 2^(kh + PW_W))
+        constexpr float H_SCALE = (float)(1 << PW_H);            // activation blocks hold H * 2^PW_H
+        const float un_hd = ldexpf(1.f, -n_s - PW_H);                               // dWpi, column sums (ones = 2^PW_H), dWv
+        const float un_w1 = ldexpf(1.f, -n_s - (k_hd - PW_W) - PW_H);                // dW1, db1
+        const float un_w0 = ldexpf(1.f, -n_s - (k_hd - PW_W) - (k_w1 - PW_W) - PW_X);  // dW0' (bias column: the ones of X' are 2^PW_X)
         xin.store(sY, gr, gh);
         fence_async_smem();
         tc_fence_before();
@@ -586,7 +598,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) h1r[j] = tanhf(v[j] * u_w0);
-            store_row32(sH1, row, half, h1r);
+            store_row32(sH1, row, half, h1r, H_SCALE);
         }
         fence_async_smem();
         tc_fence_before();
@@ -621,7 +633,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 h2r[j] = tanhf(fmaf(v[j], u_w1, f32[F32_B1 + 32 * half + j]));
                 pv = fmaf(h2r[j], f32[F32_WV + 32 * half + j], pv);
             }
-            store_row32(sH2, row, half, h2r);
+            store_row32(sH2, row, half, h2r, H_SCALE);
             if (tower == 1) f32[F32_PV + half * TM + row] = pv;
         }
         fence_async_smem();
@@ -714,7 +726,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float v[32];
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h2r[j] * h2r[j]);
+            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h2r[j] * h2r[j]) * RENORM;
             store_row32(sD2, row, half, v);  // dP2 (its own block: the dWpi GEMM may still be reading H2)
         } else {
             // ---- V head (GRAPH:10213-10400): value, clipped value loss and dL/dv on the CUDA cores
@@ -787,7 +799,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             float v[32];
             tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h1r[j] * h1r[j]);
+            for (int j = 0; j < 32; ++j) v[j] *= (1.f - h1r[j] * h1r[j]) * RENORM;
             store_row32(sD1, row, half, v);  // dP1
         }
         fence_async_smem();

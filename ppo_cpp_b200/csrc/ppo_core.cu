@@ -1733,9 +1733,11 @@ static int ensure_wide(ppo_core* c, int tiles) {
     const size_t R = (size_t)tiles * wide::TM, H = (size_t)G.H;
     const size_t sizes[] = {(size_t)tiles * G.x_tile, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.act_tower, 2 * G.dy_tower,
                             2 * G.w0_tower, 2 * G.w1_tower, 2 * G.wh_tower, 2 * R * H * sizeof(float), 2 * R * 64 * sizeof(float),
-                            4 * (size_t)tiles * wide::COLPART * sizeof(float), 2 * 4 * (size_t)tiles * H * sizeof(float), 2 * R * H * sizeof(float)};
-    size_t off[14], total = 0;
-    for (int i = 0; i < 14; ++i) {
+                            4 * (size_t)tiles * wide::COLPART * sizeof(float), 2 * 4 * (size_t)tiles * H * sizeof(float), 2 * R * H * sizeof(float),
+                            (size_t)wide::WMAX_BLOCKS * 8 * sizeof(float), 2 * (size_t)wide::SC_STRIDE * sizeof(float),
+                            2 * 4 * (size_t)tiles * H * sizeof(float)};
+    size_t off[17], total = 0;
+    for (int i = 0; i < 17; ++i) {
         off[i] = total;
         total += (sizes[i] + 1023) & ~(size_t)1023;
     }
@@ -1748,6 +1750,8 @@ static int ensure_wide(ppo_core* c, int tiles) {
     w.G1 = reinterpret_cast<float*>(base + off[9]); w.MU = reinterpret_cast<float*>(base + off[10]);
     w.G2 = reinterpret_cast<float*>(base + off[13]);
     w.colloss = reinterpret_cast<float*>(base + off[11]); w.colb1 = reinterpret_cast<float*>(base + off[12]);
+    w.pmax = reinterpret_cast<float*>(base + off[14]); w.sc = reinterpret_cast<float*>(base + off[15]);
+    w.colb0 = reinterpret_cast<float*>(base + off[16]);
     c->wide_cap = tiles;
     return PPO_OK;
 }
@@ -1768,10 +1772,12 @@ static int launch_wide_policy(ppo_core* c, const PolicyArgs& a) {
     const int H = G.H, nb = G.nb;
     const NetDims& d = c->d;
     const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
-    LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w);
+    LAUNCH(c, wide_absmax_kernel, WMAX_BLOCKS, 256, 0, a.params, d, w.pmax);
+    LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w, 1.0f / (float)c->B_global);
     LAUNCH(c, wide_policy_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a.obs, a.n, a.obs_store, d.O, w);
     GemmArgs g{};
     g.P = a.params; g.img_tower = G.act_tower; g.img_tile = G.act_tile; g.img_piece = G.act_piece; g.cap = G.cap; g.H = H;
+    g.sc = w.sc; g.sc_fwd = SC_U_W0;
     g.mode = MODE_FWD;
     g.A = w.X; g.a_tower = 0; g.a_tile = G.x_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
     g.B = w.W0; g.b_tower = G.w0_tower; g.b_piece = G.w0_piece; g.b_kb = 0; g.b_g = 4096; g.b_bytes = 4096;
@@ -1780,11 +1786,11 @@ static int launch_wide_policy(ppo_core* c, const PolicyArgs& a) {
     launch_wgemm(c, g);
     g.A = w.H1; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
-    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2;
+    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2; g.sc_fwd = SC_U_W1;
     launch_wgemm(c, g);
     g.A = w.H2;
     g.B = w.WH; g.b_tower = G.wh_tower; g.b_piece = G.wh_piece; g.b_kb = BLK8; g.b_g = 0; g.b_bytes = BLK8;
-    g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT;
+    g.n_tile = 64; g.n_blks = 1; g.ntasks = 2 * NT; g.sc_fwd = SC_U_HD;
     g.epi = EPI_STORE; g.C = w.MU; g.c_tower = G.mu_tower; g.ldc = 64;
     launch_wgemm(c, g);
     LAUNCH(c, wide_policy_head_kernel, (a.n + 127) / 128, 128, 0, a, w);
@@ -1804,11 +1810,13 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     const NetDims& d = c->d;
     {
         const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
-        LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w);
+        LAUNCH(c, wide_absmax_kernel, WMAX_BLOCKS, 256, 0, a.params, d, w.pmax);
+        LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w, a.invB);
         LAUNCH(c, wide_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a, w);
     }
     GemmArgs g{};
     g.P = a.params; g.img_tower = G.act_tower; g.img_tile = G.act_tile; g.img_piece = G.act_piece; g.cap = G.cap; g.H = H;
+    g.sc = w.sc; g.sc_fwd = SC_U_W0;
     // ---- layer 0: H1 = tanh(X' W0')  (bias through the ones column of X')
     g.mode = MODE_FWD;
     g.A = w.X; g.a_tower = 0; g.a_tile = G.x_tile; g.a_piece = BLK16; g.kblocks = 1; g.ksteps = 2;
@@ -1819,7 +1827,7 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     // ---- layer 1: H2 = tanh(H1 W1 + b1)
     g.A = w.H1; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = BLK8; g.b_g = (size_t)nb * BLK8; g.b_bytes = BLK8;
-    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2; g.gbuf = w.G2;
+    g.bias_off[0] = d.off[T_PI_FC1_B]; g.bias_off[1] = d.off[T_VF_FC1_B]; g.img_out = w.H2; g.gbuf = w.G2; g.sc_fwd = SC_U_W1;
     launch_wgemm(c, g);
     // ---- heads: [mu | v] = H2 WH, losses and head gradients (dY image) in the epilogue
     g.A = w.H2;
@@ -1837,7 +1845,7 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     // ---- dP1 = (dP2 W1^T) (1 - H1^2)
     g.A = w.dP2; g.a_tower = G.act_tower; g.a_tile = G.act_tile; g.a_piece = G.act_piece; g.kblocks = nb; g.ksteps = 4;
     g.B = w.W1; g.b_tower = G.w1_tower; g.b_piece = G.w1_piece; g.b_kb = (size_t)nb * BLK8; g.b_g = BLK16; g.b_bytes = BLK16;
-    g.gbuf = w.G1; g.img_out = w.dP1; g.colsum = nullptr;
+    g.gbuf = w.G1; g.img_out = w.dP1; g.colsum = w.colb0;  // layer-0 bias gradient from the fp32 values
     launch_wgemm(c, g);
     // ---- weight gradients, split over KG groups of samples: dW1 = H1^T dP2, dWhead = H2^T dY, dW0'^T = dP1^T X'
     GemmArgs q{};
@@ -1845,7 +1853,7 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     q.HT = 2 * NT;
     static const int kg_env = getenv("PPO_WIDE_KG") ? atoi(getenv("PPO_WIDE_KG")) : 0;  // split-K groups (measurements)
     q.KG = std::min(kg_env > 0 ? kg_env : 16, std::min(q.HT, c->max_train_grid));
-    q.partial = a.partial; q.PS = a.PS; q.H = H; q.O = d.O; q.A_dim = d.A;
+    q.partial = a.partial; q.PS = a.PS; q.H = H; q.O = d.O; q.A_dim = d.A; q.sc = w.sc;
     q.off_w1[0] = d.off[T_PI_FC1_W]; q.off_w1[1] = d.off[T_VF_FC1_W];
     q.off_w0[0] = d.off[T_PI_FC0_W]; q.off_w0[1] = d.off[T_VF_FC0_W];
     q.off_b0[0] = d.off[T_PI_FC0_B]; q.off_b0[1] = d.off[T_VF_FC0_B];
@@ -1859,7 +1867,7 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
     q.dw[2].task0 = q.dw[1].task0 + q.dw[1].ntasks;
     q.ntasks = q.dw[2].task0 + q.dw[2].ntasks;
     launch_wgemm(c, q);
-    LAUNCH(c, wide_fold_kernel, (2 * H + 2 * d.A + 1 + L_PAD + 7) / 8, 256, 0, a, w, q.KG);
+    LAUNCH(c, wide_fold_kernel, (4 * H + 2 * d.A + 1 + L_PAD + 7) / 8, 256, 0, a, w, q.KG);
     *slabs_out = q.KG;
     return PPO_OK;
 }
@@ -2352,7 +2360,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     if (!c || !which) return nullptr;
     const std::string w(which);
     if (w == "train") {
-        if (c->wide) return "wgemm_kernel (tcgen05.mma kind::f16, bf16x3 split operand images, layer-wise GEMMs with bulk-copy pipeline)";
+        if (c->wide) return "wgemm_kernel (tcgen05.mma kind::f16, fp16x2 split operand images, layer-wise GEMMs with bulk-copy pipeline)";
         if (c->small) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums)";
         if (c->umma && c->persistent_epoch && fast_path(c))
             return "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";

@@ -864,6 +864,56 @@ def test_runner_rollout_replay_equals_stepwise_protocol(core_mod, ckpt_weights, 
     b.close()
 
 
+@pytest.mark.parametrize("n_envs", [1, 40])
+def test_host_env_one_kernel_rollout_equals_stepwise_and_aborts_cleanly(core_mod, monkeypatch, ckpt_weights, n_envs):
+    """ppo_runner_rollout_host with a live host env (Python callback): up to 512 envs the whole rollout is ONE persistent
+    kernel that trades actions / observations with the host through mapped pinned memory.  It must equal the per-step
+    protocol bit for bit over consecutive rollouts, and an env that aborts must release the kernel and leave the core usable."""
+    _, flat = ckpt_weights
+    n_steps, seed = 24, 8
+    lib = ol.load()
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("PPO_DISABLE_HOST_PERSISTENT", "1")
+        else:
+            monkeypatch.delenv("PPO_DISABLE_HOST_PERSISTENT", raising=False)
+        env = lib.oracle_synth_env_create(n_envs, 18, seed ^ 0x1234, 0)
+        obs, rew, done = np.zeros((n_envs, 18), np.float32), np.zeros(n_envs, np.float32), np.zeros(n_envs, np.float32)
+        c = make_core(core_mod, flat, n_envs=n_envs, n_steps=n_steps, nminibatches=4, noptepochs=1, seed=seed)
+        lib.oracle_synth_env_reset(env, obs)
+        c.runner_reset(obs)
+
+        def step(t, act):
+            lib.oracle_synth_env_step(env, np.ascontiguousarray(act), obs, rew, done)
+            return obs, rew, done
+
+        out = []
+        for _ in range(2):
+            c.runner_rollout_host(step)
+            out.append({n: c.rollout_get(n) for n in ("obs", "actions", "values", "neglogpacs", "returns", "dones", "true_rewards", "unnormalized_rewards")})
+        st = c.vecnorm_stats()
+        lib.oracle_synth_env_destroy(env)
+        return c, out, st
+
+    c1, one_kernel, st1 = run(False)
+    c2, stepwise, st2 = run(True)
+    for a, b in zip(one_kernel, stepwise):
+        for n in a:
+            assert np.array_equal(a[n], b[n]), n
+    assert st1["obs_count"] == st2["obs_count"] and np.array_equal(st1["obs_mean"], st2["obs_mean"])
+    # an env that gives up at step 5: the call fails, nothing hangs, the next rollout works
+    monkeypatch.delenv("PPO_DISABLE_HOST_PERSISTENT", raising=False)
+    o, r, d = np.zeros((n_envs, 18), np.float32), np.zeros(n_envs, np.float32), np.zeros(n_envs, np.float32)
+    with pytest.raises(core_mod.PPOError):
+        c1.runner_rollout_host(lambda t, act: None if t == 5 else (o, r, d))
+    c1.runner_reset(o)
+    c1.runner_rollout_host(lambda t, act: (o, r, d))
+    assert np.all(np.isfinite(c1.rollout_get("returns")))
+    c1.close()
+    c2.close()
+
+
 def test_rollout_mock_env_c1(core_mod, init_weights, kat):
     """Config C1: EnvMock (constant obs/reward 1, done every 300th step) driven through the host protocol.
     Rewards, dones and the done-lag of Runner::run are exact; the normalised observation is cancellation noise
