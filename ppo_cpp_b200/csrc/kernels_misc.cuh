@@ -1154,18 +1154,31 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_big_kernel(const ReduceA
         a.loss_row[3] = 0.5f * (L[L_KL] * a.invB);
         a.loss_row[4] = L[L_CLIP] * a.invB;
     }
-    if (rg == 0) {  // pass C
+    if (rg == 0) {  // pass C, four chunks per trip: the sixteen loads of a trip are in flight together
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
-        for (int chunk = blk; chunk < nchunks; chunk += nblk) {
-            const int c = chunk * 64 + lane_c;
-            if (c < a.P) {
-                const float g = __fmul_rn(__ldcg(r.grad + c), s_scale);
-                float m = a.m[c], v = a.v[c];
-                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
-                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
-                a.m[c] = m;
-                a.v[c] = v;
-                a.params[c] = __fsub_rn(a.params[c], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+        for (int chunk0 = blk; chunk0 < nchunks; chunk0 += 4 * nblk) {
+            float gg[4], mm[4], vv[4], pp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (chunk0 + j * nblk) * 64 + lane_c;
+                const bool ok = c < a.P;
+                gg[j] = ok ? __ldcg(r.grad + c) : 0.f;
+                mm[j] = ok ? __ldcg(a.m + c) : 0.f;
+                vv[j] = ok ? __ldcg(a.v + c) : 0.f;
+                pp[j] = ok ? __ldcg(a.params + c) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (chunk0 + j * nblk) * 64 + lane_c;
+                if (c < a.P) {
+                    const float g = __fmul_rn(gg[j], s_scale);
+                    float m = mm[j], v = vv[j];
+                    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
+                    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
+                    a.m[c] = m;
+                    a.v[c] = v;
+                    a.params[c] = __fsub_rn(pp[j], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
+                }
             }
         }
     }

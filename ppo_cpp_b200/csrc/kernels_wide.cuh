@@ -604,7 +604,7 @@ struct WideBufs {
 
 // |max| of every weight matrix that becomes an operand image (block floating point), max(-logstd) for the backward scale.
 // Categories: tower * 3 + {W0' (weights and bias row), W1, head}; 6 = -logstd.  Per-block partials, no atomics.
-constexpr int WMAX_BLOCKS = 64;
+constexpr int WMAX_BLOCKS = 296;
 __global__ void __launch_bounds__(256) wide_absmax_kernel(const float* __restrict__ P, const NetDims d, float* __restrict__ pmax) {
     __shared__ float red[8][8];
     float mx[8];

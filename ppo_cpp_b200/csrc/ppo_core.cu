@@ -108,6 +108,7 @@ struct ppo_core {
     bool wide = false;    // W family (tcgen05, layer-wise GEMMs over operand images): H1 == H2 in {128, 256, 512, 1024}
     wide::WideBufs wb{};
     void* wide_mem = nullptr;
+    bool wide_images_valid = false;  // the weight images (and their scale table) were built from the current parameters
     int wide_cap = 0;     // capacity of the W-family buffers in tiles of 128 samples
     int max_train_grid = 0;
     int prof_train_grid = 0;
@@ -766,6 +767,7 @@ extern "C" int ppo_core_set_tensor(ppo_core* c, const char* name, const float* i
     CU(cudaSetDevice(c->desc.device));
     CU(cudaMemcpyAsync(p, in, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->wide_images_valid = false;
     return PPO_OK;
 }
 
@@ -1601,6 +1603,7 @@ extern "C" int ppo_rollout_synthetic(ppo_core* c) {
         const uint64_t k0 = c->ctr.kernel_launches;
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        c->wide_images_valid = false;  // the captured rollout must rebuild the W family's weight images itself (it is replayed after updates)
         const int st = rollout_synthetic_enqueue(c);
         const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
         g.kernels = c->ctr.kernel_launches - k0;
@@ -1722,6 +1725,7 @@ static int ensure_wide(ppo_core* c, int tiles) {
         CU(cudaFree(c->wide_mem));
         c->wide_mem = nullptr;
         c->wide_cap = 0;
+        c->wide_images_valid = false;
         // captured graphs hold the old pointers: drop them, they are re-captured on their next use
         for (auto& g : c->graphs)
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
@@ -1772,8 +1776,11 @@ static int launch_wide_policy(ppo_core* c, const PolicyArgs& a) {
     const int H = G.H, nb = G.nb;
     const NetDims& d = c->d;
     const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
-    LAUNCH(c, wide_absmax_kernel, WMAX_BLOCKS, 256, 0, a.params, d, w.pmax);
-    LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w, 1.0f / (float)c->B_global);
+    if (!c->wide_images_valid) {  // the weight images are those of the current parameters for the whole rollout
+        LAUNCH(c, wide_absmax_kernel, WMAX_BLOCKS, 256, 0, a.params, d, w.pmax);
+        LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w, 1.0f / (float)c->B_global);
+        c->wide_images_valid = true;
+    }
     LAUNCH(c, wide_policy_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a.obs, a.n, a.obs_store, d.O, w);
     GemmArgs g{};
     g.P = a.params; g.img_tower = G.act_tower; g.img_tile = G.act_tile; g.img_piece = G.act_piece; g.cap = G.cap; g.H = H;
@@ -1812,6 +1819,7 @@ static int launch_wide_train(ppo_core* c, const TrainArgs& a, int* slabs_out) {
         const int chunks = 2 * nb * 32 * 8 + 2 * nb * nb * 64 * 8 + 2 * nb * 64 * 8;
         LAUNCH(c, wide_absmax_kernel, WMAX_BLOCKS, 256, 0, a.params, d, w.pmax);
         LAUNCH(c, wide_prep_weights_kernel, (chunks + 255) / 256, 256, 0, a.params, d, w, a.invB);
+        c->wide_images_valid = false;  // an Adam step follows
         LAUNCH(c, wide_gather_kernel, (G.Bpad * (d.O / 8 + 1) + 255) / 256, 256, 0, a, w);
     }
     GemmArgs g{};
