@@ -2135,6 +2135,18 @@ static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
     return PPO_OK;
 }
 
+// mean losses of the update to the host; on a multi-GPU run the peer-mailbox error flag travels with them: a wait that
+// timed out (a peer died or never arrived) fails the call instead of returning numbers computed from stale slots
+static int read_losses_checked(ppo_core* c, float* mean_losses) {
+    TRY(d2h(c, mean_losses, c->loss_mean, 5));
+    unsigned err = 0;
+    const bool check = c->desc.world_size > 1 && c->mbox_ready && c->sync_vars;
+    if (check) CU(cudaMemcpyAsync(&err, c->sync_vars + SV_ERR, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (check && err) return fail(PPO_ERR_COMM, "a peer-mailbox wait timed out during the update (rank %d): a peer is gone or never arrived", c->desc.rank);
+    return PPO_OK;
+}
+
 extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* mean_losses) {
     if (!c) return fail(PPO_ERR_INVALID, "core is NULL");
     CU(cudaSetDevice(c->desc.device));
@@ -2177,10 +2189,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         }
         if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
         CU(cudaGetLastError());
-        if (mean_losses) {
-            TRY(d2h(c, mean_losses, c->loss_mean, 5));
-            CU(cudaStreamSynchronize(c->stream));
-        }
+        if (mean_losses) TRY(read_losses_checked(c, mean_losses));
         return PPO_OK;
     }
     TRY(drop_shuffle_prefetch(c, true));
@@ -2256,10 +2265,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
     }
     if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
     CU(cudaGetLastError());
-    if (mean_losses) {
-        TRY(d2h(c, mean_losses, c->loss_mean, 5));
-        CU(cudaStreamSynchronize(c->stream));
-    }
+    if (mean_losses) TRY(read_losses_checked(c, mean_losses));
     return PPO_OK;
 }
 
