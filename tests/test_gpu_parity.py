@@ -690,8 +690,9 @@ def test_rollout_persistent_equals_stepwise(core_mod, monkeypatch, h1, h2, n_env
 @pytest.mark.parametrize("n_envs,n_steps,nmb", [(256, 32, 2), (4096, 16, 8), (1000, 8, 2)])
 def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps, nmb):
     """[64,64]: the persistent epoch kernel (all minibatches of an epoch in one cooperative launch: tcgen05 tiles, column
-    reduce, global norm, Adam, three grid barriers per minibatch) against the launch-per-minibatch path over two
-    updates.  Same arithmetic; only the partition of the sum-of-squares partials differs."""
+    reduce over distributed shared memory + LL hand-overs, global norm, Adam inside thread-block clusters) against the
+    launch-per-minibatch path over two updates.  Same arithmetic; the order of the cross-CTA gradient sums and of the
+    sum-of-squares partials differs, so single parameters may differ by an ulp of their own magnitude."""
     rng = np.random.default_rng(8)
     p = rand_params(rng, 64, 64)
     res = []
@@ -710,7 +711,8 @@ def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps
             monkeypatch.delenv(env)
     a, b = res
     moved = np.abs(a["params"] - p).max()
-    assert np.abs(a["params"] - b["params"]).max() < 1e-5 * moved + 1e-9
+    ulp = np.finfo(np.float32).eps * np.abs(p).max()
+    assert np.abs(a["params"] - b["params"]).max() < 1e-5 * moved + 2 * ulp
     assert rel_err(a["losses"], b["losses"]) < 1e-5
     assert rel_err(a["m"], b["m"]) < 1e-5 and rel_err(a["v"], b["v"]) < 1e-5
     assert np.array_equal(a["b1"], b["b1"]) and np.array_equal(a["b2"], b["b2"])
