@@ -882,14 +882,20 @@ struct ReduceAdamArgs {
     unsigned* bar_gen;  // launch can be replayed from a CUDA graph)
     PeerMailbox mbox;   // world == 1: unused
     unsigned* mbox_seq; // device-resident sequence number of the gradient exchange
+    // Sum-of-squares partials as LL words instead of a grid barrier (or NULL): every block stores its partial (a double and the
+    // sequence number of the step in one 16-byte word) into the row of EVERY block, [parity][destination][source], and polls its
+    // own row — one polling thread per word, no barrier between the column sums and Adam.  sq_seq: device-resident sequence number.
+    uint4* sq_ll;
+    unsigned* sq_seq;
 };
 
 // Body shared by the stand-alone cooperative kernel and the persistent epoch kernel (kernels_umma.cuh): `blk` of `nblk`
 // blocks of 256 threads.  b1p / b2p are the beta powers BEFORE this step.  Contains one grid barrier.
 __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int blk, int nblk, GridBarrier& bar, unsigned seq,
-                                                   float b1p, float b2p, float* loss_row, long long* prof = nullptr) {
-    __shared__ float part[4][64];
+                                                   float b1p, float b2p, float* loss_row, long long* prof = nullptr, unsigned sqseq = 0u) {
+    __shared__ float part[RA_MAXJ][4][64];
     __shared__ double red[8];
+    __shared__ double s_parts[256];
     __shared__ float s_scale;
     const AdamArgs& a = r.adam;
     const int lane_c = threadIdx.x & 63, rg = threadIdx.x >> 6;
@@ -925,17 +931,18 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
             for (int u = 0; u < 16; ++u) acc[j] += v[j][u];
     }
     RA_PROF();
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RA_MAXJ; ++j) part[j][rg][lane_c] = acc[j];
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < RA_MAXJ; ++j) {
         gsum[j] = 0.f;
         const int chunk = blk + j * nblk;
         if (chunk >= nchunks) break;  // block-uniform
         const int c = chunk * 64 + lane_c;
-        __syncthreads();
-        part[rg][lane_c] = acc[j];
-        __syncthreads();
         if (rg == 0) {
-            const double t = ((double)part[0][lane_c] + (double)part[1][lane_c]) + ((double)part[2][lane_c] + (double)part[3][lane_c]);
+            const double t = ((double)part[j][0][lane_c] + (double)part[j][1][lane_c]) + ((double)part[j][2][lane_c] + (double)part[j][3][lane_c]);
             gsum[j] = (float)t;
             if (world > 1 && c < r.PS) {  // LL store of (value, seq) into every rank's slot of this rank
                 for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gsum[j]), seq);
@@ -987,11 +994,40 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
         ap[j] = mine ? __ldcg(a.params + c) : 0.f;
     }
     RA_PROF();
-    bar.sync();
+    const bool ll = r.sq_ll != nullptr;  // (nblk <= 256)
+    if (ll) {
+        const unsigned long long qb = (unsigned long long)__double_as_longlong(red[0] + red[1]);
+        uint4* const base = r.sq_ll + (size_t)(sqseq & 1u) * nblk * nblk;
+        for (int dst = threadIdx.x; dst < nblk; dst += blockDim.x) {
+            uint4* p = base + (size_t)dst * nblk + blk;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)qb), "r"(sqseq), "r"((unsigned)(qb >> 32)), "r"(sqseq) : "memory");
+        }
+        if ((int)threadIdx.x < nblk) {
+            const uint4* p = base + (size_t)blk * nblk + threadIdx.x;
+            uint4 v;
+            unsigned long long t0 = 0;
+            unsigned spins = 0;
+            while (true) {
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+                if (v.y == sqseq && v.w == sqseq) break;
+                if (((++spins) & 0x3ffu) == 0u) {  // bounded like the mailbox waits (a block of this grid never arrived)
+                    if (t0 == 0) t0 = globaltimer_ns();
+                    if (globaltimer_ns() - t0 > 4000000000ull) {
+                        *r.mbox.err = 1u;
+                        break;
+                    }
+                }
+            }
+            s_parts[threadIdx.x] = __longlong_as_double((long long)(((unsigned long long)v.z << 32) | (unsigned long long)v.x));
+        }
+        __syncthreads();
+    } else {
+        bar.sync();
+    }
     RA_PROF();
     if (threadIdx.x < 32) {
         double ss = 0.0;
-        for (int b = threadIdx.x; b < nblk; b += 32) ss += __ldcg(r.sq_partial + b);
+        for (int b = threadIdx.x; b < nblk; b += 32) ss += ll ? s_parts[b] : __ldcg(r.sq_partial + b);
         // fixed-order combine: lane partials summed by a butterfly (same order in every block and on every rank)
         ss = warp_sum(ss);
         if (threadIdx.x == 0) {
@@ -1007,7 +1043,9 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
     RA_PROF();
     const int loss_chunk = (a.P >> 6);  // the chunk that holds column P (the loss sums start there)
     if (blk == loss_chunk % nblk && threadIdx.x == 0) {
-        const float* Ls = r.grad + a.P;  // columns P.. may straddle into another block's chunk: read through L2
+        // columns P.. may straddle into another block's chunk: read through L2 (the LL variant is only used when they do not:
+        // this block wrote them itself, before the __syncthreads above)
+        const float* Ls = r.grad + a.P;
         float L[5];
         for (int k = 0; k < 5; ++k) L[k] = __ldcg(Ls + k);
         loss_row[0] = L[L_PG] * a.invB;
@@ -1041,13 +1079,16 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
 __global__ void __launch_bounds__(256) grad_reduce_adam_coop_kernel(const ReduceAdamArgs r) {
     GridBarrier bar{r.bar_ctr, gridDim.x, *r.bar_gen};
     const unsigned seq = r.mbox.world > 1 ? (*r.mbox_seq + 1u) : 0u;
+    const unsigned sqseq = r.sq_ll ? (*r.sq_seq + 1u) : 0u;
     const float b1p = r.adam.bpow_in[0], b2p = r.adam.bpow_in[1];
-    reduce_adam_device(r, (int)blockIdx.x, (int)gridDim.x, bar, seq, b1p, b2p, r.adam.loss_row);
+    reduce_adam_device(r, (int)blockIdx.x, (int)gridDim.x, bar, seq, b1p, b2p, r.adam.loss_row, nullptr, sqseq);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         r.adam.bpow_out[0] = __fmul_rn(b1p, r.adam.beta1);
         r.adam.bpow_out[1] = __fmul_rn(b2p, r.adam.beta2);
         *r.bar_gen = bar.gen;
         if (r.mbox.world > 1) *r.mbox_seq = seq;
+        // (every block has read sq_seq by now: block 0 got here only after polling a partial of each of them)
+        if (r.sq_ll) *r.sq_seq = sqseq;
     }
 }
 

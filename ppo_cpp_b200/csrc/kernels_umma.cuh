@@ -78,6 +78,8 @@ constexpr uint32_t ACC_WORK = 0, ACC_WORK_C = 64;  // Z1, Z2, MU (first 32 colum
 constexpr uint32_t ACC_DWP = 128, ACC_DWP_C = 160, ACC_CS = 192, ACC_CS_C = 200, ACC_DW1 = 208, ACC_DW1_C = 272, ACC_DB1 = 336,
                    ACC_DB1_C = 344, ACC_DW0 = 352, ACC_DW0_C = 384, TMEM_COLS = 512;
 
+// 2^k for -126 <= k <= 127 (the exponents of the block floating point scheme stay within +-100)
+__device__ __forceinline__ float pow2f(int k) { return __int_as_float((k + 127) << 23); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // byte offset of the 16-byte chunk j (8 bf16 columns) of row r inside a SWIZZLE_128B [R x 64] bf16 block
@@ -285,9 +287,12 @@ struct EpochArgs {
     ReduceAdamArgs ra;
 };
 
+// phase stamps of CTA 0 of each tower: the stand-alone kernel writes a.prof[tower][0..32), the persistent kernel stamps
+// minibatch 2 only (steady state) into a.prof[64 + 48 * tower ..)
 #define UMMA_PROF()                                                                                              \
     do {                                                                                                         \
-        if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 32) a.prof[tower * 32 + prof_i++] = clock64();      \
+        if (a.prof && blockIdx.x == 0 && tid == 0 && prof_on && prof_i < (PERSIST ? 48 : 32))                     \
+            a.prof[(PERSIST ? 64 + tower * 48 : tower * 32) + prof_i++] = clock64();                              \
     } while (0)
 
 // MODE 0: one minibatch per launch (slabs are reduced by another kernel).  MODE 1: persistent epoch, three grid barriers per
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     const int row = q * 32 + lane;                           // sample row of this thread in the epilogues
     const int tower = blockIdx.y;                            // 0 = pi, 1 = V
     int prof_i = 0;
+    bool prof_on = !PERSIST;
     UMMA_PROF();  // kernel entry
 
     uint8_t* sH1 = smem + OFF_H1;
@@ -382,6 +388,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     GridBarrier bar{PERSIST ? ep.ra.bar_ctr : nullptr, 2u * gridDim.x, PERSIST ? *ep.ra.bar_gen : 0u};
     unsigned mseq = (PERSIST && ep.ra.mbox.world > 1) ? *ep.ra.mbox_seq : 0u;
     float b1p = PERSIST ? ep.ra.adam.bpow_in[0] : 0.f, b2p = PERSIST ? ep.ra.adam.bpow_in[1] : 0.f;
+    unsigned sqseq = (PERSIST && ep.ra.sq_ll) ? *ep.ra.sq_seq : 0u;  // sequence number of the sum-of-squares LL exchange
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -426,6 +433,10 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     const int n_mb = PERSIST ? ep.M : 1;
 #define LDW(p) (PERSIST ? __ldcg(p) : __ldg(p))  // the persistent kernel re-reads parameters that it updates itself
     for (int mb = 0; mb < n_mb; ++mb) {
+        if (PERSIST) {
+            prof_on = mb == 2;
+            UMMA_PROF();  // start of the stamped minibatch
+        }
         {
             // weights -> two fp16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
             const float* P = a.params;
@@ -503,21 +514,19 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     mx[k] = m;
                 }
                 auto pow2_to_unit = [](float m) {  // k with m * 2^k in [1, 2); 0 for a zero / non-finite matrix
-                    int e = 0;
-                    if (!(m > 0.f) || !isfinite(m)) return 0;
-                    (void)frexpf(m, &e);
-                    return max(-24, min(24, 1 - e));
+                    const int ef = (__float_as_int(m) >> 23) & 0xff;  // m = f * 2^(ef - 126), f in [0.5, 1) (subnormals clamp below)
+                    if (!(m > 0.f) || ef == 0xff) return 0;
+                    return max(-24, min(24, 127 - ef));
                 };
                 k_w0 = pow2_to_unit(mx[0]) + PW_W;  // block = W * 2^k, max in [2^8, 2^9)
                 k_w1 = pow2_to_unit(mx[1]) + PW_W;
                 k_hd = pow2_to_unit(mx[2]) + PW_W;
-                int e_sig = 0;
-                (void)frexpf(expf(-mx[3]), &e_sig);           // sigma_min = f * 2^e, f in [0.5, 1)
-                const int k_sig = max(-24, min(8, e_sig - 1));  // 2^k_sig <= sigma_min
+                const int e_sig = ((__float_as_int(expf(-mx[3])) >> 23) & 0xff) - 126;  // sigma_min = f * 2^e, f in [0.5, 1)
+                const int k_sig = max(-24, min(8, e_sig - 1));                           // 2^k_sig <= sigma_min
                 // backward scale S = 2^n_s: pi  S * invB / sigma_min in (4, 16];  V  S * invB in [32, 64)
                 n_s = tower == 0 ? (-invB_exp + k_sig + 4) : (-invB_exp + 6);
             }
-            const float s_w0 = ldexpf(1.f, k_w0), s_w1 = ldexpf(1.f, k_w1), s_hd = ldexpf(1.f, k_hd);
+            const float s_w0 = pow2f(k_w0), s_w1 = pow2f(k_w1), s_hd = pow2f(k_hd);
             // ---- consume
     #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -555,14 +564,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             }
         }
         // epilogue factors of this minibatch (exact powers of two)
-        const float u_w0 = ldexpf(1.f, -k_w0 - PW_X), u_w1 = ldexpf(1.f, -k_w1 - PW_H), u_hd = ldexpf(1.f, -k_hd - PW_H);
-        const float s_hd_v = ldexpf(1.f, k_hd - PW_W);           // V tower: dP2 = dv * (wv 2^kh) (1 - g2^2), kh = k_hd - PW_W
-        const float S_b = ldexpf(1.f, n_s);                      // backward tensors are stored times S_b
+        const float u_w0 = pow2f(-k_w0 - PW_X), u_w1 = pow2f(-k_w1 - PW_H), u_hd = pow2f(-k_hd - PW_H);
+        const float s_hd_v = pow2f(k_hd - PW_W);                 // V tower: dP2 = dv * (wv 2^kh) (1 - g2^2), kh = k_hd - PW_W
+        const float S_b = pow2f(n_s);                            // backward tensors are stored times S_b
         constexpr float RENORM = 1.0f / (float)(1 << PW_W);      // after a product with a weight block (W * 2^(kh + PW_W))
         constexpr float H_SCALE = (float)(1 << PW_H);            // activation blocks hold H * 2^PW_H
-        const float un_hd = ldexpf(1.f, -n_s - PW_H);                               // dWpi, column sums (ones = 2^PW_H), dWv
-        const float un_w1 = ldexpf(1.f, -n_s - (k_hd - PW_W) - PW_H);                // dW1, db1
-        const float un_w0 = ldexpf(1.f, -n_s - (k_hd - PW_W) - (k_w1 - PW_W) - PW_X);  // dW0' (bias column: the ones of X' are 2^PW_X)
+        const float un_hd = pow2f(-n_s - PW_H);                               // dWpi, column sums (ones = 2^PW_H), dWv
+        const float un_w1 = pow2f(-n_s - (k_hd - PW_W) - PW_H);                // dW1, db1
+        const float un_w0 = pow2f(-n_s - (k_hd - PW_W) - (k_w1 - PW_W) - PW_X);  // dW0' (bias column: the ones of X' are 2^PW_X)
         xin.store(sY, gr, gh);
         fence_async_smem();
         tc_fence_before();
@@ -935,7 +944,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             ++mseq;
             reduce_adam_device(ep.ra, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), bar, mseq, b1p, b2p,
                                ep.loss_rows + (size_t)mb * 5,
-                               (a.prof && blockIdx.x == 0 && mb == 1) ? a.prof + 64 + tower * 8 : nullptr);
+                               (a.prof && blockIdx.x == 0 && mb == 2) ? a.prof + 160 + tower * 8 : nullptr, ++sqseq);
             b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
             b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
             UMMA_PROF();  // reduce + barrier 2 + Adam done
@@ -950,6 +959,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         ep.ra.adam.bpow_out[1] = b2p;
         *ep.ra.bar_gen = bar.gen;
         if (ep.ra.mbox.world > 1) *ep.ra.mbox_seq = mseq;
+        if (ep.ra.sq_ll) *ep.ra.sq_seq = sqseq;
     }
     tc_fence_before();
     __syncthreads();

@@ -154,6 +154,8 @@ struct ppo_core {
     EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
     bool persistent_epoch = false;    // U family: all minibatches of an epoch in one cooperative launch
     int epoch_grid = 0;
+    uint4* sq_ll = nullptr;           // sum-of-squares partials of the gradient step as LL words, [parity][block][block] (or NULL: grid barrier)
+    int sq_ll_blocks = 0;
     bool persistent_rollout = false;  // R family: the whole rollout as one cooperative kernel
     int roll_grid = 0, roll_tpc = 0;
     size_t roll_smem = 0;
@@ -204,7 +206,7 @@ struct ppo_core {
     ppo_counters ctr{};
 };
 // sync_vars layout: scalars first, then three barrier flag arrays of SV_MAXBLK words each
-enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SHUF_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
+enum { SV_COOP_GEN, SV_ROLL_GEN, SV_EPOCH_GEN, SV_GRAD_SEQ, SV_MOM_SEQ, SV_ERR, SV_DONE_SEQ, SV_SHUF_SEQ, SV_SQ_SEQ, SV_SCALARS = 16, SV_MAXBLK = 2048,
        SV_COOP_FLAGS = SV_SCALARS, SV_ROLL_FLAGS = SV_COOP_FLAGS + SV_MAXBLK, SV_EPOCH_FLAGS = SV_ROLL_FLAGS + SV_MAXBLK,
        SV_COUNT = SV_EPOCH_FLAGS + SV_MAXBLK };
 
@@ -398,6 +400,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     if (c->hx_mem) cudaFreeHost(c->hx_mem);
     if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
+    if (c->sq_ll) cudaFree(c->sq_ll);
+    if (c->umma_prof) cudaFree(c->umma_prof);
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->rollout_graph.exec) cudaGraphExecDestroy(c->rollout_graph.exec);
@@ -619,8 +623,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             if (st != PPO_OK) break;
         }
         if (c->umma && getenv("PPO_UMMA_PROF")) {
-            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 96) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
-            cudaMemset(c->umma_prof, 0, sizeof(long long) * 96);
+            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 176) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
+            cudaMemset(c->umma_prof, 0, sizeof(long long) * 176);
         }
         {
             int per_sm = 0, coop_ok = 0;
@@ -661,6 +665,16 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                         c->sq_partial = nullptr;
                         if (cudaMalloc(&c->sq_partial, sizeof(double) * 2 * grid) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_partial) failed"); break; }
                     }
+                }
+            }
+            // sum-of-squares partials of the cooperative gradient step as LL words (replaces its grid barrier) when one row fits the
+            // polling threads and the loss columns P .. P+4 sit in one 64-column chunk
+            {
+                const int nb = std::max(c->coop_grid, c->persistent_epoch ? 2 * c->epoch_grid : 0);
+                if (c->coop && nb <= 256 && (c->d.P & 63) + 5 <= 64 && getenv("PPO_DISABLE_SQ_LL") == nullptr) {
+                    if (cudaMalloc(&c->sq_ll, sizeof(uint4) * 2 * (size_t)nb * nb) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(sq_ll) failed"); break; }
+                    cudaMemset(c->sq_ll, 0, sizeof(uint4) * 2 * (size_t)nb * nb);  // sequence numbers start at 1
+                    c->sq_ll_blocks = nb;
                 }
             }
             c->use_graph = getenv("PPO_DISABLE_GRAPH") == nullptr;  // multi-GPU: only on the fast path (no NCCL inside a graph)
@@ -1934,6 +1948,7 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
         r.partial = c->partial; r.G = train_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
         r.bar_ctr = c->sync_vars + SV_COOP_FLAGS; r.bar_gen = c->sync_vars + SV_COOP_GEN;
         r.mbox = make_mailbox(c, true); r.mbox_seq = c->sync_vars + SV_GRAD_SEQ;
+        r.sq_ll = (c->sq_ll && !c->coop_big) ? c->sq_ll : nullptr; r.sq_seq = c->sync_vars + SV_SQ_SEQ;
         AdamArgs& ad = r.adam;
         ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
         ad.nblk = c->coop_grid; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
@@ -2120,6 +2135,7 @@ static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
     r.partial = c->partial; r.G = c->epoch_grid; r.PS = c->PS; r.grad = c->grad; r.sq_partial = c->sq_partial;
     r.bar_ctr = c->sync_vars + SV_EPOCH_FLAGS; r.bar_gen = c->sync_vars + SV_EPOCH_GEN;
     r.mbox = make_mailbox(c, true); r.mbox_seq = c->sync_vars + SV_GRAD_SEQ;
+    r.sq_ll = c->sq_ll; r.sq_seq = c->sync_vars + SV_SQ_SEQ;
     AdamArgs& ad = r.adam;
     ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
     ad.nblk = 2 * c->epoch_grid; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
@@ -2246,22 +2262,6 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         c->ctr.kernel_launches += eg.kernels;
         c->ctr.h2d_bytes += sizeof(int) * (size_t)nb;
         c->bpow_slot ^= eg.flip;
-    }
-    if (c->umma_prof && c->persistent_epoch) {
-        static int printed = 0;
-        if (printed++ == 3) {
-            long long h[96];
-            cudaStreamSynchronize(c->stream);
-            cudaMemcpy(h, c->umma_prof, sizeof(h), cudaMemcpyDeviceToHost);
-            for (int t = 0; t < 2; ++t) {
-                fprintf(stderr, "umma epoch phases tower %d:", t);
-                for (int i = 1; i < 32 && h[t * 32 + i]; ++i) fprintf(stderr, " %lld", h[t * 32 + i] - h[t * 32 + i - 1]);
-                fprintf(stderr, "\n   reduce+adam (loads | chunks+sq+prefetch | barrier | norm | adam):");
-                for (int i = 1; i < 8 && h[64 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[64 + t * 8 + i] - h[64 + t * 8 + i - 1]);
-                fprintf(stderr, "\n");
-            }
-        }
-        cudaMemsetAsync(c->umma_prof, 0, sizeof(long long) * 96, c->stream);
     }
     if (E * M > 0) LAUNCH(c, loss_mean_kernel, 1, 32, 0, c->loss_rows, E * M, c->loss_mean);
     CU(cudaGetLastError());
@@ -2471,13 +2471,15 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
     cudaEventDestroy(e1);
     if (st != PPO_OK) return st;
     if (c->umma_prof && w == "train_fwdbwd") {
-        long long h[96];
+        long long h[176];
         cudaMemcpy(h, c->umma_prof, sizeof(h), cudaMemcpyDeviceToHost);
         for (int t = 0; t < 2; ++t) {
-            fprintf(stderr, "umma phases tower %d (cycles since setup):", t);
+            fprintf(stderr, "umma phases, stand-alone kernel, tower %d (cycles):", t);
             for (int i = 1; i < 32 && h[t * 32 + i]; ++i) fprintf(stderr, " %lld", h[t * 32 + i] - h[t * 32 + i - 1]);
-            fprintf(stderr, "\n   reduce phases:");
-            for (int i = 1; i < 8 && h[64 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[64 + t * 8 + i] - h[64 + t * 8 + i - 1]);
+            fprintf(stderr, "\numma phases, epoch kernel minibatch 2, tower %d (cycles):", t);
+            for (int i = 1; i < 48 && h[64 + t * 48 + i]; ++i) fprintf(stderr, " %lld", h[64 + t * 48 + i] - h[64 + t * 48 + i - 1]);
+            fprintf(stderr, "\n   reduce phases (loads | combine + exchange + prefetch | partials / barrier | norm | Adam):");
+            for (int i = 1; i < 8 && h[160 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[160 + t * 8 + i] - h[160 + t * 8 + i - 1]);
             fprintf(stderr, "\n");
         }
     }
