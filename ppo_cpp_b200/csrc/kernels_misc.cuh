@@ -893,7 +893,7 @@ struct ReduceAdamArgs {
 // blocks of 256 threads.  b1p / b2p are the beta powers BEFORE this step.  Contains one grid barrier.
 __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int blk, int nblk, GridBarrier& bar, unsigned seq,
                                                    float b1p, float b2p, float* loss_row, long long* prof = nullptr, unsigned sqseq = 0u) {
-    __shared__ float part[RA_MAXJ][4][64];
+    __shared__ __align__(16) float part[RA_MAXJ][8][64];
     __shared__ double red[8];
     __shared__ double s_parts[256];
     __shared__ float s_scale;
@@ -909,31 +909,45 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
     RA_PROF();
     float gsum[RA_MAXJ];
     double q = 0.0;
-    float acc[RA_MAXJ];
-    // phase 1: every load of this thread (all its chunks, 8 slabs at a time) is independent of the others
+    // phase 1: thread (column quad cq of the chunk, slab group sg) loads slabs sg, sg + 16, ... as float4 (rows are 16-byte
+    // aligned: PS % 4 == 0); every load of this thread (all its chunks, 4 slabs at a time) is independent of the others
+    const int cq = threadIdx.x & 15, sg = threadIdx.x >> 4;
+    float4 acc4[RA_MAXJ];
 #pragma unroll
-    for (int j = 0; j < RA_MAXJ; ++j) acc[j] = 0.f;
+    for (int j = 0; j < RA_MAXJ; ++j) acc4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int g0 = rg; g0 < r.G; g0 += 64) {  // 16 slabs x RA_MAXJ chunks in flight per thread: one L2 round trip for G <= 64
-        float v[RA_MAXJ][16];
+    for (int g0 = sg; g0 < r.G; g0 += 64) {  // one L2 round trip for G <= 64
+        float4 v[RA_MAXJ][4];
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j) {
-            const int c = (blk + j * nblk) * 64 + lane_c;
+            const int c = (blk + j * nblk) * 64 + 4 * cq;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int g = g0 + 4 * u;
-                v[j][u] = (c < r.PS && g < r.G) ? __ldcg(r.partial + (size_t)g * r.PS + c) : 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + 16 * u;
+                v[j][u] = (c < r.PS && g < r.G) ? __ldcg(reinterpret_cast<const float4*>(r.partial + (size_t)g * r.PS + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
         for (int j = 0; j < RA_MAXJ; ++j)
 #pragma unroll
-            for (int u = 0; u < 16; ++u) acc[j] += v[j][u];
+            for (int u = 0; u < 4; ++u) {
+                acc4[j].x += v[j][u].x; acc4[j].y += v[j][u].y; acc4[j].z += v[j][u].z; acc4[j].w += v[j][u].w;
+            }
     }
     RA_PROF();
-    __syncthreads();
+    // the two slab groups of a warp by a shuffle, the eight warps through shared memory (fixed order, combined in double)
 #pragma unroll
-    for (int j = 0; j < RA_MAXJ; ++j) part[j][rg][lane_c] = acc[j];
+    for (int j = 0; j < RA_MAXJ; ++j) {
+        acc4[j].x += __shfl_xor_sync(0xffffffffu, acc4[j].x, 16);
+        acc4[j].y += __shfl_xor_sync(0xffffffffu, acc4[j].y, 16);
+        acc4[j].z += __shfl_xor_sync(0xffffffffu, acc4[j].z, 16);
+        acc4[j].w += __shfl_xor_sync(0xffffffffu, acc4[j].w, 16);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) < 16) {
+#pragma unroll
+        for (int j = 0; j < RA_MAXJ; ++j) *reinterpret_cast<float4*>(&part[j][threadIdx.x >> 5][4 * cq]) = acc4[j];
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < RA_MAXJ; ++j) {
@@ -942,7 +956,8 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
         if (chunk >= nchunks) break;  // block-uniform
         const int c = chunk * 64 + lane_c;
         if (rg == 0) {
-            const double t = ((double)part[j][0][lane_c] + (double)part[j][1][lane_c]) + ((double)part[j][2][lane_c] + (double)part[j][3][lane_c]);
+            const double t = (((double)part[j][0][lane_c] + (double)part[j][1][lane_c]) + ((double)part[j][2][lane_c] + (double)part[j][3][lane_c])) +
+                             (((double)part[j][4][lane_c] + (double)part[j][5][lane_c]) + ((double)part[j][6][lane_c] + (double)part[j][7][lane_c]));
             gsum[j] = (float)t;
             if (world > 1 && c < r.PS) {  // LL store of (value, seq) into every rank's slot of this rank
                 for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gsum[j]), seq);

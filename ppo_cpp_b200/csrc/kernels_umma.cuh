@@ -289,6 +289,11 @@ struct EpochArgs {
 
 // phase stamps of CTA 0 of each tower: the stand-alone kernel writes a.prof[tower][0..32), the persistent kernel stamps
 // minibatch 2 only (steady state) into a.prof[64 + 48 * tower ..)
+// per-CTA timeline of minibatch 2 (global timer, ns): a.prof[256 + (tower * gridDim.x + blockIdx.x) * 8 + i]
+#define UMMA_TL(i)                                                                                               \
+    do {                                                                                                         \
+        if (PERSIST && a.prof && tid == 0 && prof_on) a.prof[256 + (tower * gridDim.x + blockIdx.x) * 8 + (i)] = (long long)globaltimer_ns(); \
+    } while (0)
 #define UMMA_PROF()                                                                                              \
     do {                                                                                                         \
         if (a.prof && blockIdx.x == 0 && tid == 0 && prof_on && prof_i < (PERSIST ? 48 : 32))                     \
@@ -436,9 +441,15 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (PERSIST) {
             prof_on = mb == 2;
             UMMA_PROF();  // start of the stamped minibatch
+            UMMA_TL(0);
         }
         {
             // weights -> two fp16 pieces in the SWIZZLE_128B operand layout; all global loads are issued before the first use
+            // (Measured and not kept: reading one of 4 / 16 / 64 replicas written by the Adam step instead of the one vector that 64 CTAs
+            // fetch at the same moment — 7.07 / 7.08 / 7.27 ms per update against 7.22 on the same box, no hot-line effect worth the
+            // stores.  Issuing the weight-gradient GEMMs from warps 1 and 2 behind warp 0's critical GEMM: the time moved from the
+            // dH2 / dH1 waits to the wait at the tile's end — the tensor pipe needs ~45 cycles per tcgen05.mma of these shapes (152 per
+            // tile), whoever issues them.  A ninth, issue-only warp: three warps on one SM sub-partition cap the kernel at 168 registers.)
             const float* P = a.params;
             const float* W1 = P + d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
             const float* W0 = P + d.off[tower ? T_VF_FC0_W : T_PI_FC0_W];
@@ -578,6 +589,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         __syncthreads();
         tc_fence_after();
         UMMA_PROF();  // setup done, X' of the first tile staged
+        UMMA_TL(1);
         l_0 = l_1 = l_2 = l_dbv = 0.f;
         accw = false;
 
@@ -843,6 +855,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         cur_mbstats = ep.mbstats + mb + 1;
         load_index(blockIdx.x);
     }
+    UMMA_TL(2);  // tiles done
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
     auto put = [&](int col, float val) { my[col] = val; };
@@ -939,18 +952,22 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
             if (mb + 1 < n_mb) load_rows();  // next minibatch's first tile (index issued before the flush): lands during the barriers
             tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
+            UMMA_TL(3);  // flushed
             bar.sync();
             UMMA_PROF();  // barrier 1 passed
+            UMMA_TL(4);
             ++mseq;
             reduce_adam_device(ep.ra, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), bar, mseq, b1p, b2p,
                                ep.loss_rows + (size_t)mb * 5,
                                (a.prof && blockIdx.x == 0 && mb == 2) ? a.prof + 160 + tower * 8 : nullptr, ++sqseq);
             b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
             b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
-            UMMA_PROF();  // reduce + barrier 2 + Adam done
+            UMMA_PROF();  // reduce + partials + Adam done
+            UMMA_TL(5);
             bar.sync();
             tc_fence_after();
             UMMA_PROF();  // barrier 3 passed
+            UMMA_TL(6);
         }
     }  // minibatches
 #undef LDW
@@ -966,6 +983,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
 #undef UMMA_PROF
+#undef UMMA_TL
 
 }  // namespace umma
 }  // namespace ppo

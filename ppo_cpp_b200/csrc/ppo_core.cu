@@ -113,7 +113,7 @@ struct ppo_core {
     int max_train_grid = 0;
     int prof_train_grid = 0;
     long long* umma_prof = nullptr;  // PPO_UMMA_PROF=1: phase timestamps of the U-family train kernel
-    int PS = 0;           // partial slab width = P + L_PAD
+    int PS = 0;           // partial slab width = P + L_PAD, rounded up to whole float4
 
     float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *bpow = nullptr;  // bpow: 2 slots x 2
     int bpow_slot = 0;
@@ -460,7 +460,7 @@ static int core_alloc(ppo_core* c) {
     c->n_batch_global = c->n_batch_local * W;
     c->B_global = c->n_batch_global / D.nminibatches;
     const int widths[B_COUNT] = {O, 1, 1, A, 1, 1, 1, 1};
-    c->PS = d.P + L_PAD;
+    c->PS = (d.P + L_PAD + 3) & ~3;  // rows of the slab buffer stay 16-byte aligned (float4 loads of the column reduce)
     if (W > 1) {
         // one arena per rank, IPC-mapped by every peer: [mailbox flags | moment slots | gradient slots | the five train inputs].
         // The persistent rollout kernel stores its rows straight into every rank's copy (NVLink P2P), so the buffers are
@@ -623,8 +623,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
             if (st != PPO_OK) break;
         }
         if (c->umma && getenv("PPO_UMMA_PROF")) {
-            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 176) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
-            cudaMemset(c->umma_prof, 0, sizeof(long long) * 176);
+            if (cudaMalloc(&c->umma_prof, sizeof(long long) * 4096) != cudaSuccess) { st = fail(PPO_ERR_CUDA, "cudaMalloc(umma_prof) failed"); break; }
+            cudaMemset(c->umma_prof, 0, sizeof(long long) * 4096);
         }
         {
             int per_sm = 0, coop_ok = 0;
@@ -2481,6 +2481,18 @@ extern "C" int ppo_profile_kernel(ppo_core* c, const char* which, int iters, flo
             fprintf(stderr, "\n   reduce phases (loads | combine + exchange + prefetch | partials / barrier | norm | Adam):");
             for (int i = 1; i < 8 && h[160 + t * 8 + i]; ++i) fprintf(stderr, " %lld", h[160 + t * 8 + i] - h[160 + t * 8 + i - 1]);
             fprintf(stderr, "\n");
+        }
+        if (c->persistent_epoch && getenv("PPO_UMMA_TIMELINE")) {  // per-CTA timeline of minibatch 2, ns since the earliest start
+            std::vector<long long> tl(2 * (size_t)c->epoch_grid * 8);
+            cudaMemcpy(tl.data(), c->umma_prof + 256, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            long long t0 = tl[0];
+            for (size_t i = 0; i < tl.size(); i += 8) t0 = std::min(t0, tl[i]);
+            fprintf(stderr, "timeline: start | weights staged | tiles | flushed | barrier 1 | reduce + Adam | barrier 3\n");
+            for (int b = 0; b < 2 * c->epoch_grid; ++b) {
+                fprintf(stderr, "cta %3d:", b);
+                for (int i = 0; i < 7; ++i) fprintf(stderr, " %6lld", tl[(size_t)b * 8 + i] - t0);
+                fprintf(stderr, "\n");
+            }
         }
     }
     *avg_ms = ms / (float)iters;
