@@ -53,7 +53,8 @@ struct RolloutArgs {
     // CTA writes its actions into mapped pinned host memory, raises its flag, and polls the host's flag for the env's answer
     // (raw observation, reward, done in mapped pinned memory).  One kernel for the whole rollout: no launch, no stream
     // synchronisation and no cudaMemcpy per env step — per step it costs one PCIe write, one host poll, one PCIe read.
-    float* h_actions;             // [n][A]   device -> host
+    float* h_actions;             // [n][A]   device -> host (step t at h_actions + t * h_act_stride)
+    size_t h_act_stride;          // 0: one buffer reused every step; n * A: the caller's [n_steps][n][A] array, written in place
     const float *h_obs, *h_rew, *h_done;  // [n][O], [n], [n]   host -> device
     unsigned* h_act_flag;         // [gridDim.x]: t + 1 once this CTA's actions of step t are in h_actions
     const unsigned* h_obs_flag;   // t + 1 once the env's answer to step t is in place; PPO_HOST_ENV_ABORT = stop
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                 if (pass == 0) {  // actions of this tile -> the host's array (clipping is the env's business, hexapod_env.hpp:140)
                     for (int e = tid; e < nv * A; e += NTH) {
                         const int m = e / A, j = e - m * A;
-                        a.h_actions[(size_t)r0 * A + e] = Ac[j * (TM + 1) + m];
+                        a.h_actions[(size_t)t * a.h_act_stride + (size_t)r0 * A + e] = Ac[j * (TM + 1) + m];
                     }
                     __syncthreads();  // Ac is reused by the next tile
                     continue;

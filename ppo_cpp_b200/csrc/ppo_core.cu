@@ -189,6 +189,8 @@ struct ppo_core {
     size_t scratch_floats = 0;
     float* hx_mem = nullptr;     // host-env exchange of the persistent rollout kernel: flags, actions, obs / rew / done (mapped pinned)
     float* hx_dev = nullptr;     // ... its device address
+    float* hx_stage = nullptr;   // ... with more than 512 envs the env's answer goes through the copy engine: device staging [obs | rew | done | flag]
+    cudaStream_t stream3 = nullptr;  // ... on its own stream (the rollout kernel occupies c->stream while it polls)
     void* gae_ab = nullptr;      // per-(chunk, env) affine maps of the exact chunked GAE (gamma*lam near 1)
     size_t gae_ab_bytes = 0;
 
@@ -398,6 +400,8 @@ extern "C" void ppo_core_destroy(ppo_core* c) {
     if (c->mbox_mem) cudaFree(c->mbox_mem);
     if (c->gae_ab) cudaFree(c->gae_ab);
     if (c->hx_mem) cudaFreeHost(c->hx_mem);
+    if (c->hx_stage) cudaFree(c->hx_stage);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
     if (c->wide_mem) cudaFree(c->wide_mem);
     if (c->sync_vars) cudaFree(c->sync_vars);
     if (c->sq_ll) cudaFree(c->sq_ll);
@@ -1429,23 +1433,41 @@ static int prefetch_shuffle(ppo_core* c);
 // mapped host memory: a win while a step is latency-bound (C1: 1 env, 49 -> 17 us per env step), a loss once the
 // observations are hundreds of KB per step (C3, 4096 envs: measured 326 us per step against 64 us with the copy engine).
 static bool host_persistent_ok(const ppo_core* c) {
-    return c->persistent_rollout && c->desc.world_size == 1 && c->desc.n_envs <= 512 && getenv("PPO_DISABLE_HOST_PERSISTENT") == nullptr;
+    return c->persistent_rollout && c->desc.world_size == 1 && getenv("PPO_DISABLE_HOST_PERSISTENT") == nullptr &&
+           (c->desc.n_envs <= 512 || getenv("PPO_DISABLE_HOST_STAGED") == nullptr);
 }
+// up to 512 envs the kernel reads the env's answer with SM loads from mapped host memory; beyond, the copy engine moves it into a
+// device staging buffer and a 4-byte copy behind it raises the flag the kernel polls (SM loads over PCIe: 326 us per step at 4096 envs)
+static bool host_persistent_staged(const ppo_core* c) { return c->desc.n_envs > 512 && getenv("PPO_FORCE_HOST_MAPPED") == nullptr; }
 
 // Host-env rollout as ONE persistent kernel (kernels_rollout.cuh, host-env mode): the kernel and this loop hand the actions
 // and the env's answers back and forth through mapped pinned memory and two flags.
-static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user, float* actions) {
+// direct_actions: the callback may read the actions where the kernel put them (no copy into `actions`); actions_all: the
+// caller's pinned [n_steps][n_envs][A] array, written in place by the kernel when it is device-accessible (or NULL)
+static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user, float* actions, bool direct_actions = false,
+                                   float* actions_all = nullptr) {
     const ppo_core_desc& D = c->desc;
     const size_t N = (size_t)D.n_envs, O = (size_t)c->d.O, A = (size_t)c->d.A;
+    const bool staged = host_persistent_staged(c);
     if (!c->hx_mem) {
-        // [obs flag | act flags (grid) | actions N*A | obs N*O | rew N | done N], mapped + pinned
-        const size_t words = 64 + (size_t)((c->roll_grid + 63) & ~63) + N * A + N * O + 2 * N;
+        // [obs flag | act flags (grid) | actions N*A | obs N*O | rew N | done N | flag values 1 .. n_steps, abort], mapped + pinned
+        const size_t words = 64 + (size_t)((c->roll_grid + 63) & ~63) + N * A + N * O + 2 * N + (size_t)D.n_steps + 2;
         CU(cudaHostAlloc(reinterpret_cast<void**>(&c->hx_mem), words * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
         memset(c->hx_mem, 0, words * sizeof(float));
         CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hx_dev), c->hx_mem, 0));
     }
+    if (staged && !c->hx_stage) {
+        CU(cudaMalloc(&c->hx_stage, (N * O + 2 * N + 64) * sizeof(float)));
+        CU(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    }
     const size_t off_actf = 64, off_act = off_actf + (size_t)((c->roll_grid + 63) & ~63), off_obs = off_act + N * A, off_rew = off_obs + N * O,
-                 off_done = off_rew + N;
+                 off_done = off_rew + N, off_fval = off_done + N;
+    unsigned* flag_vals = reinterpret_cast<unsigned*>(c->hx_mem) + off_fval;  // sources of the 4-byte flag copies (staged mode)
+    for (int t = 0; t < D.n_steps; ++t) flag_vals[t] = (unsigned)t + 1u;
+    flag_vals[D.n_steps] = PPO_HOST_ENV_ABORT;
+    flag_vals[D.n_steps + 1] = 0u;
+    float* s_obs = c->hx_stage;
+    unsigned* s_flag = staged ? reinterpret_cast<unsigned*>(c->hx_stage + N * O + 2 * N) : nullptr;
     volatile unsigned* obs_flag = reinterpret_cast<volatile unsigned*>(c->hx_mem);
     volatile unsigned* act_flag = reinterpret_cast<volatile unsigned*>(c->hx_mem) + off_actf;
     float* h_act = c->hx_mem + off_act;
@@ -1453,12 +1475,31 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     *obs_flag = 0u;
     for (int b = 0; b < c->roll_grid; ++b) act_flag[b] = 0u;
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    if (staged) {
+        CU(cudaMemcpyAsync(s_flag, flag_vals + D.n_steps + 1, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream3));
+        CU(cudaStreamSynchronize(c->stream3));
+    }
     TRY(prefetch_shuffle(c));
     RolloutArgs r = make_rollout_args(c);
     r.h_actions = c->hx_dev + off_act;
     r.h_obs = c->hx_dev + off_obs; r.h_rew = c->hx_dev + off_rew; r.h_done = c->hx_dev + off_done;
     r.h_act_flag = reinterpret_cast<unsigned*>(c->hx_dev) + off_actf;
     r.h_obs_flag = reinterpret_cast<const unsigned*>(c->hx_dev);
+    if (staged) {  // observations through the copy engine; rewards / dones (8 bytes per env) stay in mapped memory: two API calls per step
+        r.h_obs = s_obs;
+        r.h_obs_flag = s_flag;
+    }
+    float* act_base = nullptr;  // host address of the kernel's action stores when they go straight into the caller's array
+    if (direct_actions && actions_all) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, actions_all, 0) == cudaSuccess && dp) {
+            r.h_actions = static_cast<float*>(dp);
+            r.h_act_stride = N * A;
+            act_base = actions_all;
+        } else {
+            cudaGetLastError();
+        }
+    }
     void* kargs[] = {&r};
     CU(cudaLaunchCooperativeKernel((void*)rollout_persistent_kernel, dim3(c->roll_grid), dim3(R_NTH), kargs, c->roll_smem, c->stream));
     c->ctr.kernel_launches++;
@@ -1478,25 +1519,47 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         }
         if (st != PPO_OK) break;
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        memcpy(actions, h_act, N * A * sizeof(float));
+        const float* acts = act_base ? act_base + (size_t)t * N * A : h_act;  // the kernel's stores into mapped host memory (posted PCIe writes)
+        if (!direct_actions) {
+            memcpy(actions, acts, N * A * sizeof(float));
+            acts = actions;
+        }
         c->ctr.d2h_bytes += N * A * sizeof(float);
         const float *o = nullptr, *rw = nullptr, *dn = nullptr;
-        if (step(user, t, actions, &o, &rw, &dn) != 0 || !o || !rw || !dn) {
+        if (step(user, t, acts, &o, &rw, &dn) != 0 || !o || !rw || !dn) {
             st = fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: the env aborted at step %d", t);
             break;
         }
-        memcpy(c->hx_mem + off_obs, o, N * O * sizeof(float));
-        memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
-        memcpy(c->hx_mem + off_done, dn, N * sizeof(float));
+        if (staged) {  // copy engine, then the flag behind the data on the same stream
+            memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
+            memcpy(c->hx_mem + off_done, dn, N * sizeof(float));
+            __atomic_thread_fence(__ATOMIC_RELEASE);
+            if (cudaMemcpyAsync(s_obs, o, N * O * sizeof(float), cudaMemcpyHostToDevice, c->stream3) != cudaSuccess ||
+                cudaMemcpyAsync(s_flag, flag_vals + t, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream3) != cudaSuccess) {
+                st = fail(PPO_ERR_CUDA, "host-env rollout: H2D copy of step %d failed: %s", t, cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        } else {
+            memcpy(c->hx_mem + off_obs, o, N * O * sizeof(float));
+            memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
+            memcpy(c->hx_mem + off_done, dn, N * sizeof(float));
+        }
         c->ctr.h2d_bytes += N * (O + 2) * sizeof(float);
         __atomic_thread_fence(__ATOMIC_RELEASE);
-        *obs_flag = (unsigned)t + 1u;
+        if (!staged) *obs_flag = (unsigned)t + 1u;
+    }
+    if (staged && st == PPO_OK) {  // the env's arrays of the last step may be released when this call returns
+        if (cudaStreamSynchronize(c->stream3) != cudaSuccess) st = fail(PPO_ERR_CUDA, "host-env rollout: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (st != PPO_OK) {
         char keep[1024];
         strncpy(keep, g_err, sizeof(keep));
         *obs_flag = PPO_HOST_ENV_ABORT;  // releases the kernel
         __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        if (staged) {
+            cudaMemcpyAsync(s_flag, flag_vals + D.n_steps, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream3);
+            cudaStreamSynchronize(c->stream3);
+        }
         cudaStreamSynchronize(c->stream);
         strncpy(g_err, keep, sizeof(g_err));
         return st;
@@ -1545,6 +1608,10 @@ extern "C" int ppo_runner_rollout_replay(ppo_core* c, const float* raw_obs, cons
             TRY(ppo_runner_observe(c, t, raw_obs + (size_t)t * env.no, raw_rew + (size_t)t * N, done + (size_t)t * N, PPO_HOST));
         }
         return ppo_runner_finish(c);
+    }
+    if (persistent) {  // the recorded env reads the actions where the kernel put them (one copy into actions_out, none without it)
+        CU(cudaSetDevice(c->desc.device));
+        return rollout_host_persistent(c, replay_env_step, &env, nullptr, true, actions_out);
     }
     std::vector<float> scratch(env.na);
     return ppo_runner_rollout_host(c, replay_env_step, &env, scratch.data());
