@@ -376,7 +376,7 @@ def run_ours(args):
         ce = c.counters()
         e2e = {"value": n_batch_global * k_e2e / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": ce["h2d_bytes"] // k_e2e,
                "d2h_bytes_per_step": ce["d2h_bytes"] // k_e2e, "steps": k_e2e, "ms_per_step": float(tt[0]) / k_e2e * 1e3,
-               "path": "ppo_runner_rollout_replay (per env step: act -> D2H actions, H2D obs/rew/done -> observe) + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
+               "path": "ppo_runner_rollout_replay (Runner::run against a host env as one persistent kernel: per env step the actions are stored into the caller's pinned array over PCIe, the env's obs come back through the copy engine with a flag copy behind them, rewards / dones through mapped memory) + ppo_train_update with pinned HOST buffers, host env = replayed synthetic arrays",
                "final_losses": [float(x) for x in losses]}
 
     # ---- multi-GPU parity, outside the timed region: the run sharded over `world` ranks against ONE GPU running the same

@@ -866,11 +866,13 @@ def test_runner_rollout_replay_equals_stepwise_protocol(core_mod, ckpt_weights, 
     b.close()
 
 
-@pytest.mark.parametrize("n_envs", [1, 40])
+@pytest.mark.parametrize("n_envs", [1, 40, 700])
 def test_host_env_one_kernel_rollout_equals_stepwise_and_aborts_cleanly(core_mod, monkeypatch, ckpt_weights, n_envs):
-    """ppo_runner_rollout_host with a live host env (Python callback): up to 512 envs the whole rollout is ONE persistent
-    kernel that trades actions / observations with the host through mapped pinned memory.  It must equal the per-step
-    protocol bit for bit over consecutive rollouts, and an env that aborts must release the kernel and leave the core usable."""
+    """ppo_runner_rollout_host with a live host env (Python callback): the whole rollout is ONE persistent kernel that trades
+    actions / observations with the host — through mapped pinned memory up to 512 envs, beyond that the env's answer goes
+    through the copy engine into a device staging buffer with a 4-byte flag copy behind it (700 envs here).  It must equal
+    the per-step protocol over consecutive rollouts (bit for bit up to 512 envs; with more CTAs the fp64 moment partials are
+    cut differently: 1e-5), and an env that aborts must release the kernel and leave the core usable."""
     _, flat = ckpt_weights
     n_steps, seed = 24, 8
     lib = ol.load()
@@ -902,8 +904,15 @@ def test_host_env_one_kernel_rollout_equals_stepwise_and_aborts_cleanly(core_mod
     c2, stepwise, st2 = run(True)
     for a, b in zip(one_kernel, stepwise):
         for n in a:
-            assert np.array_equal(a[n], b[n]), n
-    assert st1["obs_count"] == st2["obs_count"] and np.array_equal(st1["obs_mean"], st2["obs_mean"])
+            if n_envs <= 512 or n == "dones":
+                assert np.array_equal(a[n], b[n]), n
+            else:
+                assert rel_err(a[n], b[n]) < 1e-5, n
+    assert st1["obs_count"] == st2["obs_count"]
+    if n_envs <= 512:
+        assert np.array_equal(st1["obs_mean"], st2["obs_mean"])
+    else:
+        assert rel_err(st1["obs_mean"], st2["obs_mean"]) < 1e-5
     # an env that gives up at step 5: the call fails, nothing hangs, the next rollout works
     monkeypatch.delenv("PPO_DISABLE_HOST_PERSISTENT", raising=False)
     o, r, d = np.zeros((n_envs, 18), np.float32), np.zeros(n_envs, np.float32), np.zeros(n_envs, np.float32)
