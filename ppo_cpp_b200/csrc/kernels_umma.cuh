@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     for (int k = 0; k < 4; ++k) f32[F32_RED + warp * 4 + k] = mx[k];
                 }
                 __syncthreads();
+                UMMA_PROF();  // parameters arrived, maxima exchanged
     #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float m = f32[F32_RED + k];
@@ -574,6 +575,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 }
             }
         }
+        UMMA_PROF();  // weight blocks written
         // epilogue factors of this minibatch (exact powers of two)
         const float u_w0 = pow2f(-k_w0 - PW_X), u_w1 = pow2f(-k_w1 - PW_H), u_hd = pow2f(-k_hd - PW_H);
         const float s_hd_v = pow2f(k_hd - PW_W);                 // V tower: dP2 = dv * (wv 2^kh) (1 - g2^2), kh = k_hd - PW_W
