@@ -58,16 +58,17 @@ constexpr uint32_t W0_PIECE = 32 * 128;         // [32 x 64] fp16 (rows: O input
 constexpr uint32_t W1_PIECE = 64 * 128;         // [64 x 64]
 constexpr uint32_t WP_PIECE = 64 * 128;         // [64 x 64], columns >= A are zero
 constexpr uint32_t ROW8_PIECE = 2 * 1024;       // [8 x 128] fp16, K-major operand over the 128 samples
+constexpr uint32_t ROW16_BLOCK = 4 * 1024;      // [16 x 128] fp16 K-major: per 64-sample half 16 rows of 128 B (rows 0..7 | rows 8..15)
 constexpr uint32_t OFF_H1 = 0;
 constexpr uint32_t OFF_H2 = OFF_H1 + ACT_BLOCK;
-constexpr uint32_t OFF_Y = OFF_H2 + ACT_BLOCK;  // X' (obs + ones column), later [dMU | dLS], later X' again
+constexpr uint32_t OFF_Y = OFF_H2 + ACT_BLOCK;  // X' (obs + ones column)
 constexpr uint32_t OFF_D2 = OFF_Y + ACT_BLOCK;  // dP2 = dL/d(pre-activation of layer 1)
-constexpr uint32_t OFF_D1 = OFF_D2 + ACT_BLOCK; // dP1
+constexpr uint32_t OFF_D1 = OFF_D2 + ACT_BLOCK; // [dMU | dLS] (pi tower), then dP1
 constexpr uint32_t OFF_W0 = OFF_D1 + ACT_BLOCK;
 constexpr uint32_t OFF_W1 = OFF_W0 + NP * W0_PIECE;
 constexpr uint32_t OFF_WP = OFF_W1 + NP * W1_PIECE;   // pi head weights; the V tower keeps its dv rows here
 constexpr uint32_t OFF_ONES = OFF_WP + NP * WP_PIECE;
-constexpr uint32_t OFF_F32 = OFF_ONES + ROW8_PIECE;  // fp32 vectors
+constexpr uint32_t OFF_F32 = OFF_ONES + ROW16_BLOCK;  // fp32 vectors
 constexpr uint32_t F32_B1 = 0, F32_BH = 64, F32_WV = 96, F32_SD = 160, F32_LS = 192, F32_MISC = 224, F32_PV = 256,
                    F32_DV = 512, F32_RED = 640, F32_ISD = 704, F32_COUNT = 736;
 constexpr uint32_t OFF_BAR = OFF_F32 + F32_COUNT * 4;
@@ -75,8 +76,14 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 64 + 1024;  // + alignment slack
 
 // ---- TMEM columns: every accumulator has a twin ("+ XC") for the small cross products
 constexpr uint32_t ACC_WORK = 0, ACC_WORK_C = 64;  // Z1, Z2, MU (first 32 columns), dH2, dH1
-constexpr uint32_t ACC_DWP = 128, ACC_DWP_C = 160, ACC_CS = 192, ACC_CS_C = 200, ACC_DW1 = 208, ACC_DW1_C = 272, ACC_DB1 = 336,
-                   ACC_DB1_C = 344, ACC_DW0 = 352, ACC_DW0_C = 384, TMEM_COLS = 512;
+// Weight-gradient accumulators (M = 64: row r in TMEM lane 32 * (r >> 4) + (r & 15)), TWO instructions per k-step: the B operand with
+// its pieces side by side ([Q_hi | Q_lo], N = 128 / 96 / 16: the piece stride is the atom stride of the descriptor) gives the leading
+// product in columns [0, 64) and hi x lo in columns [64, ..); the second instruction adds P_lo x Q_hi to the cross columns.
+// Column sums (M = 128: row r in lane r), ONE instruction per k-step: [P_hi ; P_lo] x ones -> rows < 64 hi sums, rows >= 64 lo sums.
+// (Stacking P for the big gradients too — one instruction per k-step — was measured: the lo x hi rows then sit in other lanes than
+// the rows they belong to and the flush pays more for bringing them together than the 24 instructions saved.)
+constexpr uint32_t ACC_DWP = 128 /* N = 96 (pi) | 16 (V) */, ACC_CS = 224 /* N = 16 */, ACC_DW1 = 240 /* N = 128 */, ACC_DB1 = 368 /* N = 16 */,
+                   ACC_DW0 = 384 /* N = 96 */, TMEM_COLS = 512;
 
 // 2^k for -126 <= k <= 127 (the exponents of the block floating point scheme stay within +-100)
 __device__ __forceinline__ float pow2f(int k) { return __int_as_float((k + 127) << 23); }
@@ -167,6 +174,45 @@ __device__ __forceinline__ void issue_gemm(uint32_t dm, uint32_t dc, const Opera
     }
 }
 
+// D (+)= A * B for a GEMM whose result an epilogue waits for, in TWO instructions per k-step instead of three: the two pieces of
+// B sit one piece stride apart, which is exactly the stride between two 64-wide (MN-major view) / 64-row (K-major view) atoms
+// of the same descriptor, so ONE instruction with N doubled to 128 computes A_hi * [B_hi | B_lo] -> columns [0, 64) (leading
+// product, alone in its accumulator) and [64, 128) (cross product); the second adds A_lo * B_hi to the cross columns.  The
+// tensor pipe spends ~45 cycles per instruction of these shapes whatever N is, so instructions are what counts.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm_wide(uint32_t dwork, const Operand& A, const Operand& B, uint32_t idesc_n128, uint32_t idesc_cross) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t a = A.desc + (uint64_t)((ks >> 2) * A.k_hi + (ks & 3) * A.k_lo);
+        const uint64_t b = B.desc + (uint64_t)((ks >> 2) * B.k_hi + (ks & 3) * B.k_lo);
+        mma_f16(dwork, a, b, idesc_n128, ks ? 1u : 0u);
+        mma_f16(dwork + 64u, a + A.piece, b, idesc_cross, 1u);
+    }
+}
+
+// weight gradient, two instructions per k-step (see the TMEM map): A_hi x [B_hi | B_lo] -> d, A_lo x B_hi -> d + cross_col
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm_dw(uint32_t d, uint32_t cross_col, const Operand& A, const Operand& B, uint32_t idesc_wide, uint32_t idesc_cross,
+                                              bool accumulate) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t a = A.desc + (uint64_t)((ks >> 2) * A.k_hi + (ks & 3) * A.k_lo);
+        const uint64_t b = B.desc + (uint64_t)((ks >> 2) * B.k_hi + (ks & 3) * B.k_lo);
+        mma_f16(d, a, b, idesc_wide, (ks || accumulate) ? 1u : 0u);
+        mma_f16(d + cross_col, a + A.piece, b, idesc_cross, 1u);
+    }
+}
+// column sums, one instruction per k-step: both pieces of A stacked as M = 128
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm_stacked(uint32_t d, const Operand& A, const Operand& B, uint32_t idesc, bool accumulate) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t a = A.desc + (uint64_t)((ks >> 2) * A.k_hi + (ks & 3) * A.k_lo);
+        const uint64_t b = B.desc + (uint64_t)((ks >> 2) * B.k_hi + (ks & 3) * B.k_lo);
+        mma_f16(d, a, b, idesc, (ks || accumulate) ? 1u : 0u);
+    }
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -209,6 +255,20 @@ __device__ __forceinline__ void tmem_ld32_sum(uint32_t tmain, uint32_t tcross, f
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
+}
+#define PPO_TMEM_LD16(taddr, r)                                                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"              \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                        \
+                 : "r"(taddr))
+// the same 16 columns at a time: half the live temporaries (the epilogues of the tile loop sit at the register limit)
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t tmain, uint32_t tcross, float* v) {
+    uint32_t r[16], s[16];
+    PPO_TMEM_LD16(tmain, r);
+    PPO_TMEM_LD16(tcross, s);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(s[i]);
 }
 __device__ __forceinline__ void tmem_ld8_sum(uint32_t tmain, uint32_t tcross, float* v) {
     uint32_t r[8], s[8];
@@ -384,9 +444,9 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     // constant operand blocks: the V tower's dv rows (row 0 is rewritten per tile, rows 1..7 stay zero) and the ones block
     // (row 0 of each 8-row group = 2^PW_H = 256.0 = fp16 0x5C00, the scale of the activation blocks; rows 1..7 = 0)
     if (tower != 0)
-        for (int i = tid; i < NP * (int)ROW8_PIECE / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < (int)ROW8_PIECE / 16) {
-        const uint32_t v = ((tid & 63) < 8) ? 0x5C005C00u : 0u;
+        for (int i = tid; i < (int)ROW16_BLOCK / 16; i += NTH) reinterpret_cast<uint4*>(smem + OFF_WP)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < (int)ROW16_BLOCK / 16) {  // per 64-sample half: 128 chunks of 16 B, the first 8 are row 0
+        const uint32_t v = ((tid & 127) < 8) ? 0x5C005C00u : 0u;
         reinterpret_cast<uint4*>(smem + OFF_ONES)[tid] = make_uint4(v, v, v, v);
     }
     // persistent state: grid barrier generation, mailbox sequence number, Adam's beta powers (every CTA tracks them)
@@ -410,19 +470,26 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     const Operand opD2_k = op_kmajor(sbase + OFF_D2, ACT_PIECE, TM);
     const Operand opD2_mn = op_mnmajor(sbase + OFF_D2, ACT_PIECE, TM);
     const Operand opD1_mn = op_mnmajor(sbase + OFF_D1, ACT_PIECE, TM);
+    const Operand opD1_k = op_kmajor(sbase + OFF_D1, ACT_PIECE, TM);    // [dMU | dLS] as A (pi tower, until dP1 takes the block)
     const Operand opW0_f = op_mnmajor(sbase + OFF_W0, W0_PIECE, 32);    // forward: B(n = out, k = in)
     const Operand opW1_f = op_mnmajor(sbase + OFF_W1, W1_PIECE, 64);
     const Operand opW1_b = op_kmajor(sbase + OFF_W1, W1_PIECE, 64);     // backward: B(n = in, k = out)
     const Operand opWP_f = op_mnmajor(sbase + OFF_WP, WP_PIECE, 64);
     const Operand opWP_b = op_kmajor(sbase + OFF_WP, WP_PIECE, 64);
-    const Operand opDV = op_kmajor(sbase + OFF_WP, ROW8_PIECE, 8);      // V tower: row 0 = dv over the samples
-    const Operand opONES = op_kmajor(sbase + OFF_ONES, ROW8_PIECE, 8);
+    const Operand opDV = op_kmajor(sbase + OFF_WP, 0, 16);              // V tower: row 0 = dv_hi, row 8 = dv_lo over the samples
+    const Operand opONES = op_kmajor(sbase + OFF_ONES, 0, 16);          // row 0 = ones, the rest zero
     const uint32_t id_f64 = make_idesc(128, 64, 0, 1);    // act(K-major) x W(MN view), N = 64
+    const uint32_t id_f128 = make_idesc(128, 128, 0, 1);  // ... x [W_hi | W_lo], N = 128
+    const uint32_t id_b128 = make_idesc(128, 128, 0, 0);  // dY(K-major) x [W_hi ; W_lo] (K-major view), N = 128
     const uint32_t id_f32 = make_idesc(128, 32, 0, 1);    // head forward, N = 32
     const uint32_t id_b64 = make_idesc(128, 64, 0, 0);    // dY(K-major) x W(K-major view)
-    const uint32_t id_w64 = make_idesc(64, 64, 1, 1);     // dY^T x act over samples, N = 64
-    const uint32_t id_w32 = make_idesc(64, 32, 1, 1);     // N = 32
-    const uint32_t id_s8 = make_idesc(64, 8, 1, 0);       // column sums / V head: MN-major A x K-major [8 x 128] B
+    const uint32_t id_w128 = make_idesc(64, 128, 1, 1);   // dY_hi^T x [act_hi | act_lo] over samples
+    const uint32_t id_w96 = make_idesc(64, 96, 1, 1);     // ... x [B_hi (64 columns) | B_lo (32 columns)]
+    const uint32_t id_w64 = make_idesc(64, 64, 1, 1);     // dY_lo^T x act_hi
+    const uint32_t id_w32 = make_idesc(64, 32, 1, 1);
+    const uint32_t id_v16 = make_idesc(64, 16, 1, 0);     // V head: H2_hi^T x [dv_hi ; dv_lo] (K-major [16 x 128] B)
+    const uint32_t id_v8 = make_idesc(64, 8, 1, 0);       // H2_lo^T x dv_hi
+    const uint32_t id_s16 = make_idesc(128, 16, 1, 0);    // column sums: MN-major [A_hi ; A_lo] x K-major ones
 
     const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
     // the backward tensors (which carry the 1/B of the batch mean) are stored times a power of two so that they are O(1) as
@@ -608,7 +675,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<2, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opW0_f, id_f64, false);
+                issue_gemm_wide<2>(tmem + ACC_WORK, opY_k, opW0_f, id_f128, id_f64);
                 umma_commit(barA);
             }
             __syncwarp();
@@ -616,13 +683,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         mbar_wait(barA, phA); phA ^= 1;
         tc_fence_after();
         UMMA_PROF();
-        {
-            float v[32];
-            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h1r[j] = tanhf(v[j] * u_w0);
-            store_row32(sH1, row, half, h1r, H_SCALE);
+        for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time
+            float v[16];
+            tmem_ld16_sum(tlane + ACC_WORK + 32 * half + 16 * hh, tlane + ACC_WORK_C + 32 * half + 16 * hh, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h1r[16 * hh + j] = tanhf(v[j] * u_w0);
         }
+        store_row32(sH1, row, half, h1r, H_SCALE);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -632,7 +700,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH1_k, opW1_f, id_f64, false);
+                issue_gemm_wide<4>(tmem + ACC_WORK, opH1_k, opW1_f, id_f128, id_f64);
                 umma_commit(barA);
             }
             __syncwarp();
@@ -648,13 +716,17 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         tc_fence_after();
         UMMA_PROF();
         {
-            float v[32];
-            tmem_ld32_sum(tlane + ACC_WORK + 32 * half, tlane + ACC_WORK_C + 32 * half, v);
             float pv = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                h2r[j] = tanhf(fmaf(v[j], u_w1, f32[F32_B1 + 32 * half + j]));
-                pv = fmaf(h2r[j], f32[F32_WV + 32 * half + j], pv);
+            for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time
+                float v[16];
+                tmem_ld16_sum(tlane + ACC_WORK + 32 * half + 16 * hh, tlane + ACC_WORK_C + 32 * half + 16 * hh, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = 16 * hh + j;
+                    h2r[jj] = tanhf(fmaf(v[j], u_w1, f32[F32_B1 + 32 * half + jj]));
+                    pv = fmaf(h2r[jj], f32[F32_WV + 32 * half + jj], pv);
+                }
             }
             store_row32(sH2, row, half, h2r, H_SCALE);
             if (tower == 1) f32[F32_PV + half * TM + row] = pv;
@@ -669,7 +741,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opH2_k, opWP_f, id_f32, false);
+                    issue_gemm_wide<4>(tmem + ACC_WORK, opH2_k, opWP_f, id_f128, id_f32);
                     umma_commit(barA);
                 }
                 __syncwarp();
@@ -724,7 +796,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) z[j] = (j < A) ? g_nlp * (1.f - z[j] * z[j]) : 0.f;  // d nlp / d logstd_j
                 }
-                store_row32(sY, row, half, z);
+                store_row32(sD1, row, half, z);  // (the dP1 block is free until the end of the tile; X' stays in its own)
             }
             fence_async_smem();
             tc_fence_before();
@@ -735,10 +807,10 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_gemm<2, 2>(tmem + ACC_WORK, tmem + ACC_WORK_C, opY_k, opWP_b, id_b64, false);
+                    issue_gemm_wide<2>(tmem + ACC_WORK, opD1_k, opWP_b, id_b128, id_b64);
                     umma_commit(barA);
-                    issue_gemm<2, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opY_mn, id_w32, accw);
-                    issue_gemm<1, 8>(tmem + ACC_CS, tmem + ACC_CS_C, opY_mn, opONES, id_s8, accw);
+                    issue_gemm_dw<8>(tmem + ACC_DWP, 64u, opH2_mn, opD1_mn, id_w96, id_w32, accw);
+                    issue_gemm_stacked<8>(tmem + ACC_CS, opD1_mn, opONES, id_s16, accw);
                     umma_commit(barB);
                 }
                 __syncwarp();
@@ -770,9 +842,9 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 f32[F32_DV + row] = dv;
                 uint32_t p0, p1;
                 split_pair(dv, 0.f, p0, p1);
-                const uint32_t o = (uint32_t)((row >> 6) * 1024 + (((row & 63) >> 3) << 4) + (row & 7) * 2);  // row 0 of the [8 x 128] block
+                const uint32_t o = (uint32_t)((row >> 6) * 2048 + (((row & 63) >> 3) << 4) + (row & 7) * 2);  // row 0 (hi) / row 8 (lo) of the [16 x 128] block
                 *reinterpret_cast<uint16_t*>(smem + OFF_WP + o) = (uint16_t)p0;
-                *reinterpret_cast<uint16_t*>(smem + OFF_WP + ROW8_PIECE + o) = (uint16_t)p1;
+                *reinterpret_cast<uint16_t*>(smem + OFF_WP + 1024 + o) = (uint16_t)p1;
             }
             fence_async_smem();
             tc_fence_before();
@@ -781,7 +853,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             // dWv += H2^T * dv (off the critical path; collected by barC)
             if (warp == 0) {
                 tc_fence_after();
-                if (elect_one()) issue_gemm<2, 8>(tmem + ACC_DWP, tmem + ACC_DWP_C, opH2_mn, opDV, id_s8, accw);
+                if (elect_one()) issue_gemm_dw<8>(tmem + ACC_DWP, 8u, opH2_mn, opDV, id_v16, id_v8, accw);
                 __syncwarp();
             }
             const float dvr = f32[F32_DV + row];
@@ -800,22 +872,18 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<2, 4>(tmem + ACC_WORK, tmem + ACC_WORK_C, opD2_k, opW1_b, id_b64, false);
+                issue_gemm_wide<4>(tmem + ACC_WORK, opD2_k, opW1_b, id_b128, id_b64);
                 umma_commit(barA);
-                issue_gemm<2, 8>(tmem + ACC_DW1, tmem + ACC_DW1_C, opD2_mn, opH1_mn, id_w64, accw);
-                issue_gemm<1, 8>(tmem + ACC_DB1, tmem + ACC_DB1_C, opD2_mn, opONES, id_s8, accw);
+                issue_gemm_dw<8>(tmem + ACC_DW1, 64u, opD2_mn, opH1_mn, id_w128, id_w64, accw);
+                issue_gemm_stacked<8>(tmem + ACC_DB1, opD2_mn, opONES, id_s16, accw);
             }
             __syncwarp();
         }
-        // pi tower: X' again for the layer-0 weight gradient (its block held [dMU | dLS] in between; barB says the MMAs
-        // that read those have completed)
-        if (tower == 0) {
-            ObsRegs<O> xr;
-            xr.load(a.obs, c_grow, gh, valid);
-            mbar_wait(barB, phB); phB ^= 1;
-            xr.store(sY, gr, gh);
-        }
         mbar_wait(barA, phA); phA ^= 1;
+        // pi tower: dP1 goes where [dMU | dLS] sat; barB says the MMAs that read those (issued two phases ago) have completed
+        if (tower == 0) {
+            mbar_wait(barB, phB); phB ^= 1;
+        }
         tc_fence_after();
         UMMA_PROF();
         {
@@ -833,7 +901,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<2, 8>(tmem + ACC_DW0, tmem + ACC_DW0_C, opD1_mn, opY_mn, id_w32, accw);
+                issue_gemm_dw<8>(tmem + ACC_DW0, 64u, opD1_mn, opY_mn, id_w96, id_w32, accw);
                 umma_commit(barC);
             }
             __syncwarp();
@@ -861,9 +929,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
     auto put = [&](int col, float val) { my[col] = val; };
-    // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15)
+    // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15); the column sums (M = 128: row r in lane r) have their
+    // lo parts in the upper lane quarters: those warps park them in shared memory for the warps that own the rows
     const int r64 = q * 16 + lane;
     const bool has = lane < 16;
+    float* S4 = f32 + F32_PV;  // [db1 lo 64 | head lo 64] (the per-sample scratch of the tiles is free)
     if (!accw) {  // no tile for this CTA: write zeros
         if (tower == 0) {
             for (int i = tid; i < d.H1 * O + d.H1; i += NTH) put(d.off[T_PI_FC0_W] + i, 0.f);
@@ -876,8 +946,19 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         }
     } else {
         float v[32];
+        uint32_t r8[8];
+        if (half == 1 && q >= 2) {  // lo parts of the column sums (rows 64 + 32 (q - 2) + lane)
+            PPO_TMEM_LD8(tlane + ACC_DB1, r8);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            S4[(q - 2) * 32 + lane] = __uint_as_float(r8[0]);
+            if (tower == 0) {
+                PPO_TMEM_LD8(tlane + ACC_CS, r8);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                S4[64 + (q - 2) * 32 + lane] = __uint_as_float(r8[0]);
+            }
+        }
         // dW1^T[j][k] -> W1[k][j]
-        tmem_ld32_sum(tlane + ACC_DW1 + 32 * half, tlane + ACC_DW1_C + 32 * half, v);
+        tmem_ld32_sum(tlane + ACC_DW1 + 32 * half, tlane + ACC_DW1 + 64 + 32 * half, v);
         if (has) {
             const int g = d.off[tower ? T_VF_FC1_W : T_PI_FC1_W];
 #pragma unroll
@@ -885,7 +966,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         }
         if (half == 0) {
             // dW0'^T[j][k]: k < O -> W0[k][j], k == O -> b0[j]
-            tmem_ld32_sum(tlane + ACC_DW0, tlane + ACC_DW0_C, v);
+            tmem_ld32_sum(tlane + ACC_DW0, tlane + ACC_DW0 + 64, v);
             if (has) {
                 const int g = d.off[tower ? T_VF_FC0_W : T_PI_FC0_W], gb = d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
 #pragma unroll
@@ -895,28 +976,37 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 }
             }
         } else {
-            float b[8];
-            tmem_ld8_sum(tlane + ACC_DB1, tlane + ACC_DB1_C, b);
-            if (has) put(d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + r64, b[0] * un_w1);
             if (tower == 0) {
                 // dWpi[k][j]
-                tmem_ld32_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, v);
+                tmem_ld32_sum(tlane + ACC_DWP, tlane + ACC_DWP + 64, v);
                 if (has) {
                     const int g = d.off[T_PI_W] + r64 * A;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < A) put(g + j, v[j] * un_hd);
                 }
-                // column sums: rows < A -> dbpi, rows 32 .. 32 + A -> dlogstd
-                tmem_ld8_sum(tlane + ACC_CS, tlane + ACC_CS_C, b);
-                if (has) {
-                    if (r64 < A) put(d.off[T_PI_B] + r64, b[0] * un_hd);
-                    // d(-ent_coef*entropy)/dlogstd_j = -ent_coef, once (a.ent_coef is pre-divided by the number of ranks)
-                    if (r64 >= 32 && r64 < 32 + A) put(d.off[T_LOGSTD] + r64 - 32, b[0] * un_hd - (blockIdx.x == 0 ? a.ent_coef : 0.f));
-                }
             } else {
-                tmem_ld8_sum(tlane + ACC_DWP, tlane + ACC_DWP_C, b);
-                if (has) put(d.off[T_VF_W] + r64, b[0] * un_hd);
+                uint32_t r2[8];
+                PPO_TMEM_LD8(tlane + ACC_DWP, r8);      // x dv_hi
+                PPO_TMEM_LD8(tlane + ACC_DWP + 8, r2);  // x dv_lo, + H2_lo x dv_hi
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (has) put(d.off[T_VF_W] + r64, (__uint_as_float(r8[0]) + __uint_as_float(r2[0])) * un_hd);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this column half: the lo sums are parked
+            if (q < 2) {  // hi parts: row 32 q + lane
+                const int rr = q * 32 + lane;
+                PPO_TMEM_LD8(tlane + ACC_DB1, r8);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                put(d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + rr, (__uint_as_float(r8[0]) + S4[rr]) * un_w1);
+                if (tower == 0) {
+                    // column sums of [dMU | dLS]: rows < A -> dbpi, rows 32 .. 32 + A -> dlogstd
+                    PPO_TMEM_LD8(tlane + ACC_CS, r8);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float cs = (__uint_as_float(r8[0]) + S4[64 + rr]) * un_hd;
+                    if (rr < A) put(d.off[T_PI_B] + rr, cs);
+                    // d(-ent_coef*entropy)/dlogstd_j = -ent_coef, once (a.ent_coef is pre-divided by the number of ranks)
+                    if (rr >= 32 && rr < 32 + A) put(d.off[T_LOGSTD] + rr - 32, cs - (blockIdx.x == 0 ? a.ent_coef : 0.f));
+                }
             }
         }
     }
