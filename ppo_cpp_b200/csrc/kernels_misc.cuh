@@ -907,8 +907,9 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
         if (prof && threadIdx.x == 0 && pi < 8) prof[pi++] = clock64(); \
     } while (0)
     RA_PROF();
-    float gsum[RA_MAXJ];
+    float gsum[1];
     double q = 0.0;
+    static_assert(RA_MAXJ == 4, "one 64-thread group per chunk of a block");
     // phase 1: thread (column quad cq of the chunk, slab group sg) loads slabs sg, sg + 16, ... as float4 (rows are 16-byte
     // aligned: PS % 4 == 0); every load of this thread (all its chunks, 4 slabs at a time) is independent of the others
     const int cq = threadIdx.x & 15, sg = threadIdx.x >> 4;
@@ -949,69 +950,52 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
         for (int j = 0; j < RA_MAXJ; ++j) *reinterpret_cast<float4*>(&part[j][threadIdx.x >> 5][4 * cq]) = acc4[j];
     }
     __syncthreads();
+    // From here on thread group rg (64 threads, one per column) owns chunk blk + rg * nblk (RA_MAXJ groups = RA_MAXJ chunks): the
+    // groups combine, exchange and update their chunks side by side instead of group 0 walking through all of them.
+    const int mychunk = blk + rg * nblk;
+    const int c = mychunk * 64 + lane_c;
+    const bool have = mychunk < nchunks;  // uniform per group
+    float gs = 0.f;
+    {
+        float t4[8];
 #pragma unroll
-    for (int j = 0; j < RA_MAXJ; ++j) {
-        gsum[j] = 0.f;
-        const int chunk = blk + j * nblk;
-        if (chunk >= nchunks) break;  // block-uniform
-        const int c = chunk * 64 + lane_c;
-        if (rg == 0) {
-            const double t = (((double)part[j][0][lane_c] + (double)part[j][1][lane_c]) + ((double)part[j][2][lane_c] + (double)part[j][3][lane_c])) +
-                             (((double)part[j][4][lane_c] + (double)part[j][5][lane_c]) + ((double)part[j][6][lane_c] + (double)part[j][7][lane_c]));
-            gsum[j] = (float)t;
-            if (world > 1 && c < r.PS) {  // LL store of (value, seq) into every rank's slot of this rank
-                for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gsum[j]), seq);
-            }
-        }
+        for (int w = 0; w < 8; ++w) t4[w] = part[rg][w][lane_c];
+        const double t = (((double)t4[0] + (double)t4[1]) + ((double)t4[2] + (double)t4[3])) + (((double)t4[4] + (double)t4[5]) + ((double)t4[6] + (double)t4[7]));
+        if (have) gs = (float)t;
     }
-    if (world > 1 && rg == 0) {
-        // allreduce: add the `world` values of every column in rank order (the same order on every rank)
+    if (world > 1 && have && c < r.PS) {
+        // LL store of (value, seq) into every rank's slot of this rank, then the `world` values of the column added in rank order
+        // (the same order on every rank; four ranks' values in flight together)
+        for (int dst = 0; dst < world; ++dst) ll_store(r.mbox.ll_slot(dst, seq, r.mbox.rank) + c, __float_as_uint(gs), seq);
+        float t = 0.f;
+        for (int s0 = 0; s0 < world; s0 += 4) {
+            unsigned w[4];
+            r.mbox.ll_wait4(seq, (size_t)c, s0, w);
 #pragma unroll
-        for (int j = 0; j < RA_MAXJ; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < r.PS) {
-                float t = 0.f;
-                for (int s0 = 0; s0 < world; s0 += 4) {  // four ranks' values of this column in flight together, added in rank order
-                    unsigned w[4];
-                    r.mbox.ll_wait4(seq, (size_t)c, s0, w);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (s0 + k < world) t += __uint_as_float(w[k]);
-                }
-                gsum[j] = t;
-            }
+            for (int k = 0; k < 4; ++k)
+                if (s0 + k < world) t += __uint_as_float(w[k]);
         }
+        gs = t;
     }
-    if (rg == 0) {
-#pragma unroll
-        for (int j = 0; j < RA_MAXJ; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < r.PS) r.grad[c] = gsum[j];
-            if (c < a.P) q += (double)gsum[j] * (double)gsum[j];
-        }
+    if (have) {
+        if (c < r.PS) r.grad[c] = gs;
+        if (c < a.P) q += (double)gs * (double)gs;
     }
+    gsum[0] = gs;
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
     __syncthreads();
-    if (threadIdx.x == 0) r.sq_partial[blk] = red[0] + red[1];  // warps 0,1 hold rg == 0
-    // Adam state of this thread's columns: only this thread ever touches it, so it can be fetched ahead of the barrier
-    float am[RA_MAXJ], av[RA_MAXJ], ap[RA_MAXJ];
-#pragma unroll
-    for (int j = 0; j < RA_MAXJ; ++j) {
-        const int c = (blk + j * nblk) * 64 + lane_c;
-        const bool mine = rg == 0 && c < a.P;
-        am[j] = mine ? __ldcg(a.m + c) : 0.f;
-        av[j] = mine ? __ldcg(a.v + c) : 0.f;
-        ap[j] = mine ? __ldcg(a.params + c) : 0.f;
-    }
+    const double q_blk = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    if (threadIdx.x == 0) r.sq_partial[blk] = q_blk;
+    // Adam state of this thread's column: only this thread ever touches it, so it can be fetched ahead of the exchange
+    const bool mine = have && c < a.P;
+    float am = mine ? __ldcg(a.m + c) : 0.f;
+    float av = mine ? __ldcg(a.v + c) : 0.f;
+    const float ap = mine ? __ldcg(a.params + c) : 0.f;
     RA_PROF();
     const bool ll = r.sq_ll != nullptr;  // (nblk <= 256)
     if (ll) {
-        const unsigned long long qb = (unsigned long long)__double_as_longlong(red[0] + red[1]);
+        const unsigned long long qb = (unsigned long long)__double_as_longlong(q_blk);
         uint4* const base = r.sq_ll + (size_t)(sqseq & 1u) * nblk * nblk;
         for (int dst = threadIdx.x; dst < nblk; dst += blockDim.x) {
             uint4* p = base + (size_t)dst * nblk + blk;
@@ -1069,23 +1053,14 @@ __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int 
         loss_row[3] = 0.5f * (L[L_KL] * a.invB);
         loss_row[4] = L[L_CLIP] * a.invB;
     }
-    if (rg == 0) {
+    if (mine) {
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
-#pragma unroll
-        for (int j = 0; j < RA_MAXJ; ++j) {
-            const int chunk = blk + j * nblk;
-            if (chunk >= nchunks) break;
-            const int c = chunk * 64 + lane_c;
-            if (c < a.P) {
-                const float g = __fmul_rn(gsum[j], s_scale);
-                float m = am[j], v = av[j];
-                m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, a.beta1)));
-                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.0f, a.beta2)));
-                a.m[c] = m;
-                a.v[c] = v;
-                a.params[c] = __fsub_rn(ap[j], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), a.eps)));
-            }
-        }
+        const float g = __fmul_rn(gsum[0], s_scale);
+        am = __fadd_rn(am, __fmul_rn(__fsub_rn(g, am), __fsub_rn(1.0f, a.beta1)));
+        av = __fadd_rn(av, __fmul_rn(__fsub_rn(__fmul_rn(g, g), av), __fsub_rn(1.0f, a.beta2)));
+        a.m[c] = am;
+        a.v[c] = av;
+        a.params[c] = __fsub_rn(ap, __fdiv_rn(__fmul_rn(am, alpha), __fadd_rn(__fsqrt_rn(av), a.eps)));
     }
     RA_PROF();
 #undef RA_PROF

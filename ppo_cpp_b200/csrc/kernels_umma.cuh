@@ -927,6 +927,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     }
     UMMA_TL(2);  // tiles done
     // ---------------------------------------------------------------- flush the weight gradients of this CTA
+    // (Gathering the entries in shared memory in slab order and storing them as float4 from 32 lanes instead of 4-byte stores from the
+    // 16 lanes that hold an accumulator row was measured: 3.4 k -> 4.0 k cycles; the accumulator reads and the un-scaling are the cost.)
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
     auto put = [&](int col, float val) { my[col] = val; };
     // M = 64 accumulators: row r of D sits in TMEM lane 32 * (r >> 4) + (r & 15); the column sums (M = 128: row r in lane r) have their
