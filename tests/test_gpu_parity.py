@@ -584,10 +584,13 @@ def test_train_minibatch_one_adam_step(core_mod, init_weights, kat):
     c.close()
 
 
-@pytest.mark.parametrize("h1,h2,n_envs,n_steps,nmb,epochs", [(4, 5, 2, 64, 4, 3), (4, 5, 1, 2048, 32, 2), (64, 64, 16, 32, 8, 2)])
+@pytest.mark.parametrize("h1,h2,n_envs,n_steps,nmb,epochs", [(4, 5, 2, 64, 4, 3), (4, 5, 1, 2048, 32, 2), (64, 64, 16, 32, 8, 2),
+                                                              (64, 64, 1024, 16, 2, 2), (256, 256, 128, 32, 1, 1), (64, 64, 4096, 64, 32, 1)])
 def test_train_update_vs_oracle_learner(core_mod, kat, init_weights, h1, h2, n_envs, n_steps, nmb, epochs):
     """Whole update (epochs x minibatches, compounded glibc shuffles, scatter semantics) vs the oracle's
-    reference-structured learner on the SAME rollout."""
+    reference-structured learner on the SAME rollout.  The last two cases run the shapes of the benchmark: minibatches of 8192
+    samples = 64 tiles x 2 towers on the persistent tcgen05 epoch kernel (C3's minibatch), and a 4096-sample minibatch step of
+    the [256,256] layer-wise tcgen05 path (C4's net); the last one is C3 itself (262 144 transitions, 32 minibatches), one epoch."""
     rng = np.random.default_rng(3)
     flat = init_weights[1] if (h1, h2) == (4, 5) else rand_params(rng, h1, h2)
     nb = n_envs * n_steps
@@ -608,8 +611,12 @@ def test_train_update_vs_oracle_learner(core_mod, kat, init_weights, h1, h2, n_e
     got = c.get_tensor("params")
     # after epochs*nmb Adam steps of size ~lr the trajectories must still agree to a small fraction of the total movement
     moved = np.abs(p1[:o.P] - flat[:o.P]).max()
-    assert np.abs(got[:o.P] - p1[:o.P]).max() < 2e-3 * moved
-    assert np.allclose(losses, want, rtol=1e-4, atol=1e-6)
+    print(f"whole update [{h1},{h2}] {n_envs}x{n_steps}: param diff / moved = {np.abs(got[:o.P] - p1[:o.P]).max() / moved:.3e}, "
+          f"loss rel diff = {np.abs(losses - want).max() / np.abs(want).max():.3e}")
+    # (measured: <= 1.6e-4 of the movement over up to 16 Adam steps — about one ulp of a weight per step — and 9.6e-4 after the 32
+    # steps of a C3 epoch: early Adam steps are ~lr * sign(g), which amplifies rounding differences of small gradient entries)
+    assert np.abs(got[:o.P] - p1[:o.P]).max() < max(5e-4, 4e-5 * epochs * nmb) * moved
+    assert np.allclose(losses, want, rtol=2e-6, atol=1e-6), (losses, want)
     lib.oracle_learner_destroy(L)
     c.close()
 
