@@ -68,6 +68,9 @@ struct RolloutArgs {
     } while (0)
 
 constexpr int R_TM = 32, R_NTH = 256;
+constexpr int R_SOLO_CHUNK = 32;  // env steps whose noise is drawn ahead in the single-env path
+// shared memory of the single-env path behind RLayout: [2 buffers][2 kinds][R_SOLO_CHUNK][4 * ceil(D / 4)] floats
+__host__ __device__ inline size_t rollout_solo_noise_bytes(int D) { return (size_t)2 * 2 * R_SOLO_CHUNK * 4 * ((D + 3) / 4) * sizeof(float) + 16; }
 constexpr unsigned PPO_HOST_ENV_ABORT = 0xffffffffu;
 
 // rank r's copy of THIS rank's slab of a train-input buffer (row t = 0), or the local slab on a single GPU
@@ -178,6 +181,229 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
     const uint2 ekey = make_uint2((uint32_t)a.env.seed, (uint32_t)(a.env.seed >> 32));
 
     int prof_i = 0;
+    // ---------------------------------------------------------------------------------------------------- one env
+    // The reference's own shape (C1: a single env, 2048 steps) is ONE chain of tiny dependent operations per env step; with the
+    // tile machinery above (256 threads, a __syncthreads behind every stage, Philox + Box-Muller twice per step on five threads)
+    // it took 15 k cycles per step.  Here warp 0 walks the chain alone (thread per output unit, __syncwarp between the stages,
+    // the same fp32 operations in the same order as f_fwd / the tile code: bit-identical results) and the other seven warps
+    // draw the Gaussian noise of the NEXT 32 env steps meanwhile (it depends on the counters only).
+    const bool solo_env = a.n == 1 && gridDim.x == 1 && world == 1;
+    if (solo_env) {
+        constexpr int CH = R_SOLO_CHUNK;
+        const int NB = 4 * nblk;                                   // noise values per step and kind
+        float* NZ = smem + ((L.total_bytes + 15) / 16) * 4;        // [2 buffers][2 kinds][CH][NB] behind the tile layout
+        const uint32_t gid = a.env.env_id0;
+        const uint32_t te0 = TENV[0];
+        auto draw_chunk = [&](int c) {  // warps 1..7: noise of steps [c * CH, (c + 1) * CH)
+            float* dst = NZ + (size_t)(c & 1) * 2 * CH * NB;
+            const int per_kind = CH * nblk, total = host_env ? per_kind : 2 * per_kind;
+            for (int e = tid - 32; e < total; e += NTH - 32) {
+                const int kind = e / per_kind, r = e - kind * per_kind, s = r / nblk, blk = r - s * nblk, t = c * CH + s;
+                if (t >= a.T) continue;
+                float x4[4];
+                if (kind == 0) normal4(a.seed, a.env_id0, step0 + (uint32_t)t, (uint32_t)blk, PPO_TAG_ACTION, x4);
+                else normal4(a.env.seed, gid, te0 + (uint32_t)t, (uint32_t)blk, PPO_TAG_ENVNOISE, x4);
+                float* o = dst + ((size_t)kind * CH + s) * NB + blk * 4;
+                o[0] = x4[0]; o[1] = x4[1]; o[2] = x4[2]; o[3] = x4[3];
+            }
+        };
+        if (warp > 0) draw_chunk(0);
+        __syncthreads();
+        // constants of the rollout (the generic loop recomputes them per step with the same operations)
+        float sl_c = 0.f;  // sum of logstd in action order (GRAPH:6103-6672)
+        for (int j = 0; j < A; ++j) sl_c = __fadd_rn(sl_c, logstd[j]);
+        const int nH1 = d.H1, nH2 = d.H2;
+        const float *W0p = sW + d.off[T_PI_FC0_W], *W0v = sW + d.off[T_VF_FC0_W], *B0p = sW + d.off[T_PI_FC0_B], *B0v = sW + d.off[T_VF_FC0_B];
+        const float *W1p = sW + d.off[T_PI_FC1_W], *W1v = sW + d.off[T_VF_FC1_W], *B1p = sW + d.off[T_PI_FC1_B], *B1v = sW + d.off[T_VF_FC1_B];
+        const float *WHp = sW + d.off[T_PI_W], *WHv = sW + d.off[T_VF_W];
+        float *H1p = smem + L.f.h1[0], *H1v = smem + L.f.h1[1], *H2p = smem + L.f.h2[0], *H2v = smem + L.f.h2[1];
+        // sigma_j of this lane's actions (the generic loop takes expf(logstd[j]) per step: the same value)
+        float sd_l[2];
+        sd_l[0] = lane < A ? expf(logstd[lane]) : 1.f;
+        sd_l[1] = lane + 32 < A ? expf(logstd[lane + 32]) : 1.f;
+        for (int c = 0; c * CH < a.T; ++c) {
+            if (warp > 0) {
+                draw_chunk(c + 1);
+            } else {
+                const float* na = NZ + (size_t)(c & 1) * 2 * CH * NB;
+                const float* ne = na + (size_t)CH * NB;
+                for (int s = 0; s < CH && c * CH + s < a.T; ++s) {
+                    const int t = c * CH + s;
+                    R_PROF();  // step start
+                    // -- store the observation the policy acts on (runner.hpp:75-78)
+                    for (int k = lane; k < O; k += 32) a.obs_store[(size_t)t * O + k] = OBS[k * TM];
+                    // -- MlpPolicy::step, both towers: lane per output unit, k ascending as f_fwd
+                    for (int o = lane; o < 2 * nH1; o += 32) {
+                        const bool vt = o >= nH1;
+                        const int n = vt ? o - nH1 : o;
+                        const float* w = (vt ? W0v : W0p) + n;
+                        float acc = 0.f;
+#pragma unroll 6
+                        for (int k = 0; k < O; ++k) acc = fmaf(w[k * nH1], OBS[k * TM], acc);
+                        (vt ? H1v : H1p)[n * TM] = tanhf(acc + (vt ? B0v : B0p)[n]);
+                    }
+                    __syncwarp();
+                    for (int o = lane; o < 2 * nH2; o += 32) {
+                        const bool vt = o >= nH2;
+                        const int n = vt ? o - nH2 : o;
+                        const float* w = (vt ? W1v : W1p) + n;
+                        const float* hin = vt ? H1v : H1p;
+                        float acc = 0.f;
+#pragma unroll 4
+                        for (int k = 0; k < nH1; ++k) acc = fmaf(w[k * nH2], hin[k * TM], acc);
+                        (vt ? H2v : H2p)[n * TM] = tanhf(acc + (vt ? B1v : B1p)[n]);
+                    }
+                    __syncwarp();
+                    for (int o = lane; o < A + 1; o += 32) {
+                        const bool vh = o == A;
+                        const int N = vh ? 1 : A, n = vh ? 0 : o;
+                        const float* w = (vh ? WHv : WHp) + n;
+                        const float* hin = vh ? H2v : H2p;
+                        float acc = 0.f;
+#pragma unroll 4
+                        for (int k = 0; k < nH2; ++k) acc = fmaf(w[k * N], hin[k * TM], acc);
+                        if (vh) Vs[0] = acc + sW[d.off[T_VF_B]];
+                        else MU[n * TM] = acc + sW[d.off[T_PI_B] + n];
+                    }
+                    __syncwarp();
+                    R_PROF();  // forward done
+                    // -- Gaussian sample (GRAPH:5894-6019)
+                    for (int j = lane, jj = 0; j < A; j += 32, ++jj) {
+                        const float sd = jj ? sd_l[1] : sd_l[0];  // (A <= 32 + 32; asserted by the host: obs_dim == act_dim <= 32)
+                        const float mu = MU[j * TM];
+                        const float act = __fadd_rn(mu, __fmul_rn(sd, na[s * NB + j]));
+                        const float z = __fdiv_rn(__fsub_rn(act, mu), sd);
+                        Ac[j * (TM + 1)] = act;
+                        Z2[j * TM] = __fmul_rn(z, z);
+                        a.act_store[(size_t)t * A + j] = act;
+                        if (host_env) a.h_actions[(size_t)t * a.h_act_stride + j] = act;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {  // neglogp (GRAPH:6103-6672): sequential sum in action order
+                        float ss = 0.f;
+                        for (int j = 0; j < A; ++j) ss = __fadd_rn(ss, Z2[j * TM]);
+                        a.nlp_store[t] = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, ss), __fmul_rn(PPO_HALF_LOG_2PI, (float)A)), sl_c);
+                        a.val_store[t] = Vs[0];
+                        a.dones_store[t] = DN[0];  // done flag of the previous env step (runner.hpp:110)
+                    }
+                    R_PROF();  // sample + stores issued
+                    if (host_env) {
+                        // -- actions to the host, the env's answer back (mapped pinned memory, one flag each way)
+                        __syncwarp();
+                        unsigned v = 0u;
+                        if (lane == 0) {
+                            __threadfence_system();
+                            st_release_sys(a.h_act_flag, (unsigned)t + 1u);
+                            const unsigned long long t0 = globaltimer_ns();
+                            unsigned spins = 0;
+                            while ((v = *reinterpret_cast<const volatile unsigned*>(a.h_obs_flag)) != (unsigned)t + 1u && v != PPO_HOST_ENV_ABORT) {
+                                if (((++spins) & 0xffu) == 0u && globaltimer_ns() - t0 > 120000000000ull) {  // 120 s: the host is gone
+                                    *a.host_err = 1u;
+                                    v = PPO_HOST_ENV_ABORT;
+                                    break;
+                                }
+                            }
+                            __threadfence_system();
+                        }
+                        v = __shfl_sync(0xffffffffu, v, 0);
+                        if (v == PPO_HOST_ENV_ABORT) {
+                            if (lane == 0) s_abort = 1;
+                            break;
+                        }
+                        for (int k = lane; k < D; k += 32) RAW[k] = __ldcv(a.h_obs + k);
+                        if (lane == 0) {
+                            REW[0] = __ldcv(a.h_rew);
+                            DONE[0] = __ldcv(a.h_done);
+                        }
+                        __syncwarp();
+                        if (lane == 0) RET[0] = __fadd_rn(__fmul_rn(RET[0], a.norm_gamma), REW[0]);  // env_normalize.hpp:71
+                    } else {
+                        // -- synthetic env step
+                        const uint32_t te = te0 + (uint32_t)t;
+                        const bool dn = ((te + 1u) % 334u) == 0u;
+                        for (int k = lane; k < D; k += 32) {
+                            const float sk = S[k];
+                            float ac = Ac[k * (TM + 1)];
+                            ac = ac < -1.f ? -1.f : (ac > 1.f ? 1.f : ac);
+                            float sn = __fadd_rn(__fadd_rn(__fmul_rn(0.9f, sk), __fmul_rn(0.1f, ac)), __fmul_rn(0.01f, ne[s * NB + k]));
+                            if (k == 0) REW[0] = __fsub_rn(sn, sk);
+                            if (dn) {
+                                const uint4 w = philox4x32_10(make_uint4(gid, RES[0], (uint32_t)(k >> 2), PPO_TAG_ENVRESET), ekey);
+                                const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+                                sn = __fmul_rn(0.1f, __fsub_rn(__fmul_rn(2.0f, u32_to_unit(wv[k & 3])), 1.0f));
+                            }
+                            S[k] = sn;
+                            RAW[k] = sn;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            DONE[0] = dn ? 1.f : 0.f;
+                            TENV[0] = te + 1u;
+                            if (dn) RES[0] += 1u;
+                            RET[0] = __fadd_rn(__fmul_rn(RET[0], a.norm_gamma), REW[0]);  // env_normalize.hpp:71
+                        }
+                    }
+                    __syncwarp();
+                    R_PROF();  // env step done
+                    // -- RunningStatistics::update with a batch of one row (fp64 around the running mean, as the tile code) + Chan merge
+                    if (merge && lane <= D) {
+                        const int cidx = lane;
+                        const bool is_ret = cidx == D;
+                        const double x = is_ret ? (double)RET[0] : (double)RAW[cidx] - (double)s_mean[cidx];
+                        double ps = 0.0, pq = 0.0;
+                        ps += x;
+                        pq += x * x;
+                        if (is_ret ? a.upd_ret : a.upd_obs) {
+                            const double rows = (double)a.n_global;  // = 1: x / 1.0 is x, the divisions can go
+                            const double pv = is_ret ? 0.0 : (double)s_mean[cidx];
+                            const double m1 = ps;
+                            const double mean_d = pv + m1;
+                            double var_d = pq - m1 * m1;
+                            if (var_d < 0.0) var_d = 0.0;
+                            float mm = s_mean[cidx], vv = s_var[cidx];
+                            chan_merge(mm, vv, s_cnt[is_ret ? 1 : 0], (float)mean_d, (float)var_d, rows);
+                            s_mean[cidx] = mm;
+                            s_var[cidx] = vv;
+                        }
+                    }
+                    __syncwarp();
+                    if (merge && lane == 0) {
+                        if (a.upd_obs) s_cnt[0] = (double)a.n_global + s_cnt[0];
+                        if (a.upd_ret) s_cnt[1] = (double)a.n_global + s_cnt[1];
+                    }
+                    R_PROF();  // merged
+                    if (lane <= D) s_inv[lane] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(s_var[lane], a.eps)));
+                    __syncwarp();
+                    // -- EnvNormalize::step post-processing (env_normalize.hpp:74-91)
+                    for (int k = lane; k < D; k += 32) {
+                        float x = RAW[k];
+                        if (a.norm_obs) {
+                            x = __fmul_rn(__fsub_rn(x, s_mean[k]), s_inv[k]);
+                            x = fminf(fmaxf(x, -a.clip_obs), a.clip_obs);
+                        }
+                        OBS[k * TM] = x;
+                    }
+                    if (lane == 0) {
+                        const float raw = REW[0];
+                        float r = raw;
+                        if (a.norm_reward) {
+                            r = __fmul_rn(raw, s_inv[D]);
+                            r = fminf(fmaxf(r, -a.clip_rew), a.clip_rew);
+                        }
+                        const float dn2 = DONE[0];
+                        RET[0] = __fmul_rn(RET[0], __fsub_rn(1.0f, dn2));
+                        DN[0] = dn2;
+                        a.rew_store[t] = r;
+                        a.urew_store[t] = raw;
+                    }
+                    __syncwarp();
+                    R_PROF();  // applied
+                }
+            }
+            __syncthreads();  // next chunk's noise drawn, this chunk's steps done
+            if (s_abort) break;
+        }
+    } else
     for (int t = 0; t < a.T; ++t) {
         const uint32_t step = step0 + (uint32_t)t;
         R_PROF();  // step start

@@ -696,6 +696,7 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                     // cannot put two CTAs on one SM (they would run at half speed and everybody waits at the step barrier)
                     size_t smem = (size_t)L.total_bytes;
                     if (grid <= c->sm_count) smem = std::max(smem, std::min(max_smem, (size_t)120 * 1024));
+                    if (desc->n_envs == 1) smem = std::max(smem, (size_t)L.total_bytes + rollout_solo_noise_bytes(c->d.O));  // single-env path: noise drawn ahead
                     if (cudaFuncSetAttribute(rollout_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem(rollout_persistent_kernel, max_smem)) != cudaSuccess) {
                         cudaGetLastError();
                         break;
