@@ -55,36 +55,28 @@ struct Dims {
     static constexpr int GROUPS = (P + 31) / 32;
 };
 
-template <int O, int A, int H1, int H2>
-__global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
-    using D = Dims<O, A, H1, H2>;
-    static_assert(O % 2 == 0 && A % 2 == 0, "rows are read as float2");
-    __shared__ __align__(16) float sW[(D::P + 3 + 4) & ~3];
-    __shared__ float s_part[NTH / 32][D::GROUPS * 32 + 4];
-    __shared__ __align__(16) float s_tile[NTH / 32][32 * TR_LD];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < D::P; i += NTH) sW[i] = __ldg(a.params + i);
-    __syncthreads();
-
-    float sd[A], isd[A];
-    float sum_ls = 0.f;
+// Per-thread accumulators of a CTA's share of a minibatch
+template <int GROUPS>
+struct SmallAcc {
+    float accg[GROUPS];
+    float l_pg, l_vf, l_kl, l_cf;
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int j = 0; j < A; ++j) {
-        const float ls = sW[D::LS + j];
-        sd[j] = expf(ls);
-        isd[j] = 1.f / sd[j];
-        sum_ls += ls;
+        for (int g = 0; g < GROUPS; ++g) accg[g] = 0.f;
+        l_pg = l_vf = l_kl = l_cf = 0.f;
     }
-    const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
-    float accg[D::GROUPS];
-#pragma unroll
-    for (int g = 0; g < D::GROUPS; ++g) accg[g] = 0.f;
-    float l_pg = 0.f, l_vf = 0.f, l_kl = 0.f, l_cf = 0.f;
+};
 
-    const int nwarp_tiles = (a.count + 31) / 32;
-    for (int wt = blockIdx.x * (NTH / 32) + warp; wt < nwarp_tiles; wt += gridDim.x * (NTH / 32)) {
-        const int slot = a.slot0 + wt * 32 + lane;
-        const bool valid = wt * 32 + lane < a.count;
+// One warp tile (32 samples, one per lane): forward, loss, backward; the per-parameter contributions summed over the warp into acc
+template <int O, int A, int H1, int H2>
+__device__ __forceinline__ void small_warp_tile(const TrainArgs& a, const float* __restrict__ sW, int slot, bool valid, const float2* mbstats,
+                                                const float (&sd)[A], const float (&isd)[A], float sum_ls, float lo, float hi,
+                                                SmallAcc<Dims<O, A, H1, H2>::GROUPS>& acc, float* tile, int lane) {
+    using D = Dims<O, A, H1, H2>;
+    float (&accg)[D::GROUPS] = acc.accg;
+    float &l_pg = acc.l_pg, &l_vf = acc.l_vf, &l_kl = acc.l_kl, &l_cf = acc.l_cf;
+    (void)sd;
+    {
         float x[O], act[A];
         float adv = 0.f, R = 0.f, oldn = 0.f, oldv = 0.f;
         {
@@ -110,7 +102,7 @@ __global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
                 if (a.adv_direct) {
                     adv = __ldg(a.adv_direct + slot);
                 } else {  // advs = (returns - values - mean) / (sqrt(var) + 1e-8)  (ppo2.hpp:401-406)
-                    const float2 st = __ldg(a.mbstats);
+                    const float2 st = __ldg(mbstats);
                     adv = __fdiv_rn(__fsub_rn(__fsub_rn(R, oldv), st.x), st.y);
                 }
             }
@@ -230,9 +222,43 @@ __global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
                 else if (idx < D::P) val = dls[idx - D::LS];
                 c[i] = val;
             }
-            accg[g] += transpose_reduce32(c, s_tile[warp], lane);
+            accg[g] += transpose_reduce32(c, tile, lane);
         }
     }
+}
+
+template <int O, int A, int H1, int H2>
+__global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
+    using D = Dims<O, A, H1, H2>;
+    static_assert(O % 2 == 0 && A % 2 == 0, "rows are read as float2");
+    __shared__ __align__(16) float sW[(D::P + 3 + 4) & ~3];
+    __shared__ float s_part[NTH / 32][D::GROUPS * 32 + 4];
+    __shared__ __align__(16) float s_tile[NTH / 32][32 * TR_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < D::P; i += NTH) sW[i] = __ldg(a.params + i);
+    __syncthreads();
+
+    float sd[A], isd[A];
+    float sum_ls = 0.f;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        const float ls = sW[D::LS + j];
+        sd[j] = expf(ls);
+        isd[j] = 1.f / sd[j];
+        sum_ls += ls;
+    }
+    const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+    SmallAcc<D::GROUPS> acc;
+    acc.clear();
+
+    const int nwarp_tiles = (a.count + 31) / 32;
+    for (int wt = blockIdx.x * (NTH / 32) + warp; wt < nwarp_tiles; wt += gridDim.x * (NTH / 32)) {
+        const int slot = a.slot0 + wt * 32 + lane;
+        const bool valid = wt * 32 + lane < a.count;
+        small_warp_tile<O, A, H1, H2>(a, sW, slot, valid, a.mbstats, sd, isd, sum_ls, lo, hi, acc, s_tile[warp], lane);
+    }
+    float (&accg)[D::GROUPS] = acc.accg;
+    const float l_pg = acc.l_pg, l_vf = acc.l_vf, l_kl = acc.l_kl, l_cf = acc.l_cf;
 
     // ---- CTA combine (fixed order over the warps) -> slab
     float* my = a.partial + (size_t)blockIdx.x * a.PS;
@@ -265,6 +291,137 @@ __global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
             for (int j = 0; j < A; ++j) ent += sW[D::LS + j] + PPO_HALF_LOG_2PIE;  // GRAPH:10021-10180
         Lp[L_ENT] = ent;
         Lp[5] = 0.f; Lp[6] = 0.f; Lp[7] = 0.f;
+    }
+}
+
+// Epoch kernel of the S family for minibatches that ONE CTA handles (the reference's own C1 shape: 2048 transitions in 32
+// minibatches of 64): all minibatches of an epoch in one launch of one CTA — parameters and Adam moments live in shared memory,
+// per minibatch: warp tiles -> fixed-order combine of the warps -> sum of squares -> clip -> TF ApplyAdam in place -> next
+// minibatch.  No grid barrier, no slab, no second kernel: a launch pair per minibatch (train_small_kernel + cooperative
+// reduce / Adam) cost 12 us per step, 3.9 of C1's 9.4 ms per update.  Single GPU only (there is no exchange in here).
+struct SmallEpochArgs {
+    int M, B;                // minibatches of this launch, slots per minibatch
+    const float2* mbstats;   // [M]
+    float* loss_rows;        // [M][5]
+    AdamArgs adam;           // canonical params / m / v, lr, betas, eps, clip_norm, beta powers in / out, invB, gnorm_out
+};
+template <int O, int A, int H1, int H2>
+__global__ void __launch_bounds__(NTH) train_small_epoch_kernel(const TrainArgs a, const SmallEpochArgs ep) {
+    using D = Dims<O, A, H1, H2>;
+    constexpr int PP = (D::P + 3 + 4) & ~3;
+    __shared__ __align__(16) float sW[PP];
+    __shared__ float sM[PP], sV[PP];
+    __shared__ float s_part[NTH / 32][D::GROUPS * 32 + 4];
+    __shared__ __align__(16) float s_tile[NTH / 32][32 * TR_LD];
+    __shared__ double s_q[NTH / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const AdamArgs& ad = ep.adam;
+    for (int i = tid; i < D::P; i += NTH) {
+        sW[i] = __ldcg(ad.params + i);
+        sM[i] = __ldcg(ad.m + i);
+        sV[i] = __ldcg(ad.v + i);
+    }
+    float b1p = ad.bpow_in[0], b2p = ad.bpow_in[1];
+    const float lo = 1.f - a.cliprange, hi = 1.f + a.cliprange;
+    const int nwarp_tiles = (a.count + 31) / 32;
+    __syncthreads();
+    for (int mb = 0; mb < ep.M; ++mb) {
+        float sd[A], isd[A];
+        float sum_ls = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const float ls = sW[D::LS + j];
+            sd[j] = expf(ls);
+            isd[j] = 1.f / sd[j];
+            sum_ls += ls;
+        }
+        SmallAcc<D::GROUPS> acc;
+        acc.clear();
+        for (int wt = warp; wt < nwarp_tiles; wt += NTH / 32) {
+            const int slot = mb * ep.B + a.slot0 + wt * 32 + lane;
+            const bool valid = wt * 32 + lane < a.count;
+            small_warp_tile<O, A, H1, H2>(a, sW, slot, valid, ep.mbstats + mb, sd, isd, sum_ls, lo, hi, acc, s_tile[warp], lane);
+        }
+        // ---- combine the warps in a fixed order (as train_small_kernel), gradient of parameter i in thread i % NTH
+#pragma unroll
+        for (int g = 0; g < D::GROUPS; ++g) s_part[warp][32 * g + lane] = acc.accg[g];
+        float v4[4] = {acc.l_pg, acc.l_vf, acc.l_kl, acc.l_cf};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v4[q] = warp_sum(v4[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_part[warp][D::GROUPS * 32 + q] = v4[q];
+        }
+        __syncthreads();
+        constexpr int PT = (D::P + NTH - 1) / NTH;
+        float g[PT];
+        double q = 0.0;
+#pragma unroll
+        for (int u = 0; u < PT; ++u) {
+            const int i = tid + u * NTH;
+            float sum = 0.f;
+            if (i < D::P) {
+#pragma unroll
+                for (int w = 0; w < NTH / 32; ++w) sum += s_part[w][i];
+                if (i >= D::LS) sum -= a.ent_coef;  // d(-ent_coef*entropy)/dlogstd_j = -ent_coef
+                q += (double)sum * (double)sum;
+            }
+            g[u] = sum;
+        }
+        q = warp_sum(q);
+        if (lane == 0) s_q[warp] = q;
+        float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+        if (tid == 0) {
+            for (int w = 0; w < NTH / 32; ++w)
+                for (int k = 0; k < 4; ++k) lsum[k] += s_part[w][D::GROUPS * 32 + k];
+        }
+        __syncthreads();  // s_q complete; s_part and sW have been read
+        double ss = 0.0;
+#pragma unroll
+        for (int w = 0; w < NTH / 32; ++w) ss += s_q[w];
+        const float gnorm = (float)sqrt(ss);
+        const float inv = __fdiv_rn(1.0f, gnorm), invc = __fdiv_rn(1.0f, ad.clip_norm);
+        float scale = __fmul_rn(ad.clip_norm, fminf(inv, invc));
+        if (!isfinite(gnorm)) scale = __int_as_float(0x7fc00000);  // GRAPH:24493-24543
+        if (tid == 0) {
+            float ent = 0.f;
+            for (int j = 0; j < A; ++j) ent += sW[D::LS + j] + PPO_HALF_LOG_2PIE;  // GRAPH:10021-10180 (the parameters before this step)
+            float* lr_out = ep.loss_rows + (size_t)mb * 5;
+            lr_out[0] = lsum[0] * ad.invB;
+            lr_out[1] = 0.5f * (lsum[1] * ad.invB);
+            lr_out[2] = ent * ad.inv_world;
+            lr_out[3] = 0.5f * (lsum[2] * ad.invB);
+            lr_out[4] = lsum[3] * ad.invB;
+            *ad.gnorm_out = gnorm;
+        }
+        __syncthreads();  // thread 0 has read logstd before it moves
+        // ---- TF ApplyAdam (epsilon outside the sqrt), in place in shared memory
+        const float alpha = __fdiv_rn(__fmul_rn(ad.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+#pragma unroll
+        for (int u = 0; u < PT; ++u) {
+            const int i = tid + u * NTH;
+            if (i < D::P) {
+                const float gs = __fmul_rn(g[u], scale);
+                float m = sM[i], v = sV[i];
+                m = __fadd_rn(m, __fmul_rn(__fsub_rn(gs, m), __fsub_rn(1.0f, ad.beta1)));
+                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(gs, gs), v), __fsub_rn(1.0f, ad.beta2)));
+                sM[i] = m;
+                sV[i] = v;
+                sW[i] = __fsub_rn(sW[i], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), ad.eps)));
+            }
+        }
+        b1p = __fmul_rn(b1p, ad.beta1);
+        b2p = __fmul_rn(b2p, ad.beta2);
+        __syncthreads();  // the new parameters are in place
+    }
+    for (int i = tid; i < D::P; i += NTH) {
+        ad.params[i] = sW[i];
+        ad.m[i] = sM[i];
+        ad.v[i] = sV[i];
+    }
+    if (tid == 0) {
+        ad.bpow_out[0] = b1p;
+        ad.bpow_out[1] = b2p;
     }
 }
 

@@ -152,6 +152,7 @@ struct ppo_core {
     };
     std::vector<EpochGraph> graphs;
     EpochGraph rollout_graph;  // the whole synthetic-env rollout (n_steps x 4 kernels + bootstrap + GAE)
+    bool small_epoch = false;         // S family, minibatches of one CTA (C1): all minibatches of an epoch in one single-CTA launch
     bool persistent_epoch = false;    // U family: all minibatches of an epoch in one cooperative launch
     int epoch_grid = 0;
     uint4* sq_ll = nullptr;           // sum-of-squares partials of the gradient step as LL words, [parity][block][block] (or NULL: grid barrier)
@@ -681,6 +682,8 @@ extern "C" int ppo_core_create(const ppo_core_desc* desc, ppo_core** out) {
                     c->sq_ll_blocks = nb;
                 }
             }
+            // S family with minibatches of at most 512 samples on one GPU: one single-CTA launch per epoch
+            c->small_epoch = c->small && desc->world_size == 1 && nbg / desc->nminibatches <= 512 && getenv("PPO_DISABLE_PERSISTENT") == nullptr;
             c->use_graph = getenv("PPO_DISABLE_GRAPH") == nullptr;  // multi-GPU: only on the fast path (no NCCL inside a graph)
             c->graphs.resize(std::max(1, desc->noptepochs));
             // R family: one CTA per tile of R_TM envs (x tpc tiles) for the whole rollout; needs the parameter vector in
@@ -2053,6 +2056,7 @@ static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int 
 // (kernels_shuffle.cuh), then the epochs back to back.  Nothing here waits for the host.
 static int train_step_device(ppo_core* c, int k, float lr, float cliprange, int loss_row);
 static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e);
+static int train_epoch_small(ppo_core* c, float lr, float cliprange, int e);
 // end of the sigma exchange: "my epochs are in your array" to every rank, then wait for every rank's (fenced flag protocol)
 __global__ void shuffle_exchange_kernel(PeerMailbox mbox, unsigned* seq_var) {
     if (threadIdx.x == 0) {
@@ -2113,6 +2117,7 @@ static int enqueue_epochs(ppo_core* c, float lr, float cliprange) {
         c->cur_gather = c->sh_gather + (size_t)e * n;
         c->cur_mbstats = c->sh_mbstats + (size_t)e * M;
         if (c->persistent_epoch && fast_path(c)) TRY(train_epoch_device(c, lr, cliprange, e));
+        else if (c->small_epoch) TRY(train_epoch_small(c, lr, cliprange, e));
         else
             for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
     }
@@ -2187,6 +2192,30 @@ static int drop_shuffle_prefetch(ppo_core* c, bool restore_window) {
 }
 
 // all minibatches of epoch e in one cooperative launch (U family, persistent): see kernels_umma.cuh
+// the same for the S family when one CTA handles a minibatch: see kernels_small.cuh
+static int train_epoch_small(ppo_core* c, float lr, float cliprange, int e) {
+    const int M = c->desc.nminibatches;
+    TrainArgs a{};
+    a.obs = c->buf[B_OBS]; a.act = c->buf[B_ACTIONS]; a.ret = c->buf[B_RETURNS]; a.val = c->buf[B_VALUES]; a.nlp = c->buf[B_NEGLOGP];
+    a.gather = c->cur_gather; a.mbstats = c->cur_mbstats; a.adv_direct = nullptr; a.slot0 = 0; a.count = c->B_global;
+    a.invB = 1.0f / (float)c->B_global; a.cliprange = cliprange;
+    a.d = c->d; a.params = c->params; a.ent_coef = c->desc.ent_coef; a.vf_coef = c->desc.vf_coef;
+    a.partial = c->partial; a.PS = c->PS; a.prof = nullptr;
+    small::SmallEpochArgs ep{};
+    ep.M = M; ep.B = c->B_global; ep.mbstats = c->cur_mbstats; ep.loss_rows = c->loss_rows + (size_t)e * M * 5;
+    AdamArgs& ad = ep.adam;
+    ad.params = c->params; ad.m = c->adam_m; ad.v = c->adam_v; ad.grad = c->grad; ad.sq_partial = c->sq_partial;
+    ad.nblk = 1; ad.P = c->d.P; ad.lr = lr; ad.beta1 = c->desc.adam_beta1; ad.beta2 = c->desc.adam_beta2;
+    ad.eps = c->desc.adam_epsilon; ad.clip_norm = c->desc.max_grad_norm;
+    ad.bpow_in = c->bpow + c->bpow_slot * 2; ad.bpow_out = c->bpow + (c->bpow_slot ^ 1) * 2;
+    ad.invB = a.invB; ad.inv_world = 1.0f;
+    ad.loss_row = nullptr; ad.gnorm_out = c->gnorm;
+    LAUNCH(c, (small::train_small_epoch_kernel<18, 18, 4, 5>), 1, small::NTH, 0, a, ep);
+    CU(cudaGetLastError());
+    c->bpow_slot ^= 1;
+    return PPO_OK;
+}
+
 static int train_epoch_device(ppo_core* c, float lr, float cliprange, int e) {
     const int W = c->desc.world_size, M = c->desc.nminibatches;
     const int per_rank = c->B_global / W;
@@ -2291,6 +2320,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
         if (!update_graph_ok(c)) {
             TRY(prepare_epoch(c, pinned));
             if (c->persistent_epoch && fast_path(c)) TRY(train_epoch_device(c, lr, cliprange, e));
+            else if (c->small_epoch) TRY(train_epoch_small(c, lr, cliprange, e));
             else
                 for (int k = 0; k < M; ++k) TRY(train_step_device(c, k, lr, cliprange, e * M + k));
             continue;
@@ -2307,6 +2337,7 @@ extern "C" int ppo_train_update(ppo_core* c, float lr, float cliprange, float* m
             CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             int st = prepare_epoch(c, pinned);
             if (st == PPO_OK && c->persistent_epoch && fast_path(c)) st = train_epoch_device(c, lr, cliprange, e);
+            else if (st == PPO_OK && c->small_epoch) st = train_epoch_small(c, lr, cliprange, e);
             else
                 for (int k = 0; k < M && st == PPO_OK; ++k) st = train_step_device(c, k, lr, cliprange, e * M + k);
             const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
@@ -2443,6 +2474,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     const std::string w(which);
     if (w == "train") {
         if (c->wide) return "wgemm_kernel (tcgen05.mma kind::f16, fp16x2 split operand images, layer-wise GEMMs with bulk-copy pipeline)";
+        if (c->small && c->small_epoch) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums; persistent: train_small_epoch_kernel, one single-CTA launch per epoch with combine + clip + Adam in shared memory)";
         if (c->small) return "train_small_kernel (thread per sample, fp32 FFMA in registers, warp-transpose gradient sums)";
         if (c->umma && c->persistent_epoch && fast_path(c))
             return "train_umma_kernel (tcgen05.mma kind::f16, fp16x2 split operands, fp32 TMEM accumulators; persistent: one cooperative launch per epoch, reduce + Adam inside)";

@@ -694,19 +694,22 @@ def test_rollout_persistent_equals_stepwise(core_mod, monkeypatch, h1, h2, n_env
     assert rel_err(a["stats"]["ret_var"], b["stats"]["ret_var"]) < 1e-5
 
 
-@pytest.mark.parametrize("n_envs,n_steps,nmb", [(256, 32, 2), (4096, 16, 8), (1000, 8, 2)])
-def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, n_envs, n_steps, nmb):
+@pytest.mark.parametrize("h,n_envs,n_steps,nmb", [(64, 256, 32, 2), (64, 4096, 16, 8), (64, 1000, 8, 2), (4, 1, 2048, 32), (4, 8, 64, 4), (4, 3, 50, 1)])
+def test_epoch_persistent_equals_stepwise(core_mod, monkeypatch, h, n_envs, n_steps, nmb):
     """[64,64]: the persistent epoch kernel (all minibatches of an epoch in one cooperative launch: tcgen05 tiles, column
     reduce over distributed shared memory + LL hand-overs, global norm, Adam inside thread-block clusters) against the
     launch-per-minibatch path over two updates.  Same arithmetic; the order of the cross-CTA gradient sums and of the
-    sum-of-squares partials differs, so single parameters may differ by an ulp of their own magnitude."""
+    sum-of-squares partials differs, so single parameters may differ by an ulp of their own magnitude.
+    h = 4: the reference's [4,5] net with minibatches that one CTA handles (C1): the single-CTA epoch kernel of the S family
+    (combine, clip and Adam in shared memory) against train_small_kernel + the cooperative reduce / Adam kernel per minibatch."""
     rng = np.random.default_rng(8)
-    p = rand_params(rng, 64, 64)
+    h1, h2 = (64, 64) if h == 64 else (4, 5)
+    p = rand_params(rng, h1, h2)
     res = []
     for env in (None, "PPO_DISABLE_PERSISTENT"):
         if env:
             monkeypatch.setenv(env, "1")
-        c = make_core(core_mod, p, hidden1=64, hidden2=64, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=3, seed=21)
+        c = make_core(core_mod, p, hidden1=h1, hidden2=h2, n_envs=n_envs, n_steps=n_steps, nminibatches=nmb, noptepochs=3, seed=21)
         assert ("persistent" in c.kernel_family("train")) == (env is None)
         c.shuffle_seed(7)
         c.synth_env_reset()
