@@ -157,12 +157,17 @@ int ppo_runner_finish(ppo_core *core);
 /* The same protocol as ONE call (the loop of Runner::run, ppo2/runner.hpp:75-129, in C): per env step the actions are
  * copied to `actions` (host, [n_envs][A]), `step` advances the host env and hands back pointers to its raw
  * observation / reward / done arrays (host, valid until the next call), which are copied to the device and
- * normalised; then bootstrap value + GAE.  `step` returns 0 to continue, anything else aborts the rollout. */
+ * normalised; then bootstrap value + GAE.  `step` returns 0 to continue, anything else aborts the rollout.
+ * On one GPU the rollout runs as ONE persistent kernel that trades actions / observations with this loop once per env
+ * step (flags in mapped pinned memory; up to 512 envs the env's answer is read by the kernel from mapped memory, beyond
+ * that the observations go through the copy engine with a 4-byte flag copy behind them); `raw_obs` should be pinned
+ * memory for the copy-engine path to be asynchronous. */
 typedef int (*ppo_env_step_fn)(void *user, int t, const float *actions, const float **raw_obs, const float **raw_rew,
                                const float **done);
 int ppo_runner_rollout_host(ppo_core *core, ppo_env_step_fn step, void *user, float *actions);
 /* ... with a recorded trajectory as the env: raw_obs [n_steps][n_envs][O], raw_rew / done [n_steps][n_envs] (host);
- * actions_out [n_steps][n_envs][A] (host) receives the actions the policy took, or NULL */
+ * actions_out [n_steps][n_envs][A] (host) receives the actions the policy took, or NULL; when it is pinned memory the kernel
+ * stores the actions into it directly (PCIe writes), no staging copy */
 int ppo_runner_rollout_replay(ppo_core *core, const float *raw_obs, const float *raw_rew, const float *done,
                               float *actions_out);
 /* GPU-resident synthetic env: whole rollout on the device, no host round trips */
