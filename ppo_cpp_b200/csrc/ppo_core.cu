@@ -1489,9 +1489,11 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     r.h_obs = c->hx_dev + off_obs; r.h_rew = c->hx_dev + off_rew; r.h_done = c->hx_dev + off_done;
     r.h_act_flag = reinterpret_cast<unsigned*>(c->hx_dev) + off_actf;
     r.h_obs_flag = reinterpret_cast<const unsigned*>(c->hx_dev);
-    if (staged) {  // observations through the copy engine; rewards / dones (8 bytes per env) stay in mapped memory: two API calls per step
+    if (staged) {  // observations through the copy engine (ONE API call per step: the kernel recognises the landed sectors, see h_sentinel);
+                   // rewards / dones (8 bytes per env) stay in mapped memory
         r.h_obs = s_obs;
-        r.h_obs_flag = s_flag;
+        r.h_obs_flag = s_flag;  // abort only
+        r.h_sentinel = 1;
     }
     float* act_base = nullptr;  // host address of the kernel's action stores when they go straight into the caller's array
     if (direct_actions && actions_all) {
@@ -1508,6 +1510,8 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     CU(cudaLaunchCooperativeKernel((void*)rollout_persistent_kernel, dim3(c->roll_grid), dim3(R_NTH), kargs, c->roll_smem, c->stream));
     c->ctr.kernel_launches++;
     int st = PPO_OK;
+    static const bool hx_prof = getenv("PPO_HOST_ROLLOUT_PROF") != nullptr;  // host-side split of an env step: wait | env callback | hand-over
+    double prof_wait = 0.0, prof_env = 0.0, prof_push = 0.0;
     for (int t = 0; t < D.n_steps && st == PPO_OK; ++t) {
         // the CTAs' actions of step t
         const auto t0 = std::chrono::steady_clock::now();
@@ -1530,16 +1534,17 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         }
         c->ctr.d2h_bytes += N * A * sizeof(float);
         const float *o = nullptr, *rw = nullptr, *dn = nullptr;
+        const auto t1 = std::chrono::steady_clock::now();
         if (step(user, t, acts, &o, &rw, &dn) != 0 || !o || !rw || !dn) {
             st = fail(PPO_ERR_INVALID, "ppo_runner_rollout_host: the env aborted at step %d", t);
             break;
         }
+        const auto t2 = std::chrono::steady_clock::now();
         if (staged) {  // copy engine, then the flag behind the data on the same stream
             memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
             memcpy(c->hx_mem + off_done, dn, N * sizeof(float));
             __atomic_thread_fence(__ATOMIC_RELEASE);
-            if (cudaMemcpyAsync(s_obs, o, N * O * sizeof(float), cudaMemcpyHostToDevice, c->stream3) != cudaSuccess ||
-                cudaMemcpyAsync(s_flag, flag_vals + t, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream3) != cudaSuccess) {
+            if (cudaMemcpyAsync(s_obs, o, N * O * sizeof(float), cudaMemcpyHostToDevice, c->stream3) != cudaSuccess) {
                 st = fail(PPO_ERR_CUDA, "host-env rollout: H2D copy of step %d failed: %s", t, cudaGetErrorString(cudaGetLastError()));
                 break;
             }
@@ -1551,7 +1556,16 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         c->ctr.h2d_bytes += N * (O + 2) * sizeof(float);
         __atomic_thread_fence(__ATOMIC_RELEASE);
         if (!staged) *obs_flag = (unsigned)t + 1u;
+        if (hx_prof) {
+            const auto t3 = std::chrono::steady_clock::now();
+            prof_wait += std::chrono::duration<double, std::micro>(t1 - t0).count();
+            prof_env += std::chrono::duration<double, std::micro>(t2 - t1).count();
+            prof_push += std::chrono::duration<double, std::micro>(t3 - t2).count();
+        }
     }
+    if (hx_prof)
+        fprintf(stderr, "[host-env rollout] per env step: wait for the actions %.1f us | env callback %.1f us | hand the answer over %.1f us\n",
+                prof_wait / D.n_steps, prof_env / D.n_steps, prof_push / D.n_steps);
     if (staged && st == PPO_OK) {  // the env's arrays of the last step may be released when this call returns
         if (cudaStreamSynchronize(c->stream3) != cudaSuccess) st = fail(PPO_ERR_CUDA, "host-env rollout: %s", cudaGetErrorString(cudaGetLastError()));
     }
