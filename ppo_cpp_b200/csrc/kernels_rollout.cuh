@@ -65,6 +65,11 @@ struct RolloutArgs {
     // engine works in, a CTA goes on exactly when its slice has landed (and does not wait for the rest of the copy).  h_obs_flag then
     // only carries the abort.
     int h_sentinel;
+    // A single env (<= 30 observation dims): both directions as LL words in mapped memory — actions [A] and the env's answer
+    // [obs D | reward | done], each an 8-byte (value, t + 1) word.  No fence and no flag on either side, and the kernel's poll of the
+    // answer IS the read of the answer: one PCIe round trip instead of flag poll + payload read.  sequence 0xffffffff = abort.
+    uint2* h_act_ll;
+    const uint2* h_ans_ll;
     long long* prof;  // optional [32] phase timestamps of CTA 0 during env step 1 (PPO_ROLLOUT_PROF=1)
 };
 
@@ -290,7 +295,10 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                         Ac[j * (TM + 1)] = act;
                         Z2[j * TM] = __fmul_rn(z, z);
                         a.act_store[(size_t)t * A + j] = act;
-                        if (host_env) a.h_actions[(size_t)t * a.h_act_stride + j] = act;
+                        if (host_env) {
+                            if (a.h_act_ll) ll_store(a.h_act_ll + j, __float_as_uint(act), (unsigned)t + 1u);
+                            else a.h_actions[(size_t)t * a.h_act_stride + j] = act;
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) {  // neglogp (GRAPH:6103-6672): sequential sum in action order
@@ -301,7 +309,35 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                         a.dones_store[t] = DN[0];  // done flag of the previous env step (runner.hpp:110)
                     }
                     R_PROF();  // sample + stores issued
-                    if (host_env) {
+                    if (host_env && a.h_ans_ll) {
+                        // -- the env's answer: lane k polls word k (the actions left as LL words above)
+                        const unsigned want = (unsigned)t + 1u;
+                        uint2 w = make_uint2(0u, want);
+                        bool gone = false;
+                        if (lane < D + 2) {
+                            const unsigned long long t0 = globaltimer_ns();
+                            unsigned spins = 0;
+                            while (true) {
+                                w = ll_load(a.h_ans_ll + lane);
+                                if (w.y == want) break;
+                                if (w.y == PPO_HOST_ENV_ABORT) { gone = true; break; }
+                                if (((++spins) & 0xffu) == 0u && globaltimer_ns() - t0 > 120000000000ull) {  // 120 s: the host is gone
+                                    *a.host_err = 1u;
+                                    gone = true;
+                                    break;
+                                }
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, gone)) {
+                            if (lane == 0) s_abort = 1;
+                            break;
+                        }
+                        if (lane < D) RAW[lane] = __uint_as_float(w.x);
+                        else if (lane == D) REW[0] = __uint_as_float(w.x);
+                        else if (lane == D + 1) DONE[0] = __uint_as_float(w.x);
+                        __syncwarp();
+                        if (lane == 0) RET[0] = __fadd_rn(__fmul_rn(RET[0], a.norm_gamma), REW[0]);  // env_normalize.hpp:71
+                    } else if (host_env) {
                         // -- actions to the host, the env's answer back (mapped pinned memory, one flag each way)
                         __syncwarp();
                         unsigned v = 0u;

@@ -1455,7 +1455,7 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     const bool staged = host_persistent_staged(c);
     if (!c->hx_mem) {
         // [obs flag | act flags (grid) | actions N*A | obs N*O | rew N | done N | flag values 1 .. n_steps, abort], mapped + pinned
-        const size_t words = 64 + (size_t)((c->roll_grid + 63) & ~63) + N * A + N * O + 2 * N + (size_t)D.n_steps + 2;
+        const size_t words = 64 + (size_t)((c->roll_grid + 63) & ~63) + N * A + N * O + 2 * N + (size_t)D.n_steps + 2 + 4 + 2 * (A + O + 2);
         CU(cudaHostAlloc(reinterpret_cast<void**>(&c->hx_mem), words * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
         memset(c->hx_mem, 0, words * sizeof(float));
         CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hx_dev), c->hx_mem, 0));
@@ -1470,6 +1470,13 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     for (int t = 0; t < D.n_steps; ++t) flag_vals[t] = (unsigned)t + 1u;
     flag_vals[D.n_steps] = PPO_HOST_ENV_ABORT;
     flag_vals[D.n_steps + 1] = 0u;
+    // a single env: both directions as LL words (value, t + 1) in mapped memory, see RolloutArgs::h_act_ll
+    const bool solo_ll = !staged && N == 1 && O + 2 <= 32 && getenv("PPO_DISABLE_HOST_LL") == nullptr;
+    const size_t off_ll = (off_fval + (size_t)D.n_steps + 2 + 3) & ~(size_t)3;  // 16-byte aligned
+    volatile uint64_t* act_ll = reinterpret_cast<volatile uint64_t*>(c->hx_mem + off_ll);
+    volatile uint64_t* ans_ll = act_ll + A;
+    if (solo_ll)
+        for (size_t k = 0; k < A + O + 2; ++k) act_ll[k] = 0ull;  // sequence numbers restart at 1 with every rollout
     float* s_obs = c->hx_stage;
     unsigned* s_flag = staged ? reinterpret_cast<unsigned*>(c->hx_stage + N * O + 2 * N) : nullptr;
     volatile unsigned* obs_flag = reinterpret_cast<volatile unsigned*>(c->hx_mem);
@@ -1489,6 +1496,10 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
     r.h_obs = c->hx_dev + off_obs; r.h_rew = c->hx_dev + off_rew; r.h_done = c->hx_dev + off_done;
     r.h_act_flag = reinterpret_cast<unsigned*>(c->hx_dev) + off_actf;
     r.h_obs_flag = reinterpret_cast<const unsigned*>(c->hx_dev);
+    if (solo_ll) {
+        r.h_act_ll = reinterpret_cast<uint2*>(c->hx_dev + off_ll);
+        r.h_ans_ll = reinterpret_cast<const uint2*>(c->hx_dev + off_ll) + A;
+    }
     if (staged) {  // observations through the copy engine (ONE API call per step: the kernel recognises the landed sectors, see h_sentinel);
                    // rewards / dones (8 bytes per env) stay in mapped memory
         r.h_obs = s_obs;
@@ -1516,8 +1527,8 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         // the CTAs' actions of step t
         const auto t0 = std::chrono::steady_clock::now();
         unsigned spins = 0;
-        for (int b = 0; b < c->roll_grid; ++b) {
-            while (act_flag[b] != (unsigned)t + 1u) {
+        for (int b = 0; b < (solo_ll ? (int)A : c->roll_grid); ++b) {
+            while (solo_ll ? (unsigned)(act_ll[b] >> 32) != (unsigned)t + 1u : act_flag[b] != (unsigned)t + 1u) {
                 if (((++spins) & 0xfffffu) == 0u) {
                     if (cudaStreamQuery(c->stream) != cudaErrorNotReady) { st = fail(PPO_ERR_CUDA, "host-env rollout: the kernel ended at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); break; }
                     if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) { st = fail(PPO_ERR_CUDA, "host-env rollout: no actions from the device at step %d", t); break; }
@@ -1527,7 +1538,12 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         }
         if (st != PPO_OK) break;
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        const float* acts = act_base ? act_base + (size_t)t * N * A : h_act;  // the kernel's stores into mapped host memory (posted PCIe writes)
+        if (solo_ll)
+            for (size_t j = 0; j < A; ++j) {
+                const unsigned bits = (unsigned)act_ll[j];
+                memcpy(h_act + j, &bits, sizeof(float));
+            }
+        const float* acts = (act_base && !solo_ll) ? act_base + (size_t)t * N * A : h_act;  // the kernel's stores into mapped host memory (posted PCIe writes)
         if (!direct_actions) {
             memcpy(actions, acts, N * A * sizeof(float));
             acts = actions;
@@ -1548,6 +1564,17 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
                 st = fail(PPO_ERR_CUDA, "host-env rollout: H2D copy of step %d failed: %s", t, cudaGetErrorString(cudaGetLastError()));
                 break;
             }
+        } else if (solo_ll) {
+            const uint64_t seq = (uint64_t)((unsigned)t + 1u) << 32;
+            unsigned bits;
+            for (size_t k = 0; k < O; ++k) {
+                memcpy(&bits, o + k, sizeof(bits));
+                ans_ll[k] = seq | bits;  // one aligned 8-byte store: value and sequence number become visible together
+            }
+            memcpy(&bits, rw, sizeof(bits));
+            ans_ll[O] = seq | bits;
+            memcpy(&bits, dn, sizeof(bits));
+            ans_ll[O + 1] = seq | bits;
         } else {
             memcpy(c->hx_mem + off_obs, o, N * O * sizeof(float));
             memcpy(c->hx_mem + off_rew, rw, N * sizeof(float));
@@ -1573,6 +1600,8 @@ static int rollout_host_persistent(ppo_core* c, ppo_env_step_fn step, void* user
         char keep[1024];
         strncpy(keep, g_err, sizeof(keep));
         *obs_flag = PPO_HOST_ENV_ABORT;  // releases the kernel
+        if (solo_ll)
+            for (size_t k = 0; k < O + 2; ++k) ans_ll[k] = (uint64_t)PPO_HOST_ENV_ABORT << 32;
         __atomic_thread_fence(__ATOMIC_SEQ_CST);
         if (staged) {
             cudaMemcpyAsync(s_flag, flag_vals + D.n_steps, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream3);
