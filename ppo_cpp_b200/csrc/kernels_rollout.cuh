@@ -111,6 +111,56 @@ struct RLayout {
     }
 };
 
+// Forward pass of ONE env by one warp with the layer widths known at compile time (the reference's [4,5] net and the [64,64] default):
+// lane l owns output units l, l + 32, ... of [pi tower | V tower]; fully unrolled, so the loads of a chain are issued ahead of its fmaf
+// sequence (k ascending, as f_fwd).  With run-time widths the same loops took ~70 cycles per k-step.
+template <int O, int H1, int H2, int A, int TM>
+__device__ __forceinline__ void solo_forward(const float* __restrict__ sW, const NetDims& d, const float* __restrict__ OBS, float* H1p, float* H1v,
+                                             float* H2p, float* H2v, float* MU, float* Vs, int lane) {
+#pragma unroll
+    for (int i = 0; i < (2 * H1 + 31) / 32; ++i) {
+        const int o = lane + 32 * i;
+        if (o < 2 * H1) {
+            const bool vt = o >= H1;
+            const int n = vt ? o - H1 : o;
+            const float* w = sW + d.off[vt ? T_VF_FC0_W : T_PI_FC0_W] + n;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < O; ++k) acc = fmaf(w[k * H1], OBS[k * TM], acc);
+            (vt ? H1v : H1p)[n * TM] = tanhf(acc + sW[d.off[vt ? T_VF_FC0_B : T_PI_FC0_B] + n]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < (2 * H2 + 31) / 32; ++i) {
+        const int o = lane + 32 * i;
+        if (o < 2 * H2) {
+            const bool vt = o >= H2;
+            const int n = vt ? o - H2 : o;
+            const float* w = sW + d.off[vt ? T_VF_FC1_W : T_PI_FC1_W] + n;
+            const float* hin = vt ? H1v : H1p;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < H1; ++k) acc = fmaf(w[k * H2], hin[k * TM], acc);
+            (vt ? H2v : H2p)[n * TM] = tanhf(acc + sW[d.off[vt ? T_VF_FC1_B : T_PI_FC1_B] + n]);
+        }
+    }
+    __syncwarp();
+    static_assert(A + 1 <= 32, "one lane per head output");
+    if (lane < A + 1) {
+        const bool vh = lane == A;
+        const int N = vh ? 1 : A, n = vh ? 0 : lane;
+        const float* w = sW + d.off[vh ? T_VF_W : T_PI_W] + n;
+        const float* hin = vh ? H2v : H2p;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < H2; ++k) acc = fmaf(w[k * N], hin[k * TM], acc);
+        if (vh) Vs[0] = acc + sW[d.off[T_VF_B]];
+        else MU[n * TM] = acc + sW[d.off[T_PI_B] + n];
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const RolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     const NetDims& d = a.d;
@@ -252,6 +302,11 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                     // -- store the observation the policy acts on (runner.hpp:75-78)
                     for (int k = lane; k < O; k += 32) a.obs_store[(size_t)t * O + k] = OBS[k * TM];
                     // -- MlpPolicy::step, both towers: lane per output unit, k ascending as f_fwd
+                    if (O == 18 && A == 18 && nH1 == 4 && nH2 == 5) {
+                        solo_forward<18, 4, 5, 18, TM>(sW, d, OBS, H1p, H1v, H2p, H2v, MU, Vs, lane);
+                    } else if (O == 18 && A == 18 && nH1 == 64 && nH2 == 64) {
+                        solo_forward<18, 64, 64, 18, TM>(sW, d, OBS, H1p, H1v, H2p, H2v, MU, Vs, lane);
+                    } else {
                     for (int o = lane; o < 2 * nH1; o += 32) {
                         const bool vt = o >= nH1;
                         const int n = vt ? o - nH1 : o;
@@ -285,6 +340,7 @@ __global__ void __launch_bounds__(R_NTH) rollout_persistent_kernel(const Rollout
                         else MU[n * TM] = acc + sW[d.off[T_PI_B] + n];
                     }
                     __syncwarp();
+                    }
                     R_PROF();  // forward done
                     // -- Gaussian sample (GRAPH:5894-6019)
                     for (int j = lane, jj = 0; j < A; j += 32, ++jj) {
