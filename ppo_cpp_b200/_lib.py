@@ -11,7 +11,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libppo_core.so")
+# PPO_CORE_LIB: another build of the same library (A/B measurements of a kernel change on one box)
+LIB_PATH = os.environ.get("PPO_CORE_LIB") or os.path.join(HERE, "libppo_core.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ppo_core.h")
 
 PPO_HOST, PPO_DEVICE = 0, 1

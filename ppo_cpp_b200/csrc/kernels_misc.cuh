@@ -891,9 +891,14 @@ struct ReduceAdamArgs {
 
 // Body shared by the stand-alone cooperative kernel and the persistent epoch kernel (kernels_umma.cuh): `blk` of `nblk`
 // blocks of 256 threads.  b1p / b2p are the beta powers BEFORE this step.  Contains one grid barrier.
+// EXT: the 8 KB combine buffer is the caller's (16-byte aligned shared memory, `ext_part`) instead of a static array — the
+// persistent epoch kernel lends an operand block that is idle during the gradient step.
+template <bool EXT = false>
 __device__ __forceinline__ void reduce_adam_device(const ReduceAdamArgs& r, int blk, int nblk, GridBarrier& bar, unsigned seq,
-                                                   float b1p, float b2p, float* loss_row, long long* prof = nullptr, unsigned sqseq = 0u) {
-    __shared__ __align__(16) float part[RA_MAXJ][8][64];
+                                                   float b1p, float b2p, float* loss_row, long long* prof = nullptr, unsigned sqseq = 0u,
+                                                   float* ext_part = nullptr) {
+    __shared__ __align__(16) float part_static[EXT ? 1 : RA_MAXJ][8][64];
+    float (*part)[8][64] = EXT ? reinterpret_cast<float (*)[8][64]>(ext_part) : part_static;
     __shared__ double red[8];
     __shared__ double s_parts[256];
     __shared__ float s_scale;

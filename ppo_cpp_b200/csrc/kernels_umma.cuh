@@ -72,7 +72,12 @@ constexpr uint32_t OFF_F32 = OFF_ONES + ROW16_BLOCK;  // fp32 vectors
 constexpr uint32_t F32_B1 = 0, F32_BH = 64, F32_WV = 96, F32_SD = 160, F32_LS = 192, F32_MISC = 224, F32_PV = 256,
                    F32_DV = 512, F32_RED = 640, F32_ISD = 704, F32_COUNT = 736;
 constexpr uint32_t OFF_BAR = OFF_F32 + F32_COUNT * 4;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 64 + 1024;  // + alignment slack
+// Staging rows of the bulk copies (cp.async.bulk, the TMA engine) that bring the gathered observation rows of a tile in: one
+// 16-byte aligned window per sample row.  A row of O floats starts 8-byte aligned, so its window starts 0 or 8 bytes below it
+// and spans round16(4 O + 8) bytes at most (80 for O = 18).
+constexpr uint32_t OFF_STG = OFF_BAR + 64;
+constexpr uint32_t stg_row_bytes(int O) { return (uint32_t)((4 * O + 8 + 15) & ~15); }
+constexpr uint32_t SMEM_BYTES = OFF_STG + TM * stg_row_bytes(18) + 1024;  // + alignment slack; the widths instantiated are 18 / 18
 
 // ---- TMEM columns: every accumulator has a twin ("+ XC") for the small cross products
 constexpr uint32_t ACC_WORK = 0, ACC_WORK_C = 64;  // Z1, Z2, MU (first 32 columns), dH2, dH1
@@ -321,25 +326,39 @@ __device__ __forceinline__ void store_row32(uint8_t* block, int r, int half, con
     }
 }
 
-// Observation row of a sample, as the registers of the two threads (h = 0, 1) that stage it: columns [16h, 16h+16)
+// Observation rows of a tile travel global -> shared memory as bulk copies (one per gathered row, issued by the thread that owns the
+// sample, all completing on one mbarrier), so the gather of ppo2.hpp:291-307 costs no register and no LSU round trip on the
+// tile's critical path: the split into fp16 pieces reads the landed rows out of shared memory.
 template <int O>
-struct ObsRegs {
-    float2 x[8];
-    __device__ __forceinline__ void load(const float* __restrict__ obs, long grow, int h, bool valid) {
-        const float2* src = reinterpret_cast<const float2*>(obs + grow * O);  // rows are 8-byte aligned (O even)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = 16 * h + 2 * i;
-            x[i] = (valid && c < O) ? __ldg(src + (c >> 1)) : make_float2(0.f, 0.f);
+struct ObsStage {
+    static constexpr uint32_t ROW = stg_row_bytes(O);
+    // issued by the 128 threads gh == 0 (the mbarrier expects 128 arrivals per tile); rows that do not exist only arrive
+    static __device__ __forceinline__ void issue(const float* __restrict__ obs, long grow, bool valid, uint32_t stg_row, uint32_t bar) {
+        if (valid) {
+            const uint64_t addr = (uint64_t)(obs + grow * O);
+            const uint32_t off = (uint32_t)(addr & 15u);
+            const uint32_t bytes = (off + 4u * O + 15u) & ~15u;  // never past the 16-byte block that holds the row's last float
+            uint64_t st;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st) : "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stg_row),
+                         "l"(addr - off), "r"(bytes), "r"(bar)
+                         : "memory");
+        } else {
+            uint64_t st;
+            asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
         }
     }
-    // X' = [obs | 1 | 0 ...]: the ones column folds the layer-0 bias into the GEMM and yields its gradient
-    __device__ __forceinline__ void store(uint8_t* Y, int r, int h) const {
+    // X' = [obs | 1 | 0 ...] of row r, columns [16h, 16h+16): the ones column folds the layer-0 bias into the GEMM and yields its gradient
+    static __device__ __forceinline__ void store(uint8_t* Y, const uint8_t* stg, const float* __restrict__ obs, long grow, bool valid, int r, int h) {
+        const uint32_t off = (uint32_t)((uint64_t)(obs + grow * O) & 15u);
+        const float2* src = reinterpret_cast<const float2*>(stg + (uint32_t)r * ROW + off);  // rows are 8-byte aligned (O even)
         float v[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            v[2 * i] = x[i].x * (float)(1 << PW_X);
-            v[2 * i + 1] = x[i].y * (float)(1 << PW_X);
+            const int c = 16 * h + 2 * i;
+            const float2 x = (valid && c < O) ? src[c >> 1] : make_float2(0.f, 0.f);
+            v[2 * i] = x.x * (float)(1 << PW_X);
+            v[2 * i + 1] = x.y * (float)(1 << PW_X);
         }
         if (O >= 16 * h && O < 16 * h + 16) v[O - 16 * h] = (float)(1 << PW_X);
         store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h), v);
@@ -381,6 +400,7 @@ template <int O, int A, int MODE>
 __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, const EpochArgs ep) {
     constexpr bool PERSIST = MODE != 0;
     static_assert(O % 2 == 0 && O >= 2 && O <= 30 && A % 2 == 0 && A >= 2 && A <= 32, "unsupported obs/act width");
+    static_assert(OFF_STG + TM * stg_row_bytes(O) + 1024 <= SMEM_BYTES, "staging rows of this obs width do not fit SMEM_BYTES");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -398,9 +418,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     uint8_t* sH2 = smem + OFF_H2;
     uint8_t* sY = smem + OFF_Y;
     float* f32 = reinterpret_cast<float*>(smem + OFF_F32);
+    // barD: the bulk copies of a tile's observation rows (128 arrivals + their bytes);
     // barA: the GEMM the next epilogue waits for; barB: the MMAs that read [dMU | dLS] out of Y (pi tower, before X' returns
     // there); barC: everything a tile issued (weight gradients included), waited once at the tile's end
-    const uint32_t barA = sbase + OFF_BAR, barB = barA + 8, barC = barA + 16;
+    const uint32_t barA = sbase + OFF_BAR, barB = barA + 8, barC = barA + 16, barD = barA + 24;
+    const uint8_t* sStg = smem + OFF_STG;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
     uint8_t* sD2 = smem + OFF_D2;
     uint8_t* sD1 = smem + OFF_D1;
@@ -409,7 +431,6 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     // ---------------------------------------------------------------- inputs of the first tile (latency overlaps the setup)
     // Thread (gr = tid & 127, gh = tid >> 7) stages half of observation row gr; for column half 0, gr == row.
     const int gr = tid & 127, gh = tid >> 7;
-    ObsRegs<O> xin;
     long grow = 0;
     bool gvalid = false;
     float s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
@@ -427,7 +448,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         grow = gvalid ? (long)(a.gather ? __ldg(a.gather + in_s0 + gr) : (in_s0 + gr)) : 0;
     };
     auto load_rows = [&]() {
-        xin.load(a.obs, grow, gh, gvalid);
+        if (gh == 0) ObsStage<O>::issue(a.obs, grow, gvalid, sbase + OFF_STG + (uint32_t)gr * ObsStage<O>::ROW, barD);
         s_ret = s_oldn = s_oldv = s_advd = 0.f;
         if (gh == 0 && gvalid) {
             s_ret = __ldg(a.ret + grow);
@@ -441,13 +462,14 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         load_index(tile);
         load_rows();
     };
-    load_inputs(blockIdx.x);
+    load_index(blockIdx.x);  // the rows follow once the mbarrier of their bulk copies exists
 
     // ---------------------------------------------------------------- one-time setup
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barB));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barC));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barD), "n"(TM));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -510,7 +532,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     int invB_exp;
     (void)frexpf(a.invB, &invB_exp);  // invB = m * 2^e, m in [0.5, 1)
     int k_w0 = 0, k_w1 = 0, k_hd = 0, n_s = 0;
-    uint32_t phA = 0, phB = 0, phC = 0;
+    uint32_t phA = 0, phB = 0, phC = 0, phD = 0;
     float l_0, l_1, l_2, l_dbv;  // pi: pg, kl, clipfrac sums; V: vf sum, dbv (per minibatch)
     bool accw;
     float h1r[32], h2r[32];
@@ -569,6 +591,9 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 bv = LDW(P + d.off[T_VF_B]);
             }
             }
+            // first tile of the launch: bulk copies of the gathered observation rows + the per-sample scalars, behind the parameter loads
+            // (the gather index they need has been in flight since the kernel's entry; later minibatches issue theirs at barrier 1)
+            if (mb == 0) load_rows();
             // ---- block floating point: every weight matrix is stored times a power of two that brings its largest entry into
             // [1, 2) (exact in fp32; undone in the fp32 epilogues), so that both fp16 pieces of the entries that matter are
             // normal numbers whatever the scale of the matrix (the policy head starts at 1e-3, GRAPH:4843).  The same powers
@@ -665,7 +690,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         const float un_hd = pow2f(-n_s - PW_H);                               // dWpi, column sums (ones = 2^PW_H), dWv
         const float un_w1 = pow2f(-n_s - (k_hd - PW_W) - PW_H);                // dW1, db1
         const float un_w0 = pow2f(-n_s - (k_hd - PW_W) - (k_w1 - PW_W) - PW_X);  // dW0' (bias column: the ones of X' are 2^PW_X)
-        xin.store(sY, gr, gh);
+        mbar_wait(barD, phD); phD ^= 1;  // the observation rows of the first tile have landed
+        ObsStage<O>::store(sY, sStg, a.obs, grow, gvalid, gr, gh);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -926,7 +952,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         tc_fence_after();
         UMMA_PROF();
         if (more) {
-            xin.store(sY, gr, gh);
+            mbar_wait(barD, phD); phD ^= 1;
+            ObsStage<O>::store(sY, sStg, a.obs, grow, gvalid, gr, gh);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -1057,16 +1084,22 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     UMMA_PROF();
         if (PERSIST) {
             // slabs complete -> reduce (+ allreduce) -> global norm -> Adam -> parameters visible to every CTA
-            if (mb + 1 < n_mb) load_rows();  // next minibatch's first tile (index issued before the flush): lands during the barriers
             tc_fence_before();  // orders this minibatch's tcgen05.ld before the next minibatch's MMAs (barriers below)
             UMMA_TL(3);  // flushed
-            bar.sync();
+            bar.arrive();
+            // next minibatch's first tile (index issued before the flush): 128 bulk copies are ~0.3 us of issue, so they go out
+            // after this CTA's arrival at the barrier, while the others still come in, and land during the gradient step
+            if (mb + 1 < n_mb) load_rows();
+            bar.wait();
             UMMA_PROF();  // barrier 1 passed
             UMMA_TL(4);
             ++mseq;
-            reduce_adam_device(ep.ra, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), bar, mseq, b1p, b2p,
-                               ep.loss_rows + (size_t)mb * 5,
-                               (a.prof && blockIdx.x == 0 && mb == 2) ? a.prof + 160 + tower * 8 : nullptr, ++sqseq);
+            // (the combine buffer of the gradient step is the H1 block: every MMA that read it has completed, the next writer is the
+            // H1 epilogue of the next minibatch, two grid barriers away)
+            reduce_adam_device<true>(ep.ra, (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(2 * gridDim.x), bar, mseq, b1p, b2p,
+                                     ep.loss_rows + (size_t)mb * 5,
+                                     (a.prof && blockIdx.x == 0 && mb == 2) ? a.prof + 160 + tower * 8 : nullptr, ++sqseq,
+                                     reinterpret_cast<float*>(sH1));
             b1p = __fmul_rn(b1p, ep.ra.adam.beta1);
             b2p = __fmul_rn(b2p, ep.ra.adam.beta2);
             UMMA_PROF();  // reduce + partials + Adam done
