@@ -211,10 +211,33 @@ __global__ void norm_moments_kernel(const MomentsArgs a) {
     __syncthreads();
     if (!last) return;
     __threadfence();
-    for (int c = tid; c < 2 * (D + 1); c += nth) {
-        double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += a.partial[(size_t)b * 2 * (D + 1) + c];
-        colsum[c] = t;
+    // the last block adds the per-block partials in a fixed order: G threads per column take interleaved blocks (loads batched eight
+    // deep), then the G sums are added in order.  (One thread per column walking all blocks was a chain of 296 dependent L2 round
+    // trips: 59 k of the kernel's 66 k cycles at 65 536 envs — profiles/r2_small_kernels_ncu.txt.)
+    {
+        const int W2 = 2 * (D + 1);
+        const int G = max(1, min(nth / W2, 8));
+        double* gp = sm;  // [G][W2] <= [nth][2]
+        if (tid < G * W2) {
+            const int g = tid / W2, c = tid - g * W2;
+            double t = 0.0;
+            unsigned b = (unsigned)g;
+            for (; b + 7u * G < gridDim.x; b += 8u * G) {
+                double v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldcg(a.partial + (size_t)(b + i * G) * W2 + c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t += v[i];
+            }
+            for (; b < gridDim.x; b += G) t += __ldcg(a.partial + (size_t)b * W2 + c);
+            gp[tid] = t;
+        }
+        __syncthreads();
+        for (int c = tid; c < W2; c += nth) {
+            double t = 0.0;
+            for (int g = 0; g < G; ++g) t += gp[g * W2 + c];
+            colsum[c] = t;
+        }
     }
     __syncthreads();
     for (int c = tid; c < D; c += nth) {

@@ -294,6 +294,134 @@ __global__ void __launch_bounds__(NTH) train_small_kernel(const TrainArgs a) {
     }
 }
 
+// Policy step of the S family (MlpPolicy::step / value / deterministic action, policies.hpp:33-77): one THREAD per env, parameters in
+// shared memory (LDS.128 broadcasts), the env's observation row in registers, the same accumulation order as the tile kernels
+// (k ascending from 0, bias added last, tanhf) so that actions / values / neglogp are bit-identical to every other forward path.
+// Observation rows come in and action rows go out through a shared-memory tile, so global accesses are contiguous per warp.
+// (policy_tile_kernel, which served this net before, spends 12 M warp instructions on 65 536 envs: 4x4 register tiles over layers
+// that are 4 and 5 wide leave most threads of a phase idle — 37 us per step against 7; profiles/r2_small_kernels_ncu.txt.)
+template <int O, int A, int H1, int H2>
+__global__ void __launch_bounds__(NTH) policy_small_kernel(const PolicyArgs a) {
+    using D = Dims<O, A, H1, H2>;
+    constexpr int XL = O + 1 + ((O + 1) % 2 == 0 ? 1 : 0);  // odd row strides: a lane reading its own row hits its own bank
+    constexpr int AL = A + 1 + ((A + 1) % 2 == 0 ? 1 : 0);
+    __shared__ __align__(16) float sW[(D::P + 3 + 4) & ~3];
+    __shared__ float sX[NTH * XL];
+    __shared__ float sA[NTH * AL];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < D::P; i += NTH) sW[i] = __ldg(a.params + i);
+    const int ntiles = (a.n + NTH - 1) / NTH;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * NTH, nv = min(NTH, a.n - r0);
+        __syncthreads();  // parameters staged (first tile) / previous tile's action rows written out
+        {
+            const float* src = a.obs + (size_t)r0 * O;
+            float* dst = a.obs_store ? a.obs_store + (size_t)r0 * O : nullptr;
+            for (int e = tid; e < nv * O; e += NTH) {
+                const float x = src[e];
+                sX[(e / O) * XL + (e % O)] = x;
+                if (dst) dst[e] = x;
+            }
+        }
+        __syncthreads();
+        if (tid < nv) {
+            const int row = r0 + tid;
+            float x[O];
+#pragma unroll
+            for (int k = 0; k < O; ++k) x[k] = sX[tid * XL + k];
+            float mu[A];
+            if (a.mode != 1) {
+                float h1[H1], h2[H2];
+#pragma unroll
+                for (int n = 0; n < H1; ++n) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < O; ++k) s = fmaf(sW[D::PI0W + k * H1 + n], x[k], s);
+                    h1[n] = tanhf(s + sW[D::PI0B + n]);
+                }
+#pragma unroll
+                for (int n = 0; n < H2; ++n) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < H1; ++k) s = fmaf(sW[D::PI1W + k * H2 + n], h1[k], s);
+                    h2[n] = tanhf(s + sW[D::PI1B + n]);
+                }
+#pragma unroll
+                for (int j = 0; j < A; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < H2; ++k) s = fmaf(sW[D::PIW + k * A + j], h2[k], s);
+                    mu[j] = s + sW[D::PIB + j];
+                }
+            }
+            if (a.mode != 2) {
+                float g1[H1], g2[H2];
+#pragma unroll
+                for (int n = 0; n < H1; ++n) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < O; ++k) s = fmaf(sW[D::VF0W + k * H1 + n], x[k], s);
+                    g1[n] = tanhf(s + sW[D::VF0B + n]);
+                }
+#pragma unroll
+                for (int n = 0; n < H2; ++n) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < H1; ++k) s = fmaf(sW[D::VF1W + k * H2 + n], g1[k], s);
+                    g2[n] = tanhf(s + sW[D::VF1B + n]);
+                }
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < H2; ++k) v = fmaf(sW[D::VFW + k], g2[k], v);
+                v += sW[D::VFB];
+                if (a.value) a.value[row] = v;
+                if (a.val_store) a.val_store[row] = v;
+            }
+            if (a.mode == 0) {
+                const uint32_t step = a.eps ? 0u : *a.step_ctr;
+                float ss = 0.f, sl = 0.f;
+#pragma unroll
+                for (int j0 = 0; j0 < A; j0 += 4) {
+                    float e4[4];
+                    if (!a.eps) normal4(a.seed, a.env_id0 + (uint32_t)row, step, (uint32_t)(j0 >> 2), PPO_TAG_ACTION, e4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = j0 + q;
+                        if (j < A) {
+                            const float ls = sW[D::LS + j];
+                            const float sd = expf(ls);  // logstd_b = mean*0 + logstd; std = exp (GRAPH:5098-5779)
+                            const float e = a.eps ? a.eps[(size_t)row * A + j] : e4[q];
+                            const float act = __fadd_rn(mu[j], __fmul_rn(sd, e));  // GRAPH:5992-6019
+                            const float z = __fdiv_rn(__fsub_rn(act, mu[j]), sd);
+                            ss = __fadd_rn(ss, __fmul_rn(z, z));
+                            sl = __fadd_rn(sl, ls);
+                            sA[tid * AL + j] = act;
+                        }
+                    }
+                }
+                // 0.5*sum(z^2) + 0.5*log(2pi)*float(A) + sum(logstd)   (GRAPH:6103-6672)
+                const float nl = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, ss), __fmul_rn(PPO_HALF_LOG_2PI, (float)A)), sl);
+                if (a.neglogp) a.neglogp[row] = nl;
+                if (a.nlp_store) a.nlp_store[row] = nl;
+            } else if (a.mode == 2) {
+#pragma unroll
+                for (int j = 0; j < A; ++j) sA[tid * AL + j] = mu[j];  // mean + 0.0 (GRAPH:6046-6076)
+            }
+            if (a.dones_store) a.dones_store[row] = a.dones_in[row];
+        }
+        __syncthreads();
+        if (a.mode != 1) {
+            float* o1 = a.action ? a.action + (size_t)r0 * A : nullptr;
+            float* o2 = a.act_store ? a.act_store + (size_t)r0 * A : nullptr;
+            for (int e = tid; e < nv * A; e += NTH) {
+                const float act = sA[(e / A) * AL + (e % A)];
+                if (o1) o1[e] = act;
+                if (o2) o2[e] = act;
+            }
+        }
+    }
+}
+
 // Epoch kernel of the S family for minibatches that ONE CTA handles (the reference's own C1 shape: 2048 transitions in 32
 // minibatches of 64): all minibatches of an epoch in one launch of one CTA — parameters and Adam moments live in shared memory,
 // per minibatch: warp tiles -> fixed-order combine of the warps -> sum of squares -> clip -> TF ApplyAdam in place -> next

@@ -919,6 +919,13 @@ static int launch_policy(ppo_core* c, PolicyArgs& a) {
     a.env_id0 = (uint32_t)c->desc.env_offset;
     a.step_ctr = c->step_ctr;
     if (c->wide && a.n >= WIDE_POLICY_MIN) return launch_wide_policy(c, a);
+    if (c->small) {  // thread per env
+        const int ntiles = (a.n + small::NTH - 1) / small::NTH;
+        const int grid = std::max(1, std::min(ntiles, c->sm_count * 8));
+        LAUNCH(c, (small::policy_small_kernel<18, 18, 4, 5>), grid, small::NTH, 0, a);
+        CU(cudaGetLastError());
+        return PPO_OK;
+    }
     if (c->fused) {
         const int ntiles = (a.n + F_TM_POLICY - 1) / F_TM_POLICY;
         const int grid = std::max(1, std::min(ntiles, c->sm_count * 2));
@@ -2528,6 +2535,7 @@ extern "C" const char* ppo_core_kernel_family(ppo_core* c, const char* which) {
     if (w == "rollout") return (c->persistent_rollout && fast_path(c)) ? "rollout_persistent_kernel (one cooperative launch per rollout)" : "per-step kernels";
     if (w == "policy") {
         if (c->wide && c->desc.n_envs >= WIDE_POLICY_MIN) return "wgemm_kernel forward (tcgen05, split-bf16 operand images) + wide_policy_head_kernel";
+        if (c->small) return "policy_small_kernel (thread per env, fp32 FFMA in registers, parameters in shared memory)";
         if (c->fused) return "policy_fused_kernel (fp32 FFMA, weights staged in shared memory)";
         return "policy_tile_kernel (fp32 FFMA, generic hidden sizes)";
     }
