@@ -558,6 +558,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             const float* B0 = P + d.off[tower ? T_VF_FC0_B : T_PI_FC0_B];
             float4 w1v[2][2], w0v[2];
             float wpv[8];
+            constexpr int WPI_LD = (HID * A + NTH - 1) / NTH;
+            float wpf[WPI_LD];
             float b1 = 0.f, wv = 0.f, ls = 0.f, bh = 0.f, bv = 0.f;
             {
     #pragma unroll
@@ -575,11 +577,25 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             }
     #pragma unroll
             for (int k = 0; k < 8; ++k) wpv[k] = 0.f;
-            if (tower == 0) {  // Wpi [64 x A] -> chunks 0..3 of every row (columns >= A zero): 256 tasks
-                const int r = tid >> 2, j = tid & 3;
-                const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
+            // Wpi [64 x A].  Persistent kernel: read as the flat run of 64 A floats it is (thread t takes t, t + 256, ...: a warp
+            // instruction is 128 contiguous bytes) and dealt out through shared memory behind the maxima's barrier.  Each thread
+            // fetching the 8 columns of its own chunk with scalar loads (the rows are only 4-byte aligned: the tensor starts at an
+            // odd offset) is 8 L2 requests per sector from every one of the 64 pi CTAs at the same moment right after a grid
+            // barrier: the parameters of the pi tower arrived 1.4 k cycles after those of the V tower (C3 train phase 6.44 ->
+            // 6.14 ms).  The stand-alone kernel keeps the per-chunk loads: there the flat variant measured 16.4 us against 15.0.
+            if (tower == 0) {
+                if (PERSIST) {
     #pragma unroll
-                for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? LDW(src + k) : 0.f;
+                    for (int i = 0; i < WPI_LD; ++i) {
+                        const int e = tid + NTH * i;
+                        wpf[i] = e < HID * A ? LDW(P + d.off[T_PI_W] + e) : 0.f;
+                    }
+                } else {
+                    const int r = tid >> 2, j = tid & 3;
+                    const float* src = P + d.off[T_PI_W] + r * A + 8 * j;
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? LDW(src + k) : 0.f;
+                }
             }
             if (tid < HID) {
                 b1 = LDW(P + d.off[tower ? T_VF_FC1_B : T_PI_FC1_B] + tid);
@@ -594,6 +610,12 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
             // first tile of the launch: bulk copies of the gathered observation rows + the per-sample scalars, behind the parameter loads
             // (the gather index they need has been in flight since the kernel's entry; later minibatches issue theirs at barrier 1)
             if (mb == 0) load_rows();
+            float* xw = reinterpret_cast<float*>(sD2);  // the idle dP2 block is the exchange buffer of Wpi (read back behind the maxima's barrier)
+            if (PERSIST && tower == 0) {
+    #pragma unroll
+                for (int i = 0; i < WPI_LD; ++i)
+                    if (tid + NTH * i < HID * A) xw[tid + NTH * i] = wpf[i];
+            }
             // ---- block floating point: every weight matrix is stored times a power of two that brings its largest entry into
             // [1, 2) (exact in fp32; undone in the fp32 epilogues), so that both fp16 pieces of the entries that matter are
             // normal numbers whatever the scale of the matrix (the policy head starts at 1e-3, GRAPH:4843).  The same powers
@@ -608,8 +630,13 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                     for (int h = 0; h < 2; ++h)
                         mx[1] = fmaxf(mx[1], fmaxf(fmaxf(fabsf(w1v[i][h].x), fabsf(w1v[i][h].y)), fmaxf(fabsf(w1v[i][h].z), fabsf(w1v[i][h].w))));
                 if (tower == 0) {
+                    if (PERSIST) {
     #pragma unroll
-                    for (int k = 0; k < 8; ++k) mx[2] = fmaxf(mx[2], fabsf(wpv[k]));
+                        for (int i = 0; i < WPI_LD; ++i) mx[2] = fmaxf(mx[2], fabsf(wpf[i]));  // (entries past the tensor's end are 0)
+                    } else {
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k) mx[2] = fmaxf(mx[2], fabsf(wpv[k]));
+                    }
                 } else if (tid < HID) {
                     mx[2] = fabsf(wv);
                 }
@@ -624,6 +651,11 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 }
                 __syncthreads();
                 UMMA_PROF();  // parameters arrived, maxima exchanged
+                if (PERSIST && tower == 0) {  // Wpi -> chunks 0..3 of every row (columns >= A zero): 256 tasks
+                    const int r = tid >> 2, j = tid & 3;
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) wpv[k] = (8 * j + k < A) ? xw[r * A + 8 * j + k] : 0.f;
+                }
     #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float m = f32[F32_RED + k];
