@@ -313,7 +313,7 @@ def run_ours(args):
     if wide:  # dense-GEMM regime: algorithmic fp32 FLOPs against the measured bf16 tensor peak
         roofline = {"bound": "tensor", "achieved": ach_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak,
                     "peak_source": src + " bf16_tflops (burst)",
-                    "note": "fp32 parity costs 6 bf16 MMAs per fp32 MAC (bf16x3 split), so frac <= 1/6 on this pipe" if on_tensor
+                    "note": "fp32 parity costs 3 fp16 MMAs per fp32 MAC (fp16x2 split: hi*hi, hi*lo, lo*hi), so frac <= 1/3 on this pipe; the kernel is a latency chain (one 128-sample tile per CTA, 13 dependent GEMM -> epilogue phases), not a throughput problem: DESIGN.md 3.3" if on_tensor
                     else "runs on the fp32 FFMA pipe (nominal 74.4 TFLOP/s)"}
     else:  # tiny nets: 160 B per sample against the measured HBM copy bandwidth
         roofline = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,

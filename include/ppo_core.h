@@ -96,7 +96,12 @@ int ppo_core_init_orthogonal(ppo_core *core, uint64_t seed);
 /* TF Saver V2 bundle written by PPO2::save (ppo2.hpp:107-131): `<prefix>.data-00000-of-00001` holds the 15
  * model tensors as raw fp32 in sorted-name order.  load() restores weights only — Adam restarts (ppo2.hpp:169-223). */
 int ppo_core_load_checkpoint_data(ppo_core *core, const char *prefix);
+/* writes `<prefix>.data-00000-of-00001` and `<prefix>.index` (the bundle's table of name -> dtype / shape / offset / size / crc32c),
+ * so the reference's PPO2::load (ppo2.hpp:169-189, `save/restore_all`) and TensorFlow read the checkpoint back */
 int ppo_core_save_checkpoint_data(ppo_core *core, const char *prefix);
+/* the `.index` alone, for a `.data` payload held by the caller (the 15 tensors of an MLP [hidden1, hidden2] policy in ascending name
+ * order, n_floats values); no device needed.  Byte-identical to TensorFlow 1.14's BundleWriter on the reference's shipped checkpoint. */
+int ppo_checkpoint_write_index(const char *prefix, int obs_dim, int act_dim, int hidden1, int hidden2, const float *data, size_t n_floats);
 
 /* tensors by TF variable name: "model/pi_fc0/w" ... "model/q/b"; Adam slots "<name>/Adam", "<name>/Adam_1";
  * "beta1_power", "beta2_power"; "params" = the whole flat vector (n_params_total). Host buffers. */

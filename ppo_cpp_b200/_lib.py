@@ -81,6 +81,7 @@ def load():
         "ppo_core_init_orthogonal": ([core, C.c_uint64], C.c_int),
         "ppo_core_load_checkpoint_data": ([core, C.c_char_p], C.c_int),
         "ppo_core_save_checkpoint_data": ([core, C.c_char_p], C.c_int),
+        "ppo_checkpoint_write_index": ([C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_size_t], C.c_int),
         "ppo_core_num_tensors": ([], C.c_int),
         "ppo_core_tensor_name": ([C.c_int], C.c_char_p),
         "ppo_core_tensor_size": ([core, C.c_char_p], C.c_int),

@@ -906,7 +906,9 @@ extern "C" int ppo_core_save_checkpoint_data(ppo_core* c, const char* prefix) {
     if (!f) return fail(PPO_ERR_IO, "cannot open %s for writing", path.c_str());
     const size_t put = fwrite(raw.data(), sizeof(float), raw.size(), f);
     fclose(f);
-    return put == raw.size() ? PPO_OK : fail(PPO_ERR_IO, "short write to %s", path.c_str());
+    if (put != raw.size()) return fail(PPO_ERR_IO, "short write to %s", path.c_str());
+    const int st = ppo_checkpoint_write_index(prefix, c->d.O, c->d.A, c->d.H1, c->d.H2, raw.data(), raw.size());
+    return st == PPO_OK ? PPO_OK : fail(st, "cannot write %s.index", prefix);
 }
 
 // ------------------------------------------------------------------------------------------------ policy

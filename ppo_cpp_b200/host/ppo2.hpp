@@ -114,7 +114,7 @@ public:
 
     void save(std::string save_path, int save_id = -1) {
         if (save_id >= 0) save_path += "." + std::to_string(save_id);
-        // weights: TF Saver V2 data file layout (15 model tensors, sorted names, raw fp32)
+        // weights: TF Saver V2 bundle (<path>.data-00000-of-00001: 15 model tensors, sorted names, raw fp32; <path>.index: its table)
         ppo_check(ppo_core_save_checkpoint_data(core_.get(), save_path.c_str()), "Error saving checkpoint");
         std::cout << "Success save weights !! " << "\n";
         nlohmann::json json{};

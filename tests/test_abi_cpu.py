@@ -85,6 +85,82 @@ def test_meta_parse_errors():
     assert b"cannot open" in lib.ppo_last_error()
 
 
+def _parse_bundle_index(buf):
+    """Independent reader of a Saver-V2 `.index` (LevelDB table, one data block): {key: BundleEntryProto fields}."""
+    def varint(b, i):
+        v = s = 0
+        while True:
+            c = b[i]; i += 1
+            v |= (c & 0x7F) << s; s += 7
+            if c < 0x80:
+                return v, i
+    assert buf[-8:] == (0xdb4775248b80fb57).to_bytes(8, "little")
+    foot = buf[-48:]
+    _, i = varint(foot, 0); _, i = varint(foot, i)          # meta-index handle
+    ioff, i = varint(foot, i); isz, i = varint(foot, i)      # index handle
+    iblk = buf[ioff:ioff + isz]
+    _, j = varint(iblk, 0); kl, j = varint(iblk, j); vl, j = varint(iblk, j)
+    doff, k = varint(iblk, j + kl); dsz, k = varint(iblk, k)
+    blk = buf[doff:doff + dsz]
+    nrest = int.from_bytes(blk[-4:], "little")
+    end = len(blk) - 4 - 4 * nrest
+    out, key, i = {}, b"", 0
+    while i < end:
+        sh, i = varint(blk, i); un, i = varint(blk, i); vl, i = varint(blk, i)
+        key = key[:sh] + blk[i:i + un]; i += un
+        val = blk[i:i + vl]; i += vl
+        f, j = {"shape": []}, 0
+        while j < len(val):
+            tag = val[j]; j += 1
+            if tag == 0x35:
+                f["crc"] = int.from_bytes(val[j:j + 4], "little"); j += 4
+            elif tag in (0x12, 0x1a):
+                ln, j = varint(val, j); sub = val[j:j + ln]; j += ln
+                q = 0
+                while tag == 0x12 and q < len(sub):  # TensorShapeProto.dim { size }
+                    assert sub[q] == 0x12
+                    dl, q = varint(sub, q + 1)
+                    assert sub[q] == 0x08
+                    f["shape"].append(varint(sub, q + 1)[0]); q += dl
+            else:
+                v, j = varint(val, j)
+                f[{0x08: "dtype", 0x20: "offset", 0x28: "size"}[tag]] = v
+        out[key.decode()] = f
+    return out
+
+
+def test_checkpoint_index_is_tensorflows(tmp_path):
+    """The `.index` we write for the reference's shipped checkpoint is TensorFlow's own file, byte for byte
+    (resources/ppo_cl/2019-08-20_21_13_01_2859_0.pkl.71.index, copied to tests/golden/ckpt_71.index), and an independent reader
+    finds the 15 tensors with the offsets of the `.data` file; other widths parse with consistent offsets / sizes."""
+    import numpy as np
+    lib = _lib.load()
+    ck = np.load(os.path.join(os.path.dirname(__file__), "golden", "ckpt_71_weights.npz"))
+    names = sorted(k.replace("__", "/") for k in ck.files)
+    payload = np.concatenate([ck[n.replace("/", "__")].astype(np.float32).ravel() for n in names])
+    fp = payload.ctypes.data_as(C.POINTER(C.c_float))
+    assert lib.ppo_checkpoint_write_index(str(tmp_path / "a").encode(), 18, 18, 4, 5, fp, payload.size) == 0
+    got = open(tmp_path / "a.index", "rb").read()
+    want = open(os.path.join(os.path.dirname(__file__), "golden", "ckpt_71.index"), "rb").read()
+    assert got == want
+    ent = _parse_bundle_index(got)
+    assert list(ent)[0] == "" and list(ent)[1:] == names
+    off = 0
+    for n in names:
+        e = ent[n]
+        assert e["dtype"] == 1 and tuple(e["shape"]) == ck[n.replace("/", "__")].shape
+        assert e.get("offset", 0) == off and e["size"] == 4 * ck[n.replace("/", "__")].size
+        off += e["size"]
+    assert off == 1768
+    # a [64,64] policy on (36, 18): several restart-free entries with multi-byte varints
+    big = np.arange(36 * 64 * 2 + 64 * 64 * 2 + 64 * 4 + 64 * 18 * 2 + 18 * 3 + 64 + 1, dtype=np.float32)
+    assert lib.ppo_checkpoint_write_index(str(tmp_path / "b").encode(), 36, 18, 64, 64, big.ctypes.data_as(C.POINTER(C.c_float)), big.size) == 0
+    ent = _parse_bundle_index(open(tmp_path / "b.index", "rb").read())
+    assert ent["model/pi_fc0/w"]["shape"] == [36, 64] and ent["model/vf/w"]["shape"] == [64, 1]
+    assert sum(e["size"] for k, e in ent.items() if k) == 4 * big.size
+    assert lib.ppo_checkpoint_write_index(str(tmp_path / "c").encode(), 36, 18, 64, 64, fp, payload.size) == -1  # wrong payload size
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -976,6 +976,8 @@ def test_graph_and_checkpoint_io(core_mod, init_weights, ckpt_weights, tmp_path)
     assert np.array_equal(c.get_tensor("params"), ckflat)
     c.save_checkpoint_data(str(tmp_path / "again"))
     assert open(prefix + ".data-00000-of-00001", "rb").read() == open(str(tmp_path / "again") + ".data-00000-of-00001", "rb").read()
+    # ... and the bundle's .index is the file TensorFlow wrote for this checkpoint (the reference's shipped *.pkl.71.index)
+    assert open(str(tmp_path / "again") + ".index", "rb").read() == open(os.path.join(os.path.dirname(__file__), "golden", "ckpt_71.index"), "rb").read()
     with pytest.raises(core_mod.PPOError):
         c.load_meta_txt(str(tmp_path / "missing.meta.txt"))
     c.close()

@@ -81,6 +81,7 @@ def test_cli_flags_and_csv_line(tmp_path):
     names = sorted(os.listdir(ck))
     assert "t0.pkl.0.json" in names and "t0.pkl.1.json" in names and "t0.pkl.0.data-00000-of-00001" in names
     assert os.path.getsize(ck / "t0.pkl.0.data-00000-of-00001") == 1768  # 442 fp32, as the reference's checkpoint
+    assert os.path.getsize(ck / "t0.pkl.0.index") == 498  # the bundle's table, the size of the reference's own *.pkl.71.index
     tb = tmp_path / "exp" / "tensorboard" / "t0"
     assert any(f.startswith("PPO2.out.tfevents.") for f in os.listdir(tb)), os.listdir(tb)  # TensorboardWriter (ppo2.hpp:248)
     # playback of the saved checkpoint (-p): restores weights + normaliser statistics, no training
