@@ -23,6 +23,10 @@
 //     over the 128 samples of the tile).  The back-propagated dP2 / dP1 have their own blocks, so the weight-gradient
 //     GEMMs (which still read H2 / H1) never sit on the tile's critical path: they run on the tensor pipe while the CUDA
 //     cores do the next epilogue, and one commit at the end of the tile collects them.
+//   * the gathered observation rows of a tile (the minibatch slice of ppo2.hpp:291-307, 72 bytes each at a shuffled row index) come in
+//     through the TMA engine: one cp.async.bulk per row into a shared-memory staging row (a 16-byte aligned 80-byte window around the
+//     row), all 128 completing on one mbarrier; the persistent kernel issues them behind its arrival at the grid barrier of the previous
+//     minibatch, so they land during the gradient step, and the fp16 split reads them out of shared memory.
 //   * bias gradients and the logstd gradient are column sums over samples: one extra N=8 MMA against a block whose
 //     first row is ones.  The V head (N = 1) is a dot product in the epilogue; its weight gradient is again an N=8 MMA.
 //   * weight gradients accumulate in TMEM across the tiles a CTA processes and are written once to the CTA's slab.
