@@ -352,17 +352,25 @@ struct ObsStage {
             asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
         }
     }
-    // X' = [obs | 1 | 0 ...] of row r, columns [16h, 16h+16): the ones column folds the layer-0 bias into the GEMM and yields its gradient
-    static __device__ __forceinline__ void store(uint8_t* Y, const uint8_t* stg, const float* __restrict__ obs, long grow, bool valid, int r, int h) {
+    // the landed row of this thread (columns [16h, 16h+16)) -> registers: kept apart from the split so that the compiler can weave the
+    // split into whatever runs between the two (the weight blocks: with the wait and the split in one piece behind them it was 1.2 k cycles)
+    float2 x[8];
+    __device__ __forceinline__ void load(const uint8_t* stg, const float* __restrict__ obs, long grow, bool valid, int r, int h) {
         const uint32_t off = (uint32_t)((uint64_t)(obs + grow * O) & 15u);
         const float2* src = reinterpret_cast<const float2*>(stg + (uint32_t)r * ROW + off);  // rows are 8-byte aligned (O even)
-        float v[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = 16 * h + 2 * i;
-            const float2 x = (valid && c < O) ? src[c >> 1] : make_float2(0.f, 0.f);
-            v[2 * i] = x.x * (float)(1 << PW_X);
-            v[2 * i + 1] = x.y * (float)(1 << PW_X);
+            x[i] = (valid && c < O) ? src[c >> 1] : make_float2(0.f, 0.f);
+        }
+    }
+    // X' = [obs | 1 | 0 ...] of row r, columns [16h, 16h+16): the ones column folds the layer-0 bias into the GEMM and yields its gradient
+    __device__ __forceinline__ void store(uint8_t* Y, int r, int h) const {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[2 * i] = x[i].x * (float)(1 << PW_X);
+            v[2 * i + 1] = x[i].y * (float)(1 << PW_X);
         }
         if (O >= 16 * h && O < 16 * h + 16) v[O - 16 * h] = (float)(1 << PW_X);
         store_chunk(Y, ACT_PIECE, chunk_off(r, 2 * h), v);
@@ -435,6 +443,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
     // ---------------------------------------------------------------- inputs of the first tile (latency overlaps the setup)
     // Thread (gr = tid & 127, gh = tid >> 7) stages half of observation row gr; for column half 0, gr == row.
     const int gr = tid & 127, gh = tid >> 7;
+    ObsStage<O> xin;
     long grow = 0;
     bool gvalid = false;
     float s_ret = 0.f, s_oldn = 0.f, s_oldv = 0.f;  // per-sample scalars (threads of column half 0)
@@ -655,6 +664,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
                 }
                 __syncthreads();
                 UMMA_PROF();  // parameters arrived, maxima exchanged
+                mbar_wait(barD, phD); phD ^= 1;  // the observation rows of the first tile have landed (persistent kernel: a gradient step ago)
+                xin.load(sStg, a.obs, grow, gvalid, gr, gh);
                 if (PERSIST && tower == 0) {  // Wpi -> chunks 0..3 of every row (columns >= A zero): 256 tasks
                     const int r = tid >> 2, j = tid & 3;
     #pragma unroll
@@ -726,8 +737,7 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         const float un_hd = pow2f(-n_s - PW_H);                               // dWpi, column sums (ones = 2^PW_H), dWv
         const float un_w1 = pow2f(-n_s - (k_hd - PW_W) - PW_H);                // dW1, db1
         const float un_w0 = pow2f(-n_s - (k_hd - PW_W) - (k_w1 - PW_W) - PW_X);  // dW0' (bias column: the ones of X' are 2^PW_X)
-        mbar_wait(barD, phD); phD ^= 1;  // the observation rows of the first tile have landed
-        ObsStage<O>::store(sY, sStg, a.obs, grow, gvalid, gr, gh);
+        xin.store(sY, gr, gh);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -989,7 +999,8 @@ __global__ void __launch_bounds__(NTH, 1) train_umma_kernel(const TrainArgs a, c
         UMMA_PROF();
         if (more) {
             mbar_wait(barD, phD); phD ^= 1;
-            ObsStage<O>::store(sY, sStg, a.obs, grow, gvalid, gr, gh);
+            xin.load(sStg, a.obs, grow, gvalid, gr, gh);
+            xin.store(sY, gr, gh);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
